@@ -1,0 +1,312 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+TEST INFRASTRUCTURE.  Run in the build container only (the reference does not exist on the GPU
+box):   python oracle/make_golden.py
+The committed fixtures are what pins ``oracle/sseg_oracle.py`` (tests/test_oracle_golden.py) and,
+on the GPU box, the CUDA engine (tests/test_gpu_*.py).
+
+Harness = SURVEY.md section 8(c): four monkeypatches so the reference's ``_train`` bodies run
+without a GPU (``Tensor.cuda``/``Module.cuda`` -> identity, ``torch.cuda.device_count`` -> 1,
+``model_zoo.load_url`` -> {}), args built through the reference's own parser, and a Python list
+of (inp, gt) tuples standing in for the DataLoader.  Model weights are NOT taken from the
+reference's RNG: ``oracle.sseg_oracle.init_deeplabv2(seed)`` state is loaded into the reference
+modules, so tests can rebuild identical weights without shipping 176 MB.
+"""
+import os
+import sys
+import collections
+import random
+
+import numpy as np
+import torch
+
+REF = '/root/reference'
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(ROOT, 'tests', 'golden')
+sys.path.insert(0, ROOT)
+
+from oracle import sseg_oracle as O  # noqa: E402
+
+
+def patch_and_import():
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    torch.cuda.device_count = lambda: 1
+    import torch.utils.model_zoo as mz
+    mz.load_url = lambda *a, **k: {}
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(REF, 'task', 'sseg'))
+    import logging
+    import pixelssl
+    logging.getLogger('PixelSSL').setLevel(logging.ERROR)
+    import proxy as sseg_proxy
+    return pixelssl, sseg_proxy
+
+
+def make_args(pixelssl, sseg_proxy, algorithm, extra, batch, ubs, epochs=2, iters_per_epoch=5):
+    from pixelssl import runner
+    from pixelssl.utils import cmd
+    cfg = collections.OrderedDict([
+        ('exp_id', 'golden'), ('ssl_algorithm', algorithm),
+        ('models', {'model': 'deeplabv2'}), ('optimizers', {'model': 'sgd'}),
+        ('lrers', {'model': 'polynomiallr'}), ('criterions', {'model': 'sseg_criterion'}),
+        ('lr', 0.00025), ('momentum', 0.9), ('weight_decay', 0.0005),
+        ('output_stride', 16), ('backbone', 'resnet101'),
+        ('epochs', epochs), ('batch_size', batch), ('unlabeled_batch_size', ubs),
+        ('log_freq', 1000), ('visualize', False), ('im_size', 97),
+    ])
+    cfg.update(extra)
+    parser = runner.create_parser(algorithm)
+    sseg_proxy.add_parser_arguments(parser)
+    args = cmd.parse_args(parser, cfg)
+    # the fields TaskProxy autosets (task_template/proxy.py:63-71,195,239,252-268,414)
+    args.gpus = 1
+    args.task = 'sseg'
+    args.labeled_batch_size = batch - ubs
+    args.iters_per_epoch = iters_per_epoch
+    args.is_epoch_lrer = False
+    return args
+
+
+def build_algorithm(pixelssl, args, algorithm):
+    import model as sseg_model
+    import criterion as sseg_criterion
+    import func as sseg_func
+    from pixelssl.nn import optimizer, lrer
+    alg = pixelssl.ssl_algorithm.__dict__[algorithm].__dict__[algorithm](
+        args, {'model': sseg_model.deeplabv2()}, {'model': optimizer.sgd(args)},
+        {'model': lrer.polynomiallr(args)}, {'model': sseg_criterion.sseg_criterion()},
+        sseg_func.task_func()(args))
+    return alg
+
+
+def load_state(dp_model, state):
+    sd = {'module.model.' + k: v.clone() for k, v in state.items()}
+    missing = dp_model.load_state_dict(sd, strict=True)
+    return missing
+
+
+def checksums(named):
+    """[sum, sum of squares] in fp64 per tensor, in order."""
+    return np.array([[float(t.double().sum()), float((t.double() ** 2).sum())] for _, t in named])
+
+
+SAMPLE_PARAMS = ['backbone.conv1.weight', 'backbone.bn1.weight', 'backbone.bn1.bias',
+                 'backbone.layer1.0.conv2.weight', 'backbone.layer1.0.downsample.0.weight',
+                 'backbone.layer2.0.conv2.weight', 'backbone.layer3.11.bn2.weight',
+                 'backbone.layer4.2.conv3.weight', 'classifier.conv2d_list.0.bias',
+                 'classifier.conv2d_list.3.bias']
+
+
+def sample_of(t, n=4096):
+    f = t.detach().reshape(-1)
+    stride = max(1, f.numel() // n)
+    return f[::stride][:n].clone().numpy()
+
+
+def golden_mt(pixelssl, sseg_proxy, size=97, lbs=2, ubs=2, steps=3):
+    torch.manual_seed(0)
+    args = make_args(pixelssl, sseg_proxy, 'ssl_mt',
+                     {'cons_for_labeled': False, 'cons_scale': 1.0, 'cons_rampup_epochs': 1,
+                      'ema_decay': 0.99}, lbs + ubs, ubs, epochs=2, iters_per_epoch=5)
+    alg = build_algorithm(pixelssl, args, 'ssl_mt')
+    s0 = O.randomize_bn_affine(O.init_deeplabv2(11, cls_bias_std=0.01), 12)
+    t0 = O.randomize_bn_affine(O.init_deeplabv2(21, cls_bias_std=0.01), 22)
+    load_state(alg.s_model, s0)
+    load_state(alg.t_model, t0)
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    rec = {'size': size, 'lbs': lbs, 'ubs': ubs, 'steps': steps,
+           's_seed': np.array([11, 12]), 't_seed': np.array([21, 22]), 'data_seed': 100}
+    batches = [O.synthetic_batch(100 + i, lbs + ubs, lbs, size, size) for i in range(steps)]
+    loader = [((img.clone(),), (lab.clone(),)) for img, lab in batches]
+    # run step by step so grads / logits of each step can be captured:
+    # cur_step = len(loader_k) * epoch + idx; with a 1-element loader and epoch=k -> cur_step=k,
+    # rampup total = 1 * cons_rampup_epochs = 1 step  => ramp(0)=exp(-5), ramp(k>=1)=1.
+    for k in range(steps):
+        alg._train([loader[k]], k)
+        sm = alg.s_model.module.model
+        tm = alg.t_model.module.model
+        sp = dict(sm.named_parameters())
+        tp = dict(tm.named_parameters())
+        rec['s_task_loss_%d' % k] = float(alg.meters['s_task_loss'].val)
+        rec['t_task_loss_%d' % k] = float(alg.meters['t_task_loss'].val)
+        rec['cons_loss_%d' % k] = float(alg.meters['cons_loss'].val)
+        rec['grad_checksum_%d' % k] = checksums([(n, sp[n].grad) for n in names])
+        rec['s_param_checksum_%d' % k] = checksums([(n, sp[n]) for n in names])
+        rec['t_param_checksum_%d' % k] = checksums([(n, tp[n]) for n in names])
+        bufs = [(n, b) for n, b in sm.named_buffers() if 'num_batches' not in n]
+        rec['s_buffer_checksum_%d' % k] = checksums(bufs)
+        tbufs = [(n, b) for n, b in tm.named_buffers() if 'num_batches' not in n]
+        rec['t_buffer_checksum_%d' % k] = checksums(tbufs)
+        for n in SAMPLE_PARAMS:
+            rec['grad_%d/%s' % (k, n)] = sample_of(sp[n].grad)
+            rec['s_param_%d/%s' % (k, n)] = sample_of(sp[n])
+        rec['lr_%d' % k] = np.array([g['lr'] for g in alg.s_optimizer.param_groups])
+    rec['names'] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, 'mt_steps_%d.npz' % size), **rec)
+    print('mt golden:', {k: rec[k] for k in rec if 'loss' in k})
+
+
+def golden_forward(pixelssl, size=129, batch=2):
+    """Reference DeepLabV2 forward (train-mode BN) + CE + softmax on oracle-initialised weights."""
+    sys.path.insert(0, os.path.join(REF, 'task', 'sseg'))
+    from module import deeplab_v2
+    net = deeplab_v2.DeepLabV2('resnet101', 16, 21, True, False, None)
+    st = O.randomize_bn_affine(O.init_deeplabv2(31, cls_bias_std=0.01), 32)
+    net.load_state_dict({k: v.clone() for k, v in st.items()}, strict=True)
+    net.train()
+    img, lab = O.synthetic_batch(200, batch, batch, size, size)
+    logits, latent = net(img)
+    rec = {'size': size, 'batch': batch, 'seed': np.array([31, 32]), 'data_seed': 200,
+           'logits': logits.detach().numpy(), 'latent_sample': sample_of(latent, 8192),
+           'latent_checksum': checksums([('l', latent.detach())])}
+    rec['running_checksum'] = checksums([(n, b) for n, b in net.named_buffers() if 'num_batches' not in n])
+    np.savez_compressed(os.path.join(OUT, 'deeplabv2_forward_%d.npz' % size), **rec)
+    print('forward golden: logits', tuple(logits.shape), float(logits.abs().max()))
+
+
+def golden_ops(pixelssl, sseg_proxy):
+    """Small op-level vectors from the reference's own classes / call sites."""
+    import criterion as sseg_criterion
+    from pixelssl.nn import func as pfunc
+    from pixelssl.nn import lrer as plrer
+    from pixelssl.nn.module import GaussianBlurLayer, GaussianNoiseLayer
+    from pixelssl.ssl_algorithm import ssl_cutmix
+    rec = {}
+    # --- CommonSSEGCriterion (task/sseg/criterion.py:18-38)
+    args = make_args(pixelssl, sseg_proxy, 'ssl_null', {'ignore_unlabeled': True}, 2, 0)
+    crit = sseg_criterion.CommonSSEGCriterion(args)
+    g = torch.Generator().manual_seed(7)
+    logits = (torch.randn(3, 21, 37, 41, generator=g) * 3).requires_grad_(True)
+    _, lab = O.synthetic_batch(8, 3, 3, 37, 41)
+    loss = crit.forward((logits,), (lab,), (None,))
+    loss.mean().backward()
+    rec['ce_logits'] = logits.detach().numpy()
+    rec['ce_labels'] = lab.numpy()
+    rec['ce_loss'] = loss.detach().numpy()
+    rec['ce_grad'] = logits.grad.numpy()
+    # --- nn.MSELoss consistency (ssl_mt.py:115,179-187)
+    a = torch.randn(2, 21, 33, 35, generator=g).requires_grad_(True)
+    b = torch.randn(2, 21, 33, 35, generator=g)
+    m = torch.nn.MSELoss()(a, b)
+    (0.37 * m).backward()
+    rec['mse_s'], rec['mse_t'] = a.detach().numpy(), b.numpy()
+    rec['mse_loss'], rec['mse_grad_scale'], rec['mse_grad'] = float(m), 0.37, a.grad.numpy()
+    # --- sigmoid_rampup, PolynomialLR
+    rec['rampup'] = np.array([pfunc.sigmoid_rampup(c, 30) for c in range(0, 40, 3)] +
+                             [pfunc.sigmoid_rampup(5, 0)])
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([{'params': [p], 'lr': 0.00025}], lr=0.00025, momentum=0.9)
+    sch = plrer.PolynomialLR(opt, epochs=2, iters_per_epoch=5, power=0.9)
+    lrs = [opt.param_groups[0]['lr']]
+    for _ in range(8):
+        opt.step()
+        sch.step()
+        lrs.append(opt.param_groups[0]['lr'])
+    rec['poly_lr'] = np.array(lrs)
+    # --- BoxMaskGenerator (ssl_cutmix.py:470-547) + mix (ssl_cutmix.py:195,428)
+    np.random.seed(1234)
+    gen = ssl_cutmix.BoxMaskGenerator(prop_range=(0.5, 0.5), boxes_num=1, random_aspect_ratio=True,
+                                      area_prop=True, within_bounds=True, invert=True)
+    masks = gen.produce(4, (65, 97))
+    rec['cutmix_masks'] = masks
+    np.random.seed(99)
+    gen2 = ssl_cutmix.BoxMaskGenerator(prop_range=(0.25, 0.5), boxes_num=1, random_aspect_ratio=True,
+                                       area_prop=True, within_bounds=True, invert=True)
+    rec['cutmix_masks_b'] = gen2.produce(3, (513, 513)).reshape(3, 513, 513)[:, ::8, ::8].copy()
+    np.random.seed(99)
+    full = gen2.produce(3, (513, 513))
+    rec['cutmix_masks_b_sum'] = full.reshape(3, -1).sum(1)
+    u1 = torch.randn(4, 3, 65, 97, generator=g) * 1e3
+    u2 = torch.randn(4, 3, 65, 97, generator=g)
+    u1[0, 0, 0, :4] = torch.tensor([float('inf'), -0.0, 0.0, 1e-42])
+    mk = torch.tensor(masks)
+    rec['cutmix_a'], rec['cutmix_b'] = u1.numpy(), u2.numpy()
+    rec['cutmix_mixed'] = (mk * u1 + (1 - mk) * u2).numpy()
+    prob = torch.softmax(torch.randn(4, 21, 65, 97, generator=g) * 4, dim=1)
+    rec['conf_prob'] = prob.numpy()
+    rec['conf_value'] = float((prob.max(dim=1)[0] > 0.97).float().mean())
+    # --- GaussianBlurLayer weights (gaussian_blur.py:52-64) and one blur
+    for k in (5, 33, 65):
+        layer = GaussianBlurLayer(1, k)
+        rec['blur_w_%d' % k] = layer.op[1].weight.detach().numpy()[0, 0]
+    x = torch.rand(2, 1, 40, 44, generator=g)
+    rec['blur_x'] = x.numpy()
+    rec['blur_y_5'] = GaussianBlurLayer(1, 5)(x).detach().numpy()
+    rec['blur_y_33'] = GaussianBlurLayer(1, 33)(x).detach().numpy()
+    # --- GaussianNoiseLayer (gaussian_noise.py:17-40) with a captured noise draw
+    random.seed(5)
+    torch.manual_seed(5)
+    layer = GaussianNoiseLayer(0.3)
+    xin = torch.randn(2, 3, 19, 23, generator=g)
+    y = layer(xin.clone())
+    rec['noise_x'], rec['noise_n'], rec['noise_y'] = xin.numpy(), layer.noise.numpy().copy(), y.numpy()
+    # --- SyncBN multi-replica statistics (batchnorm.py:113-125)
+    from pixelssl.nn.module import SynchronizedBatchNorm2d
+    bn = SynchronizedBatchNorm2d(6)
+    bn.weight.data = torch.randn(6, generator=g)
+    bn.bias.data = torch.randn(6, generator=g)
+    parts = [torch.randn(2, 6, 5, 7, generator=g) * 2 + 1, torch.randn(3, 6, 5, 7, generator=g)]
+    sz = sum(p.numel() // 6 for p in parts)
+    s = sum(p.transpose(0, 1).reshape(6, -1).sum(1) for p in parts)
+    ss = sum((p ** 2).transpose(0, 1).reshape(6, -1).sum(1) for p in parts)
+    mean, inv_std = bn._compute_mean_std(s, ss, sz)
+    rec['sbn_parts0'], rec['sbn_parts1'] = parts[0].numpy(), parts[1].numpy()
+    rec['sbn_w'], rec['sbn_b'] = bn.weight.detach().numpy(), bn.bias.detach().numpy()
+    rec['sbn_mean'], rec['sbn_inv_std'] = mean.numpy(), inv_std.numpy()
+    rec['sbn_running_mean'], rec['sbn_running_var'] = bn.running_mean.numpy(), bn.running_var.numpy()
+    np.savez_compressed(os.path.join(OUT, 'ops.npz'), **rec)
+    print('ops golden written:', len(rec), 'arrays')
+
+
+def golden_null_cutmix(pixelssl, sseg_proxy, size=65):
+    """One SSLNULL step and one SSLCUTMIX step through the reference's own _train bodies."""
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    # --- supervised-only (ssl_null.py:78-144)
+    args = make_args(pixelssl, sseg_proxy, 'ssl_null', {'ignore_unlabeled': True}, 2, 0)
+    alg = build_algorithm(pixelssl, args, 'ssl_null')
+    load_state(alg.model, O.randomize_bn_affine(O.init_deeplabv2(41, cls_bias_std=0.01), 42))
+    img, lab = O.synthetic_batch(300, 2, 2, size, size)
+    alg._train([((img.clone(),), (lab.clone(),))], 0)
+    sp = dict(alg.model.module.model.named_parameters())
+    rec = {'size': size, 'task_loss': float(alg.meters['task_loss'].val),
+           'grad_checksum': checksums([(n, sp[n].grad) for n in names]),
+           'param_checksum': checksums([(n, sp[n]) for n in names])}
+    np.savez_compressed(os.path.join(OUT, 'null_step_%d.npz' % size), **rec)
+    print('null golden:', rec['task_loss'])
+    # --- CutMix (ssl_cutmix.py:132-255), lbs 2 + ubs 4 -> 2 mixed
+    args = make_args(pixelssl, sseg_proxy, 'ssl_cutmix',
+                     {'cons_scale': 20.0, 'cons_rampup_epochs': 0, 'cons_threshold': 0.05,
+                      'ema_decay': 0.99, 'mask_prop_range': '(0.5, 0.5)', 'cons_type': 'mse'}, 6, 4)
+    alg = build_algorithm(pixelssl, args, 'ssl_cutmix')
+    load_state(alg.s_model, O.randomize_bn_affine(O.init_deeplabv2(51, cls_bias_std=0.01), 52))
+    load_state(alg.t_model, O.randomize_bn_affine(O.init_deeplabv2(61, cls_bias_std=0.01), 62))
+    img, lab = O.synthetic_batch(400, 6, 2, size, size)
+    np.random.seed(4321)
+    alg._train([((img.clone(),), (lab.clone(),))], 0)
+    sp = dict(alg.s_model.module.model.named_parameters())
+    tp = dict(alg.t_model.module.model.named_parameters())
+    rec = {'size': size, 'task_loss': float(alg.meters['task_loss'].val),
+           'cons_loss': float(alg.meters['cons_loss'].val), 'mask_seed': 4321,
+           'cons_threshold': 0.05,
+           'grad_checksum': checksums([(n, sp[n].grad) for n in names]),
+           's_param_checksum': checksums([(n, sp[n]) for n in names]),
+           't_param_checksum': checksums([(n, tp[n]) for n in names])}
+    np.savez_compressed(os.path.join(OUT, 'cutmix_step_%d.npz' % size), **rec)
+    print('cutmix golden:', rec['task_loss'], rec['cons_loss'])
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    pixelssl, sseg_proxy = patch_and_import()
+    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix']
+    if 'ops' in which:
+        golden_ops(pixelssl, sseg_proxy)
+    if 'forward' in which:
+        golden_forward(pixelssl)
+    if 'mt' in which:
+        golden_mt(pixelssl, sseg_proxy)
+    if 'nullcutmix' in which:
+        golden_null_cutmix(pixelssl, sseg_proxy)
