@@ -1,0 +1,196 @@
+/*
+ * pixelssl_b200 -- C ABI of the B200-native (sm_100a) hot path of PixelSSL's semantic-segmentation
+ * SSL training step.  Plain pointers and sizes, no torch types.  Every pointer is a DEVICE pointer
+ * unless the parameter name ends in `_host`.  `stream` is a cudaStream_t passed as void*.
+ * Every entry point returns 0 on success or a cudaError_t / negative pxl error code; nothing is
+ * ever computed on the host as a fallback.
+ *
+ * Each group cites the reference call site it replaces (paths relative to the PixelSSL tree).
+ * Layouts: "NHWC" = channels innermost (torch channels_last), used for backbone activations;
+ * "planar" = NCHW, used for the C=21 logit / probability maps exactly like the reference.
+ * The reference-side binding is Python: see INTEGRATION.md (ctypes stub used by
+ * pixelssl_b200/_lib.py).
+ */
+#ifndef PIXELSSL_B200_H
+#define PIXELSSL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PXL_ERR_BAD_ARG   (-1)
+#define PXL_ERR_UNSUPPORTED (-2)
+
+/* library identity: returns the ABI version (bumped on signature changes) */
+int pxl_abi_version(void);
+/* number of kernel launches issued through this library since load / last reset (bench.py
+ * reports it as gpu_launches) */
+int64_t pxl_launch_count(void);
+void pxl_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Consistency loss: nn.MSELoss() on student vs detached teacher maps
+ *   pixelssl/ssl_algorithm/ssl_mt.py:115,179-187 (logits), ssl_cutmix.py:212-215,
+ *   ssl_gct.py:450, ssl_cct.py:484 (softmax maps)
+ * loss_out[0] = loss_scale * mean((s - t)^2) over n elements (fp64 accumulation, deterministic
+ * two-level reduction).  If grad_s != NULL also writes grad_s = loss_scale * 2 (s - t) / n
+ * (the fused fwd+bwd form: 12 B/element algorithmic traffic; forward-only is 8 B/element).
+ * workspace: >= pxl_mse_workspace_bytes() bytes, zero-initialised once (the kernel restores it).
+ * ------------------------------------------------------------------------------------------- */
+int64_t pxl_mse_workspace_bytes(void);
+int pxl_mse_consistency(const float* s, const float* t, int64_t n, float loss_scale,
+                        float* loss_out, float* grad_s, void* workspace, void* stream);
+/* generic backward for a device-resident upstream scalar: grad_s = upstream[0]*scale*2(s-t)/n */
+int pxl_mse_consistency_bwd(const float* s, const float* t, int64_t n, float loss_scale,
+                            const float* upstream, float* grad_s, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-pixel cross-entropy: CommonSSEGCriterion.forward, task/sseg/criterion.py:24-38
+ *   (nn.CrossEntropyLoss(ignore_index, reduction='none') on gt.long(), then mean over ALL H*W)
+ * logits planar [n, C, H*W]; labels fp32 [n, H*W] holding integers; per_sample[n] receives
+ * sum_pixels(ce)/HW (ignored pixels add 0 but count in the denominator).
+ * grad_logits (nullable) = g * (softmax - onehot) / HW on valid pixels, 0 on ignored ones, with
+ * g = upstream[i] if upstream != NULL else upstream_const (e.g. 1/lbs for the torch.mean that
+ * follows at ssl_mt.py:160).  Labels outside [0, C) other than ignore_index -> PXL_ERR_BAD_ARG is
+ * NOT detected on device; they are treated as ignored (documented deviation: torch asserts).
+ * ------------------------------------------------------------------------------------------- */
+int pxl_ce2d(const float* logits, const float* labels, int n, int C, int64_t HW, int ignore_index,
+             float* per_sample, float* grad_logits, const float* upstream, float upstream_const,
+             void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Channel softmax on planar maps: F.softmax(pred, dim=1), task/sseg/model.py:62,121;
+ * task/sseg/func.py:216-220
+ * ------------------------------------------------------------------------------------------- */
+int pxl_softmax_planar(const float* logits, float* prob, int n, int C, int64_t HW, void* stream);
+/* grad_logits = p * (g - sum_c g*p) */
+int pxl_softmax_planar_bwd(const float* prob, const float* grad_prob, float* grad_logits,
+                           int n, int C, int64_t HW, void* stream);
+/* fused CutMix / GCT / CCT consistency: loss = loss_scale*mean((softmax(s_logits)-t_prob)^2);
+ * optional prob_out (softmax of s), optional grad_logits (through the softmax).
+ * ssl_cutmix.py:206-215 */
+int pxl_softmax_mse(const float* s_logits, const float* t_prob, int n, int C, int64_t HW,
+                    float loss_scale, float* loss_out, float* prob_out, float* grad_logits,
+                    void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Bilinear resize, F.interpolate(mode='bilinear'): deeplab_v2.py:32, _pspnet.py:99-100,127,
+ * ssl_gct.py:580, ssl_adv.py:488, ssl_cct.py:482.  Planar [n*C, h, w] -> [n*C, H, W].
+ * in_nhwc != 0: the input is NHWC with channel stride ldc (e.g. the ASPP output padded to 32).
+ * ------------------------------------------------------------------------------------------- */
+int pxl_bilinear_fwd(const float* in, float* out, int n, int C, int h, int w, int H, int W,
+                     int align_corners, int in_nhwc, int ldc, void* stream);
+int pxl_bilinear_bwd(const float* grad_out, float* grad_in, int n, int C, int h, int w, int H, int W,
+                     int align_corners, int in_nhwc, int ldc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CutMix: mask*a + (1-mask)*b, bit-exact with the reference's fp32 evaluation order
+ *   ssl_cutmix.py:195,428.  a,b,out: [n, C, HW]; mask: [n, 1, HW] (broadcast over C).
+ * Confidence: count of pixels with max_c p > thr (ssl_cutmix.py:200); count_out is int64[1].
+ * ------------------------------------------------------------------------------------------- */
+int pxl_cutmix_mix(const float* mask, const float* a, const float* b, float* out,
+                   int n, int C, int64_t HW, void* stream);
+int pxl_cutmix_confidence(const float* prob, int n, int C, int64_t HW, float thr,
+                          unsigned long long* count_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm2d (training and eval), NHWC rows = N*H*W, C channels:
+ *   _SynchronizedBatchNorm.forward, sync_batchnorm/batchnorm.py:48-78,113-125
+ * stats: sums[0:C] = sum x, sums[C:2C] = sum x^2 as fp64 (atomically accumulated; caller zeroes).
+ *   For N>1 GPUs the caller all-reduces `sums` (NCCL) between stats and finalize.
+ * finalize: from sums & count -> mean, invstd (biased var; invstd = 1/sqrt(var+eps), or
+ *   clamp(var,eps)^-1/2 when clamp_mode!=0 = the reference's multi-replica formula), updates
+ *   running stats with the unbiased variance (momentum), writes scale=gamma*invstd,
+ *   shift=beta-mean*scale.
+ * apply: y = x*scale + shift (+ residual) (ReLU if relu!=0).
+ * ------------------------------------------------------------------------------------------- */
+int pxl_bn_stats(const float* x, int64_t rows, int C, double* sums, void* stream);
+int pxl_bn_finalize(const double* sums, double count, int C, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps,
+                    int clamp_mode, float* mean, float* invstd, float* scale, float* shift,
+                    void* stream);
+/* eval mode: scale/shift from running stats */
+int pxl_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift, void* stream);
+int pxl_bn_apply(const float* x, const float* scale, const float* shift, const float* residual,
+                 int relu, float* y, int64_t rows, int C, void* stream);
+/* backward of y = relu?(bn(x) + residual?):
+ *   reduce: dsums[0:C] = sum dz, dsums[C:2C] = sum dz*xhat with dz = dy * (y>0 if relu) (fp64;
+ *   caller zeroes; all-reduced for N>1);  writes nothing else.
+ *   dx:  dx = gamma*invstd*(dz - dsums0/count - xhat*dsums1/count); dres (nullable) = dz.
+ *   dgamma += dsums1, dbeta += dsums0 are produced by pxl_bn_bwd_params. */
+int pxl_bn_bwd_reduce(const float* x, const float* y, const float* dy, const float* mean,
+                      const float* invstd, int relu, int64_t rows, int C, double* dsums, void* stream);
+int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, const float* mean,
+                  const float* invstd, const float* gamma, const double* dsums, double count,
+                  int relu, float* dx, float* dres, int64_t rows, int C, void* stream);
+int pxl_bn_bwd_params(const double* dsums, int C, float* dgamma, float* dbeta, int accumulate,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MaxPool2d(3, stride 2, pad 1) on NHWC: resnet.py:72,125
+ * ------------------------------------------------------------------------------------------- */
+int pxl_maxpool3x3s2_fwd(const float* x, float* y, int N, int H, int W, int C, int OH, int OW,
+                         void* stream);
+int pxl_maxpool3x3s2_bwd(const float* x, const float* y, const float* dy, float* dx,
+                         int N, int H, int W, int C, int OH, int OW, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution, NHWC activations, weights [Cout][tap][Cin] (= torch channels_last OIHW storage),
+ * arbitrary tap table (dy,dx per tap) so that a dilated 3x3 is 9 taps and the whole ASPP head
+ * (deeplab_v2.py:71-85: 4 dilated 3x3 convs summed) is ONE 36-tap convolution.
+ *   nn.Conv2d call sites: resnet.py:18-25,69,88-91 ; deeplab_v2.py:76,81-85 ; _pspnet.py:17,46,69,90
+ *
+ * geometry: out[n,oy,ox,co] = bias[co] + sum_t sum_ci in[n, (oy*mul + dy_t)/div, (ox*mul + dx_t)/div, ci]
+ *                                                   * w[co][t][ci]
+ *   (terms whose coordinate is not divisible by div or falls outside [0,H)x[0,W) are zero).
+ *   forward conv: mul=stride, div=1, dy_t = r*dil - pad.   dgrad: mul=1, div=stride, taps negated,
+ *   weights transposed to [Cin][tap][Cout] (pxl_conv_transpose_weights).
+ * precision: 0 = fp32 FFMA (exact fp32 accumulate), 1 = tf32 tensor cores (tcgen05), 2 = 3xTF32
+ *   error-compensated tcgen05.  Unsupported (shape, precision) combos return PXL_ERR_UNSUPPORTED.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int N, H, W, Cin;        /* input tensor  */
+    int OH, OW, Cout;        /* output tensor */
+    int ldo;                 /* output channel stride (>= Cout; 32 for the padded ASPP output) */
+    int mul, div;            /* coordinate transform, see above */
+    int ntaps;               /* <= PXL_MAX_TAPS */
+    int precision;
+} pxl_conv_geom;
+#define PXL_MAX_TAPS 64
+int pxl_conv_nhwc(const pxl_conv_geom* geom_host, const int* taps_dydx_host /* 2*ntaps ints */,
+                  const float* in, const float* w, const float* bias /* nullable */,
+                  float* out, void* stream);
+/* dW[co][t][ci] += sum over output pixels of dy[n,oy,ox,co] * in[n, iy, ix, ci]   (accumulates) */
+int pxl_conv_wgrad_nhwc(const pxl_conv_geom* geom_host, const int* taps_dydx_host,
+                        const float* in, const float* dy, float* dw, void* stream);
+/* w [Cout][T][Cin] -> wt [Cin][T][Cout] */
+int pxl_conv_transpose_weights(const float* w, float* wt, int Cout, int T, int Cin, void* stream);
+/* dbias[co] (+)= sum over rows of dy[row, co] (row stride ldo) */
+int pxl_bias_grad(const float* dy, int64_t rows, int Cout, int ldo, float* dbias, int accumulate,
+                  void* stream);
+
+/* stem: conv 7x7 stride 2 pad 3 on the planar [N,3,H,W] image -> NHWC [N,OH,OW,64]
+ * (resnet.py:69,121); weights [64][7*7][3].  wgrad accumulates into dw. */
+int pxl_stem_conv7x7s2(const float* img_planar, const float* w, float* out, int N, int H, int W,
+                       int OH, int OW, void* stream);
+int pxl_stem_conv7x7s2_wgrad(const float* img_planar, const float* dy, float* dw, int N, int H, int W,
+                             int OH, int OW, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimiser + EMA on flat parameter arenas:
+ *   torch.optim.SGD as configured by pixelssl/nn/optimizer.py:57-75 (momentum, wd, dampening 0)
+ *   + SSLMT._update_ema_variables, ssl_mt.py:359-363 / ssl_cutmix.py:434-438
+ * d = g + wd*p ; buf = d (first_step) else mom*buf + d ; p -= lr*buf ; if teacher != NULL:
+ * teacher = teacher*ema_d + (1-ema_d)*p.   28 B/param fused (20 without the teacher).
+ * ------------------------------------------------------------------------------------------- */
+int pxl_sgd_ema(float* p, const float* g, float* buf, float* teacher, int64_t n, float lr,
+                float momentum, float weight_decay, float ema_d, int first_step, void* stream);
+int pxl_ema(float* teacher, const float* student, int64_t n, float ema_d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXELSSL_B200_H */

@@ -1,0 +1,95 @@
+"""ctypes binding of libpixelssl_b200.so (the C ABI declared in include/pixelssl_b200.h).
+
+There is NO fallback: if the shared library is missing or a symbol is absent, importing / calling
+raises.  The binding below is exactly the stub shown in INTEGRATION.md."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libpixelssl_b200.so')
+
+c_void_p, c_int, c_int64, c_float, c_double = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                               ctypes.c_float, ctypes.c_double)
+
+
+class ConvGeom(ctypes.Structure):
+    """mirror of pxl_conv_geom"""
+    _fields_ = [('N', c_int), ('H', c_int), ('W', c_int), ('Cin', c_int),
+                ('OH', c_int), ('OW', c_int), ('Cout', c_int), ('ldo', c_int),
+                ('mul', c_int), ('div', c_int), ('ntaps', c_int), ('precision', c_int)]
+
+
+P = c_void_p
+# name -> (restype, argtypes); must list every symbol of include/pixelssl_b200.h
+SIGNATURES = {
+    'pxl_abi_version': (c_int, []),
+    'pxl_launch_count': (c_int64, []),
+    'pxl_reset_launch_count': (None, []),
+    'pxl_mse_workspace_bytes': (c_int64, []),
+    'pxl_mse_consistency': (c_int, [P, P, c_int64, c_float, P, P, P, P]),
+    'pxl_mse_consistency_bwd': (c_int, [P, P, c_int64, c_float, P, P, P]),
+    'pxl_ce2d': (c_int, [P, P, c_int, c_int, c_int64, c_int, P, P, P, c_float, P]),
+    'pxl_softmax_planar': (c_int, [P, P, c_int, c_int, c_int64, P]),
+    'pxl_softmax_planar_bwd': (c_int, [P, P, P, c_int, c_int, c_int64, P]),
+    'pxl_softmax_mse': (c_int, [P, P, c_int, c_int, c_int64, c_float, P, P, P, P, P]),
+    'pxl_bilinear_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'pxl_bilinear_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'pxl_cutmix_mix': (c_int, [P, P, P, P, c_int, c_int, c_int64, P]),
+    'pxl_cutmix_confidence': (c_int, [P, c_int, c_int, c_int64, c_float, P, P]),
+    'pxl_bn_stats': (c_int, [P, c_int64, c_int, P, P]),
+    'pxl_bn_finalize': (c_int, [P, c_double, c_int, P, P, P, P, c_float, c_float, c_int, P, P, P, P, P]),
+    'pxl_bn_eval_coeffs': (c_int, [c_int, P, P, P, P, c_float, P, P, P]),
+    'pxl_bn_apply': (c_int, [P, P, P, P, c_int, P, c_int64, c_int, P]),
+    'pxl_bn_bwd_reduce': (c_int, [P, P, P, P, P, c_int, c_int64, c_int, P, P]),
+    'pxl_bn_bwd_dx': (c_int, [P, P, P, P, P, P, P, c_double, c_int, P, P, c_int64, c_int, P]),
+    'pxl_bn_bwd_params': (c_int, [P, c_int, P, P, c_int, P]),
+    'pxl_maxpool3x3s2_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'pxl_maxpool3x3s2_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'pxl_conv_nhwc': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P]),
+    'pxl_conv_wgrad_nhwc': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P]),
+    'pxl_conv_transpose_weights': (c_int, [P, P, c_int, c_int, c_int, P]),
+    'pxl_bias_grad': (c_int, [P, c_int64, c_int, c_int, P, c_int, P]),
+    'pxl_stem_conv7x7s2': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'pxl_stem_conv7x7s2_wgrad': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'pxl_sgd_ema': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, P]),
+    'pxl_ema': (c_int, [P, P, c_int64, c_float, P]),
+}
+
+PXL_ERR_BAD_ARG = -1
+PXL_ERR_UNSUPPORTED = -2
+
+_lib = None
+
+
+class PxlError(RuntimeError):
+    def __init__(self, fn, code):
+        self.fn, self.code = fn, code
+        what = {PXL_ERR_BAD_ARG: 'bad argument', PXL_ERR_UNSUPPORTED: 'unsupported configuration'}.get(
+            code, 'cudaError_t %d' % code)
+        super().__init__('%s failed: %s' % (fn, what))
+
+
+def load():
+    """Load (once) and type the library.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'pixelssl_b200: %s not found. Build it with `python -c "import __graft_entry__ as g; '
+            'g.build()"` (nvcc, sm_100a). There is no CPU/PyTorch fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing: loud by design
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise PxlError on a non-zero return."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise PxlError(name, rc)
+    return rc

@@ -1,0 +1,425 @@
+// NHWC BatchNorm (train / eval, forward / backward), 3x3/2 max-pool, fused SGD+EMA.
+// All HBM-bound: every kernel moves 128-bit vectors along the channel dimension, one pass per
+// tensor, with per-channel reductions finished in fp64 atomics (tiny: 2*C doubles per layer).
+#include "common.cuh"
+#include <math_constants.h>
+
+// ------------------------------------------------------------------------------------------
+// thread layout shared by the per-channel reductions: a block covers CW = 4*TX channels
+// (TX lanes x float4) and strides over rows with TY = 256/TX row lanes.
+// ------------------------------------------------------------------------------------------
+struct RedLayout { int TX, TY, colBlocks, rowBlocks; int64_t rowsPerBlock; };
+
+static RedLayout red_layout(int64_t rows, int C) {
+    RedLayout L;
+    int c4 = C / 4;
+    L.TX = c4 >= 32 ? 32 : (c4 >= 16 ? 16 : (c4 >= 8 ? 8 : (c4 >= 4 ? 4 : (c4 >= 2 ? 2 : 1))));
+    L.TY = 256 / L.TX;
+    L.colBlocks = (int)pxl_cdiv(c4, L.TX);
+    int64_t target = (int64_t)PXL_NUM_SMS * 8 / L.colBlocks;
+    if (target < 1) target = 1;
+    int64_t rpb = pxl_cdiv(rows, target);
+    if (rpb < L.TY * 4) rpb = L.TY * 4;
+    L.rowsPerBlock = rpb;
+    L.rowBlocks = (int)pxl_cdiv(rows, rpb);
+    return L;
+}
+
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+
+// reduce two float4 accumulators over the TY row-lanes of the block, then fp64 atomics
+__device__ __forceinline__ void block_reduce_cols(float4 s0, float4 s1, int TX, int TY, int c4, int c4max,
+                                                  double* out0, double* out1) {
+    __shared__ float4 sm0[256];
+    __shared__ float4 sm1[256];
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    sm0[threadIdx.x] = s0;
+    sm1[threadIdx.x] = s1;
+    __syncthreads();
+    for (int h = TY >> 1; h > 0; h >>= 1) {
+        if (ty < h) {
+            sm0[threadIdx.x] = f4add(sm0[threadIdx.x], sm0[threadIdx.x + h * TX]);
+            sm1[threadIdx.x] = f4add(sm1[threadIdx.x], sm1[threadIdx.x + h * TX]);
+        }
+        __syncthreads();
+    }
+    if (ty == 0 && c4 < c4max) {
+        float4 a = sm0[tx], b = sm1[tx];
+        atomicAdd(out0 + 4 * c4 + 0, (double)a.x); atomicAdd(out0 + 4 * c4 + 1, (double)a.y);
+        atomicAdd(out0 + 4 * c4 + 2, (double)a.z); atomicAdd(out0 + 4 * c4 + 3, (double)a.w);
+        atomicAdd(out1 + 4 * c4 + 0, (double)b.x); atomicAdd(out1 + 4 * c4 + 1, (double)b.y);
+        atomicAdd(out1 + 4 * c4 + 2, (double)b.z); atomicAdd(out1 + 4 * c4 + 3, (double)b.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward statistics: sums[0:C] += sum x ; sums[C:2C] += sum x^2
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const float* __restrict__ x, int64_t rows, int C, int TX, int TY, int64_t rowsPerBlock,
+                double* __restrict__ sums) {
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
+    const int64_t r0 = (int64_t)blockIdx.x * rowsPerBlock;
+    const int64_t r1 = min(rows, r0 + rowsPerBlock);
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    if (c4 < c4max) {
+        const float4* xp = reinterpret_cast<const float4*>(x) + c4;
+        for (int64_t r = r0 + ty; r < r1; r += TY) {
+            float4 v = __ldg(xp + r * c4max);
+            s = f4add(s, v);
+            q = f4add(q, f4mul(v, v));
+        }
+    }
+    block_reduce_cols(s, q, TX, TY, c4, c4max, sums, sums + C);
+}
+
+extern "C" int pxl_bn_stats(const float* x, int64_t rows, int C, double* sums, void* stream) {
+    if (!x || !sums || rows <= 0 || C <= 0 || (C & 3)) return PXL_ERR_BAD_ARG;
+    RedLayout L = red_layout(rows, C);
+    dim3 grid(L.rowBlocks, L.colBlocks);
+    bn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, C, L.TX, L.TY, L.rowsPerBlock, sums);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* running_mean, float* running_var, float momentum, float eps,
+                                   int clamp_mode, float* mean, float* invstd, float* scale, float* shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = sums[c] / count;
+    double var = sums[C + c] / count - m * m;     // biased
+    if (var < 0.0) var = 0.0;
+    const float mf = (float)m;
+    float is;
+    if (clamp_mode) is = 1.0f / sqrtf(fmaxf((float)var, eps));   // batchnorm.py:125 multi-replica path
+    else is = 1.0f / sqrtf((float)var + eps);                    // F.batch_norm path (batchnorm.py:50-53)
+    if (running_mean) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mf;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+    mean[c] = mf;
+    invstd[c] = is;
+    const float sc = gamma[c] * is;
+    scale[c] = sc;
+    shift[c] = beta[c] - mf * sc;
+}
+
+extern "C" int pxl_bn_finalize(const double* sums, double count, int C, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float momentum, float eps,
+                               int clamp_mode, float* mean, float* invstd, float* scale, float* shift,
+                               void* stream) {
+    if (!sums || !gamma || !beta || !mean || !invstd || !scale || !shift || C <= 0 || count <= 0) return PXL_ERR_BAD_ARG;
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, count, C, gamma, beta, running_mean, running_var,
+                                                                         momentum, eps, clamp_mode, mean, invstd, scale, shift);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+__global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* beta, const float* rm,
+                                      const float* rv, float eps, float* scale, float* shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float sc = gamma[c] / sqrtf(rv[c] + eps);
+    scale[c] = sc;
+    shift[c] = beta[c] - rm[c] * sc;
+}
+
+extern "C" int pxl_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
+                                  const float* running_var, float eps, float* scale, float* shift, void* stream) {
+    if (!gamma || !beta || !running_mean || !running_var || !scale || !shift || C <= 0) return PXL_ERR_BAD_ARG;
+    bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, running_mean, running_var, eps, scale, shift);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// apply: y = x*scale + shift (+ residual) (ReLU)        8 B/elem (12 with residual)
+// ------------------------------------------------------------------------------------------
+template <bool RES, bool RELU>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float4* __restrict__ x, const float4* __restrict__ scale, const float4* __restrict__ shift,
+                const float4* __restrict__ res, float4* __restrict__ y, int64_t n4, int c4max) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int c = (int)(i % c4max);
+        float4 v = __ldcs(x + i);
+        const float4 sc = __ldg(scale + c), sh = __ldg(shift + c);
+        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        if (RES) { float4 r = __ldcs(res + i); v = f4add(v, r); }
+        if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        y[i] = v;
+    }
+}
+
+extern "C" int pxl_bn_apply(const float* x, const float* scale, const float* shift, const float* residual,
+                            int relu, float* y, int64_t rows, int C, void* stream) {
+    if (!x || !scale || !shift || !y || rows <= 0 || C <= 0 || (C & 3)) return PXL_ERR_BAD_ARG;
+    const int64_t n4 = rows * (C / 4);
+    int blocks = (int)(pxl_cdiv(n4, 256 * 2) < PXL_NUM_SMS * 8 ? pxl_cdiv(n4, 256 * 2) : PXL_NUM_SMS * 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float4 *x4 = (const float4*)x, *s4 = (const float4*)scale, *h4 = (const float4*)shift, *r4 = (const float4*)residual;
+    float4* y4 = (float4*)y;
+    if (residual && relu) bn_apply_kernel<true, true><<<blocks, 256, 0, st>>>(x4, s4, h4, r4, y4, n4, C / 4);
+    else if (residual) bn_apply_kernel<true, false><<<blocks, 256, 0, st>>>(x4, s4, h4, r4, y4, n4, C / 4);
+    else if (relu) bn_apply_kernel<false, true><<<blocks, 256, 0, st>>>(x4, s4, h4, r4, y4, n4, C / 4);
+    else bn_apply_kernel<false, false><<<blocks, 256, 0, st>>>(x4, s4, h4, r4, y4, n4, C / 4);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward.  dz = dy * (y > 0) when the ReLU was fused.
+//   reduce: dsums[0:C] += sum dz ; dsums[C:2C] += sum dz * xhat
+//   dx = gamma*invstd * (dz - dsums0/count - xhat*dsums1/count)
+// ------------------------------------------------------------------------------------------
+template <bool RELU>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, int64_t rows, int C,
+                     int TX, int TY, int64_t rowsPerBlock, double* __restrict__ dsums) {
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
+    const int64_t r0 = (int64_t)blockIdx.x * rowsPerBlock;
+    const int64_t r1 = min(rows, r0 + rowsPerBlock);
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    if (c4 < c4max) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + c4);
+        const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + c4);
+        const float4* xp = reinterpret_cast<const float4*>(x) + c4;
+        const float4* yp = reinterpret_cast<const float4*>(y) + c4;
+        const float4* dp = reinterpret_cast<const float4*>(dy) + c4;
+        for (int64_t r = r0 + ty; r < r1; r += TY) {
+            float4 d = __ldg(dp + r * c4max);
+            if (RELU) {
+                float4 o = __ldg(yp + r * c4max);
+                d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
+                d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
+            }
+            float4 v = __ldg(xp + r * c4max);
+            float4 xh = make_float4((v.x - m.x) * is.x, (v.y - m.y) * is.y, (v.z - m.z) * is.z, (v.w - m.w) * is.w);
+            s = f4add(s, d);
+            q = f4add(q, f4mul(d, xh));
+        }
+    }
+    block_reduce_cols(s, q, TX, TY, c4, c4max, dsums, dsums + C);
+}
+
+extern "C" int pxl_bn_bwd_reduce(const float* x, const float* y, const float* dy, const float* mean,
+                                 const float* invstd, int relu, int64_t rows, int C, double* dsums, void* stream) {
+    if (!x || !dy || !mean || !invstd || !dsums || rows <= 0 || C <= 0 || (C & 3) || (relu && !y)) return PXL_ERR_BAD_ARG;
+    RedLayout L = red_layout(rows, C);
+    dim3 grid(L.rowBlocks, L.colBlocks);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (relu) bn_bwd_reduce_kernel<true><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums);
+    else bn_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+template <bool RELU, bool DRES>
+__global__ void __launch_bounds__(256)
+bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, const float4* __restrict__ dy,
+                 const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                 const double* __restrict__ dsums, double inv_count, float4* __restrict__ dx, float4* __restrict__ dres,
+                 int64_t n4, int C) {
+    const int c4max = C >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int c = 4 * (int)(i % c4max);
+        float4 d = __ldcs(dy + i);
+        if (RELU) {
+            float4 o = __ldcs(y + i);
+            d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
+            d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
+        }
+        if (DRES) dres[i] = d;
+        const float4 v = __ldcs(x + i);
+        float4 r;
+        float* rp = &r.x; const float* dp = &d.x; const float* vp = &v.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float m = __ldg(mean + c + k), is = __ldg(invstd + c + k), g = __ldg(gamma + c + k);
+            const float mdz = (float)(__ldg(dsums + c + k) * inv_count);
+            const float mdzx = (float)(__ldg(dsums + C + c + k) * inv_count);
+            const float xh = (vp[k] - m) * is;
+            rp[k] = g * is * (dp[k] - mdz - xh * mdzx);
+        }
+        dx[i] = r;
+    }
+}
+
+extern "C" int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, const float* mean,
+                             const float* invstd, const float* gamma, const double* dsums, double count,
+                             int relu, float* dx, float* dres, int64_t rows, int C, void* stream) {
+    if (!x || !dy || !mean || !invstd || !gamma || !dsums || !dx || rows <= 0 || C <= 0 || (C & 3) || (relu && !y)) return PXL_ERR_BAD_ARG;
+    const int64_t n4 = rows * (C / 4);
+    int blocks = (int)(pxl_cdiv(n4, 256 * 2) < PXL_NUM_SMS * 8 ? pxl_cdiv(n4, 256 * 2) : PXL_NUM_SMS * 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float4 *x4 = (const float4*)x, *y4 = (const float4*)y, *d4 = (const float4*)dy;
+    float4 *o4 = (float4*)dx, *r4 = (float4*)dres;
+    const double ic = 1.0 / count;
+    if (relu && dres) bn_bwd_dx_kernel<true, true><<<blocks, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, n4, C);
+    else if (relu) bn_bwd_dx_kernel<true, false><<<blocks, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, n4, C);
+    else if (dres) bn_bwd_dx_kernel<false, true><<<blocks, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, n4, C);
+    else bn_bwd_dx_kernel<false, false><<<blocks, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, n4, C);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+__global__ void bn_bwd_params_kernel(const double* __restrict__ dsums, int C, float* dgamma, float* dbeta, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float db = (float)dsums[c], dg = (float)dsums[C + c];
+    if (accumulate) { dgamma[c] += dg; dbeta[c] += db; }
+    else { dgamma[c] = dg; dbeta[c] = db; }
+}
+
+extern "C" int pxl_bn_bwd_params(const double* dsums, int C, float* dgamma, float* dbeta, int accumulate, void* stream) {
+    if (!dsums || !dgamma || !dbeta || C <= 0) return PXL_ERR_BAD_ARG;
+    bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dsums, C, dgamma, dbeta, accumulate);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// MaxPool2d(kernel 3, stride 2, padding 1), NHWC (resnet.py:72).  Backward routes each output
+// gradient to the FIRST maximum in row-major window order (strict '>' scan, like ATen).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H, int W, int c4max, int OH, int OW) {
+    const int64_t total = (int64_t)N * OH * OW * c4max;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % c4max);
+        int64_t p = i / c4max;
+        const int ox = (int)(p % OW); p /= OW;
+        const int oy = (int)(p % OH);
+        const int n = (int)(p / OH);
+        float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int iy = oy * 2 - 1 + r;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int ix = ox * 2 - 1 + s;
+                if (ix < 0 || ix >= W) continue;
+                const float4 v = __ldg(x + ((int64_t)(n * H + iy) * W + ix) * c4max + c);
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        }
+        y[i] = m;
+    }
+}
+
+extern "C" int pxl_maxpool3x3s2_fwd(const float* x, float* y, int N, int H, int W, int C, int OH, int OW, void* stream) {
+    if (!x || !y || N <= 0 || (C & 3) || OH != (H + 2 - 3) / 2 + 1 || OW != (W + 2 - 3) / 2 + 1) return PXL_ERR_BAD_ARG;
+    const int64_t total = (int64_t)N * OH * OW * (C / 4);
+    int blocks = (int)(pxl_cdiv(total, 256) < PXL_NUM_SMS * 16 ? pxl_cdiv(total, 256) : PXL_NUM_SMS * 16);
+    maxpool_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C / 4, OH, OW);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
+                   int N, int H, int W, int C, int OH, int OW) {
+    const int64_t total = (int64_t)N * OH * OW * C;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % C);
+        int64_t p = i / C;
+        const int ox = (int)(p % OW); p /= OW;
+        const int oy = (int)(p % OH);
+        const int n = (int)(p / OH);
+        float m = -CUDART_INF_F;
+        int64_t arg = -1;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int iy = oy * 2 - 1 + r;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int ix = ox * 2 - 1 + s;
+                if (ix < 0 || ix >= W) continue;
+                const int64_t idx = ((int64_t)(n * H + iy) * W + ix) * C + c;
+                const float v = __ldg(x + idx);
+                if (arg < 0 || v > m || isnan(v)) { m = v; arg = idx; }
+            }
+        }
+        if (arg >= 0) atomicAdd(dx + arg, __ldg(dy + i));
+    }
+}
+
+extern "C" int pxl_maxpool3x3s2_bwd(const float* x, const float* y, const float* dy, float* dx,
+                                    int N, int H, int W, int C, int OH, int OW, void* stream) {
+    (void)y;
+    if (!x || !dy || !dx || N <= 0) return PXL_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)N * H * W * C, st);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t total = (int64_t)N * OH * OW * C;
+    int blocks = (int)(pxl_cdiv(total, 256) < PXL_NUM_SMS * 16 ? pxl_cdiv(total, 256) : PXL_NUM_SMS * 16);
+    maxpool_bwd_kernel<<<blocks, 256, 0, st>>>(x, dy, dx, N, H, W, C, OH, OW);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused SGD(momentum, weight decay) + teacher EMA over a flat parameter arena
+//   (nn/optimizer.py:57-75 ; ssl_mt.py:359-363).  28 B/param: r p, r g, r buf, r t ; w p, w buf, w t
+// ------------------------------------------------------------------------------------------
+template <bool EMA, bool FIRST>
+__global__ void __launch_bounds__(256)
+sgd_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, float* __restrict__ t,
+               int64_t n, float lr, float mom, float wd, float d) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float omd = 1.f - d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float pv = p[i];
+        // torch: d_p = g.add(p, alpha=wd); buf = d_p (first) | buf.mul_(mom).add_(d_p); p.add_(buf, alpha=-lr)
+        float dp = fmaf(wd, pv, g[i]);
+        float b;
+        if (FIRST) b = dp;
+        else b = __fadd_rn(__fmul_rn(buf[i], mom), dp);
+        buf[i] = b;
+        const float np = fmaf(-lr, b, pv);
+        p[i] = np;
+        if (EMA) t[i] = fmaf(omd, np, __fmul_rn(t[i], d));   // t.mul_(d).add_(s, alpha=1-d)
+    }
+}
+
+extern "C" int pxl_sgd_ema(float* p, const float* g, float* buf, float* teacher, int64_t n, float lr,
+                           float momentum, float weight_decay, float ema_d, int first_step, void* stream) {
+    if (!p || !g || !buf || n <= 0) return PXL_ERR_BAD_ARG;
+    int blocks = (int)(pxl_cdiv(n, 256 * 4) < PXL_NUM_SMS * 8 ? pxl_cdiv(n, 256 * 4) : PXL_NUM_SMS * 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (teacher && first_step) sgd_ema_kernel<true, true><<<blocks, 256, 0, st>>>(p, g, buf, teacher, n, lr, momentum, weight_decay, ema_d);
+    else if (teacher) sgd_ema_kernel<true, false><<<blocks, 256, 0, st>>>(p, g, buf, teacher, n, lr, momentum, weight_decay, ema_d);
+    else if (first_step) sgd_ema_kernel<false, true><<<blocks, 256, 0, st>>>(p, g, buf, teacher, n, lr, momentum, weight_decay, ema_d);
+    else sgd_ema_kernel<false, false><<<blocks, 256, 0, st>>>(p, g, buf, teacher, n, lr, momentum, weight_decay, ema_d);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+ema_kernel(float* __restrict__ t, const float* __restrict__ s, int64_t n, float d) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float omd = 1.f - d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        t[i] = fmaf(omd, s[i], __fmul_rn(t[i], d));
+}
+
+extern "C" int pxl_ema(float* teacher, const float* student, int64_t n, float ema_d, void* stream) {
+    if (!teacher || !student || n <= 0) return PXL_ERR_BAD_ARG;
+    int blocks = (int)(pxl_cdiv(n, 256 * 4) < PXL_NUM_SMS * 8 ? pxl_cdiv(n, 256 * 4) : PXL_NUM_SMS * 8);
+    ema_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(teacher, student, n, ema_d);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,572 @@
+"""Torch-facing wrappers of the C-ABI kernels: torch only provides device memory, the current
+stream and autograd bookkeeping; every FLOP and byte below runs in libpixelssl_b200.so.
+
+Conventions
+  * backbone activations: logical [N,C,H,W] tensors in ``torch.channels_last`` (physical NHWC);
+  * conv weights: logical [Cout,Cin,kh,kw] in channels_last (physical [Cout][kh*kw][Cin]);
+  * logit / probability maps (C = num_classes): plain contiguous NCHW ("planar"), as in the
+    reference; labels: float [n,1,H,W] holding integers (task/sseg/data.py:179-182).
+All tensors must be fp32 CUDA tensors; anything else raises (no silent fallback)."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvGeom, call
+
+CL = torch.channels_last
+# conv precision policy (pxl_conv_geom.precision): 0 fp32 FFMA, 1 TF32 tcgen05, 2 3xTF32 tcgen05
+PRECISION = {'fp32': 0, 'tf32': 1, 'tf32x3': 2}
+_conv_precision = 0
+
+
+def set_conv_precision(name):
+    global _conv_precision
+    _conv_precision = PRECISION[name]
+
+
+def get_conv_precision():
+    return _conv_precision
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, name, cl=False):
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise TypeError('%s must be a CUDA float32 tensor (got %s on %s)' % (name, t.dtype, t.device))
+    if cl:
+        if t.dim() != 4 or not t.is_contiguous(memory_format=CL):
+            raise ValueError('%s must be a 4-D channels_last tensor' % name)
+    elif not t.is_contiguous():
+        raise ValueError('%s must be contiguous' % name)
+
+
+def as_cl(t):
+    """Return t in channels_last physical layout (no copy if it already is)."""
+    return t.contiguous(memory_format=CL)
+
+
+_workspaces = {}
+
+
+def _mse_ws(device):
+    ws = _workspaces.get(device)
+    if ws is None:
+        n = _lib.load().pxl_mse_workspace_bytes()
+        ws = torch.zeros((n + 7) // 8, dtype=torch.float64, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+
+def mse_consistency_raw(s, t, loss_scale=1.0, want_grad=True):
+    """Fused forward(+backward) of loss_scale * mean((s-t)^2).  Returns (loss[1], grad or None)."""
+    _chk(s, 's'); _chk(t, 't')
+    if s.shape != t.shape:
+        raise ValueError('shape mismatch')
+    loss = torch.empty(1, dtype=torch.float32, device=s.device)
+    grad = torch.empty_like(s) if want_grad else None
+    call('pxl_mse_consistency', _p(s), _p(t), s.numel(), float(loss_scale), _p(loss), _p(grad),
+         _p(_mse_ws(s.device)), _stream())
+    return loss, grad
+
+
+class _MseConsistency(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, t, loss_scale, unit_upstream):
+        need = ctx.needs_input_grad[0]
+        loss, grad = mse_consistency_raw(s, t, loss_scale, want_grad=need and unit_upstream)
+        ctx.unit, ctx.scale = unit_upstream, loss_scale
+        if need:
+            if unit_upstream:
+                ctx.save_for_backward(grad)
+            else:
+                ctx.save_for_backward(s, t)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.unit:
+            (grad,) = ctx.saved_tensors
+            return grad, None, None, None
+        s, t = ctx.saved_tensors
+        grad = torch.empty_like(s)
+        g = g.reshape(1).contiguous().float()
+        call('pxl_mse_consistency_bwd', _p(s), _p(t), s.numel(), float(ctx.scale), _p(g), _p(grad), _stream())
+        return grad, None, None, None
+
+
+def mse_consistency(s, t, loss_scale=1.0, unit_upstream=False):
+    """nn.MSELoss()(s, t.detach()) * loss_scale (ssl_mt.py:115,179-187).
+
+    unit_upstream=True: the caller guarantees the returned scalar is added, un-scaled, into the
+    loss on which ``backward()`` is called (d total / d this = 1), so the gradient is produced by
+    the same kernel launch as the loss (12 B/element instead of 8 + 12)."""
+    return _MseConsistency.apply(s.contiguous(), t.detach().contiguous(), float(loss_scale), bool(unit_upstream))
+
+
+def _labels_flat(gt, n, hw):
+    if gt.numel() != n * hw:
+        raise ValueError('label tensor has %d elements, expected %d' % (gt.numel(), n * hw))
+    _chk(gt, 'gt')
+    return gt
+
+
+class _CrossEntropy2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, gt, ignore_index, upstream_const):
+        _chk(logits, 'logits')
+        n, c, h, w = logits.shape
+        gt = _labels_flat(gt, n, h * w)
+        per = torch.empty(n, dtype=torch.float32, device=logits.device)
+        need = ctx.needs_input_grad[0]
+        fused = need and upstream_const is not None
+        grad = torch.empty_like(logits) if fused else None
+        call('pxl_ce2d', _p(logits), _p(gt), n, c, h * w, int(ignore_index), _p(per), _p(grad),
+             _p(None), float(upstream_const or 0.0), _stream())
+        ctx.fused, ctx.ignore = fused, int(ignore_index)
+        if need:
+            if fused:
+                ctx.save_for_backward(grad)
+            else:
+                ctx.save_for_backward(logits, gt)
+        return per
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.fused:
+            (grad,) = ctx.saved_tensors
+            return grad, None, None, None
+        logits, gt = ctx.saved_tensors
+        n, c, h, w = logits.shape
+        per = torch.empty(n, dtype=torch.float32, device=logits.device)
+        grad = torch.empty_like(logits)
+        g = g.contiguous().float()
+        call('pxl_ce2d', _p(logits), _p(gt), n, c, h * w, ctx.ignore, _p(per), _p(grad), _p(g), 0.0, _stream())
+        return grad, None, None, None
+
+
+def cross_entropy2d(logits, gt, ignore_index=255, upstream_const=None):
+    """CommonSSEGCriterion.forward (task/sseg/criterion.py:24-38) -> per-sample loss [n].
+
+    upstream_const: if given, the caller guarantees d total / d per_sample[i] == upstream_const
+    (e.g. 1/n when ``torch.mean`` of the result goes straight into the loss) and the gradient is
+    written by the forward launch."""
+    return _CrossEntropy2d.apply(logits.contiguous(), gt.contiguous(), ignore_index, upstream_const)
+
+
+class _Softmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits):
+        _chk(logits, 'logits')
+        n, c, h, w = logits.shape
+        prob = torch.empty_like(logits)
+        call('pxl_softmax_planar', _p(logits), _p(prob), n, c, h * w, _stream())
+        ctx.save_for_backward(prob)
+        return prob
+
+    @staticmethod
+    def backward(ctx, g):
+        (prob,) = ctx.saved_tensors
+        n, c, h, w = prob.shape
+        g = g.contiguous()
+        out = torch.empty_like(prob)
+        call('pxl_softmax_planar_bwd', _p(prob), _p(g), _p(out), n, c, h * w, _stream())
+        return out
+
+
+def softmax_planar(logits):
+    """F.softmax(pred, dim=1) on a planar map (task/sseg/model.py:62)."""
+    return _Softmax.apply(logits.contiguous())
+
+
+class _SoftmaxMse(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, tprob, loss_scale):
+        _chk(logits, 'logits'); _chk(tprob, 'tprob')
+        n, c, h, w = logits.shape
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        need = ctx.needs_input_grad[0]
+        grad = torch.empty_like(logits) if need else None
+        call('pxl_softmax_mse', _p(logits), _p(tprob), n, c, h * w, float(loss_scale), _p(loss), _p(None),
+             _p(grad), _p(_mse_ws(logits.device)), _stream())
+        if need:
+            ctx.save_for_backward(grad)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None
+
+
+def softmax_mse(logits, tprob, loss_scale=1.0):
+    """loss_scale * MSE(softmax(logits), tprob) with the gradient through the softmax produced in
+    the same pass (ssl_cutmix.py:206-215).  Backward multiplies by the upstream scalar."""
+    return _SoftmaxMse.apply(logits.contiguous(), tprob.detach().contiguous(), float(loss_scale))
+
+
+def cutmix_mix(mask, a, b):
+    """mask*a + (1-mask)*b, bit-exact with the reference's fp32 op order (ssl_cutmix.py:195,428).
+    mask: [n,1,H,W]; a, b: [n,C,H,W] planar."""
+    _chk(mask, 'mask'); _chk(a, 'a'); _chk(b, 'b')
+    n, c, h, w = a.shape
+    out = torch.empty_like(a)
+    call('pxl_cutmix_mix', _p(mask), _p(a), _p(b), _p(out), n, c, h * w, _stream())
+    return out
+
+
+def cutmix_confidence(prob, thr):
+    """mean(max_c p > thr) over the batch as a device scalar (ssl_cutmix.py:200)."""
+    _chk(prob, 'prob')
+    n, c, h, w = prob.shape
+    cnt = torch.empty(1, dtype=torch.int64, device=prob.device)
+    call('pxl_cutmix_confidence', _p(prob), n, c, h * w, float(thr), _p(cnt), _stream())
+    return cnt.to(torch.float32).reshape(()) / float(n * h * w)
+
+
+# ------------------------------------------------------------------------------------------------
+# bilinear resize
+# ------------------------------------------------------------------------------------------------
+
+class _Bilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, C, size, align_corners, in_nhwc):
+        H, W = size
+        if in_nhwc:
+            _chk(x, 'x', cl=True)
+            n, ldc, h, w = x.shape
+        else:
+            _chk(x, 'x')
+            n, ldc, h, w = x.shape
+            if ldc != C:
+                raise ValueError('planar input must have exactly C channels')
+        out = torch.empty((n, C, H, W), dtype=torch.float32, device=x.device)
+        call('pxl_bilinear_fwd', _p(x), _p(out), n, C, h, w, H, W, int(align_corners), int(in_nhwc), ldc, _stream())
+        ctx.meta = (n, C, h, w, H, W, int(align_corners), int(in_nhwc), ldc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, C, h, w, H, W, ac, nhwc, ldc = ctx.meta
+        g = g.contiguous()
+        if nhwc:
+            gin = torch.zeros((n, ldc, h, w), dtype=torch.float32, device=g.device).contiguous(memory_format=CL)
+        else:
+            gin = torch.empty((n, C, h, w), dtype=torch.float32, device=g.device)
+        call('pxl_bilinear_bwd', _p(g), _p(gin), n, C, h, w, H, W, ac, nhwc, ldc, _stream())
+        return gin, None, None, None, None
+
+
+def bilinear(x, size, align_corners=True, channels=None, nhwc=False):
+    """F.interpolate(x, size, mode='bilinear', align_corners) -> planar [n,C,H,W].
+    nhwc=False: x planar [n,C,h,w].  nhwc=True: x channels_last [n,ldc,h,w] of which the first
+    ``channels`` (<= ldc) channels are real (e.g. the 32-lane padded ASPP output)."""
+    if channels is None:
+        channels = x.shape[1]
+    x = as_cl(x) if nhwc else x.contiguous()
+    return _Bilinear.apply(x, int(channels), (int(size[0]), int(size[1])), bool(align_corners), bool(nhwc))
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------------
+
+def _taps(kh, kw, dil, pad):
+    t = []
+    for r in range(kh):
+        for s in range(kw):
+            t += [r * dil - pad, s * dil - pad]
+    return t
+
+
+def _ctaps(t):
+    return (ctypes.c_int * len(t))(*t)
+
+
+def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, out=None, precision=None):
+    """Launch pxl_conv_nhwc on raw NHWC buffers.  w_packed: [Cout][ntaps][Cin] contiguous."""
+    ntaps = len(taps) // 2
+    prec = _conv_precision if precision is None else precision
+    if out is None:
+        out = torch.empty((N, ldo, OH, OW), dtype=torch.float32, device=x.device).contiguous(memory_format=CL)
+        if ldo != Cout:
+            out.zero_()
+    geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
+    try:
+        call('pxl_conv_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(w_packed), _p(bias), _p(out), _stream())
+    except _lib.PxlError as e:
+        if e.code != _lib.PXL_ERR_UNSUPPORTED or prec == 0:
+            raise
+        geom.precision = 0          # shape not covered by the tensor-core kernel: precise FFMA kernel
+        call('pxl_conv_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(w_packed), _p(bias), _p(out), _stream())
+    return out
+
+
+def conv_wgrad_raw(x, dy, dw, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, precision=None):
+    """dw[Cout][ntaps][Cin] += ...  (dw must be initialised by the caller)."""
+    ntaps = len(taps) // 2
+    prec = _conv_precision if precision is None else precision
+    geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
+    try:
+        call('pxl_conv_wgrad_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(dy), _p(dw), _stream())
+    except _lib.PxlError as e:
+        if e.code != _lib.PXL_ERR_UNSUPPORTED or prec == 0:
+            raise
+        geom.precision = 0
+        call('pxl_conv_wgrad_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(dy), _p(dw), _stream())
+    return dw
+
+
+def transpose_weights(w_packed, Cout, T, Cin):
+    wt = torch.empty(Cin * T * Cout, dtype=torch.float32, device=w_packed.device)
+    call('pxl_conv_transpose_weights', _p(w_packed), _p(wt), Cout, T, Cin, _stream())
+    return wt
+
+
+class _Conv2d(torch.autograd.Function):
+    """nn.Conv2d on NHWC (resnet.py:18-25 etc.).  weight logical [Cout,Cin,kh,kw] channels_last."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation):
+        _chk(x, 'x', cl=True); _chk(weight, 'weight', cl=True)
+        N, Cin, H, W = x.shape
+        Cout, Cin2, kh, kw = weight.shape
+        if Cin2 != Cin:
+            raise ValueError('channel mismatch')
+        OH = (H + 2 * padding - dilation * (kh - 1) - 1) // stride + 1
+        OW = (W + 2 * padding - dilation * (kw - 1) - 1) // stride + 1
+        taps = _taps(kh, kw, dilation, padding)
+        out = conv_raw(x, weight, bias, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1)
+        ctx.save_for_backward(x, weight)
+        ctx.meta = (taps, N, H, W, Cin, OH, OW, Cout, stride, kh * kw, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        taps, N, H, W, Cin, OH, OW, Cout, stride, T, has_bias = ctx.meta
+        dy = as_cl(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wt = transpose_weights(weight, Cout, T, Cin)
+            ntaps = [-v for v in taps]
+            dx = conv_raw(dy, wt, None, ntaps, N, OH, OW, Cout, H, W, Cin, Cin, 1, stride)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros_like(weight, memory_format=torch.preserve_format)
+            conv_wgrad_raw(x, dy, dw, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(Cout, dtype=torch.float32, device=dy.device)
+            call('pxl_bias_grad', _p(dy), N * OH * OW, Cout, Cout, _p(db), 0, _stream())
+        return dx, dw, db, None, None, None
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1):
+    return _Conv2d.apply(x, weight, bias, int(stride), int(padding), int(dilation))
+
+
+class _Aspp(torch.autograd.Function):
+    """Classifier_Module.forward (deeplab_v2.py:81-85): sum of 4 dilated 3x3 convs (2048 -> C, with
+    bias) as ONE 36-tap convolution that reads the latent once.  Output: channels_last
+    [N, ldo=32, h, w] whose first C channels are the logits at latent resolution."""
+    LDO = 32
+
+    @staticmethod
+    def forward(ctx, x, dilations, *wb):
+        _chk(x, 'x', cl=True)
+        nb = len(dilations)
+        weights, biases = wb[:nb], wb[nb:]
+        N, Cin, H, W = x.shape
+        C = weights[0].shape[0]
+        ldo = max(_Aspp.LDO, (C + 3) // 4 * 4)
+        taps = []
+        for d in dilations:
+            taps += _taps(3, 3, d, d)
+        # pack [ldo][9*nb][Cin]; rows >= C stay zero (they pad the dgrad operand)
+        wp = torch.zeros((ldo, 9 * nb, Cin), dtype=torch.float32, device=x.device)
+        for i, wgt in enumerate(weights):
+            _chk(wgt, 'aspp weight', cl=True)
+            wp[:C, 9 * i:9 * i + 9] = wgt.permute(0, 2, 3, 1).reshape(C, 9, Cin)
+        bsum = biases[0]
+        for b in biases[1:]:
+            bsum = bsum + b
+        out = conv_raw(x, wp, bsum.contiguous(), taps, N, H, W, Cin, H, W, C, ldo, 1, 1)
+        ctx.save_for_backward(x, wp)
+        ctx.meta = (taps, N, H, W, Cin, C, ldo, nb)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wp = ctx.saved_tensors
+        taps, N, H, W, Cin, C, ldo, nb = ctx.meta
+        dy = as_cl(dy)          # [N, ldo, H, W]; lanes >= C are zero (bilinear backward zero-fills)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wt = transpose_weights(wp, ldo, 9 * nb, Cin)          # [Cin][36][ldo]
+            dx = conv_raw(dy, wt, None, [-v for v in taps], N, H, W, ldo, H, W, Cin, Cin, 1, 1)
+        dwp = torch.zeros((C, 9 * nb, Cin), dtype=torch.float32, device=dy.device)
+        conv_wgrad_raw(x, dy, dwp, taps, N, H, W, Cin, H, W, C, ldo, 1, 1)
+        db = torch.empty(C, dtype=torch.float32, device=dy.device)
+        call('pxl_bias_grad', _p(dy), N * H * W, C, ldo, _p(db), 0, _stream())
+        dws = [dwp[:, 9 * i:9 * i + 9].reshape(C, 3, 3, Cin).permute(0, 3, 1, 2) for i in range(nb)]
+        return (dx, None) + tuple(dws) + tuple(db for _ in range(nb))
+
+
+def aspp(x, weights, biases, dilations=(6, 12, 18, 24)):
+    return _Aspp.apply(x, tuple(dilations), *(tuple(weights) + tuple(biases)))
+
+
+class _Stem(torch.autograd.Function):
+    """conv 7x7/2 pad 3 on the planar image -> NHWC (resnet.py:69,121); no input gradient."""
+
+    @staticmethod
+    def forward(ctx, img, weight):
+        _chk(img, 'img'); _chk(weight, 'weight', cl=True)
+        N, C, H, W = img.shape
+        if C != 3 or tuple(weight.shape) != (64, 3, 7, 7):
+            raise ValueError('stem expects a 3-channel image and a [64,3,7,7] weight')
+        OH, OW = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+        out = torch.empty((N, 64, OH, OW), dtype=torch.float32, device=img.device).contiguous(memory_format=CL)
+        call('pxl_stem_conv7x7s2', _p(img), _p(weight), _p(out), N, H, W, OH, OW, _stream())
+        ctx.save_for_backward(img)
+        ctx.meta = (N, H, W, OH, OW)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (img,) = ctx.saved_tensors
+        N, H, W, OH, OW = ctx.meta
+        dy = as_cl(dy)
+        dw = torch.zeros((64, 3, 7, 7), dtype=torch.float32, device=dy.device).contiguous(memory_format=CL)
+        call('pxl_stem_conv7x7s2_wgrad', _p(img), _p(dy), _p(dw), N, H, W, OH, OW, _stream())
+        return None, dw
+
+
+def stem_conv(img, weight):
+    return _Stem.apply(img.contiguous(), weight)
+
+
+# ------------------------------------------------------------------------------------------------
+# batch norm (+ReLU, +residual), max-pool
+# ------------------------------------------------------------------------------------------------
+
+class _BnAct(torch.autograd.Function):
+    """_SynchronizedBatchNorm.forward (batchnorm.py:48-78) fused with the ReLU / residual add that
+    follow it in Bottleneck.forward (resnet.py:33-48).  ``group``: torch.distributed group whose
+    ranks share batch statistics (the reference's cross-replica SyncBN); None = local."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps, relu, group):
+        _chk(x, 'x', cl=True)
+        N, C, H, W = x.shape
+        rows = N * H * W
+        dev = x.device
+        y = torch.empty_like(x)
+        coeff = torch.empty((4, C), dtype=torch.float32, device=dev)     # mean, invstd, scale, shift
+        count = float(rows)
+        clamp = 0
+        if training:
+            sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+            call('pxl_bn_stats', _p(x), rows, C, _p(sums), _stream())
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(sums, group=group)
+                count = float(rows) * dist.get_world_size(group)
+                clamp = 1     # batchnorm.py:125: the multi-replica path clamps var instead of adding eps
+            call('pxl_bn_finalize', _p(sums), count, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                 float(momentum), float(eps), clamp, _p(coeff[0]), _p(coeff[1]), _p(coeff[2]), _p(coeff[3]), _stream())
+        else:
+            call('pxl_bn_eval_coeffs', C, _p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps),
+                 _p(coeff[2]), _p(coeff[3]), _stream())
+        if residual is not None:
+            _chk(residual, 'residual', cl=True)
+        call('pxl_bn_apply', _p(x), _p(coeff[2]), _p(coeff[3]), _p(residual), int(relu), _p(y), rows, C, _stream())
+        ctx.save_for_backward(x, y if relu else None, gamma, coeff, running_var)
+        ctx.meta = (rows, C, count, bool(relu), residual is not None, bool(training), float(eps), group)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, coeff, running_var = ctx.saved_tensors
+        rows, C, count, relu, has_res, training, eps, group = ctx.meta
+        dy = as_cl(dy)
+        dev = dy.device
+        if not training:
+            raise NotImplementedError('backward through eval-mode BN is not on the training path')
+        dsums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+        call('pxl_bn_bwd_reduce', _p(x), _p(y), _p(dy), _p(coeff[0]), _p(coeff[1]), int(relu), rows, C, _p(dsums), _stream())
+        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+        # parameter gradients use the LOCAL sums (DDP averages them with the other grads)
+        call('pxl_bn_bwd_params', _p(dsums), C, _p(dgamma), _p(dbeta), 0, _stream())
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(dsums, group=group)
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if has_res else None
+        call('pxl_bn_bwd_dx', _p(x), _p(y), _p(dy), _p(coeff[0]), _p(coeff[1]), _p(gamma), _p(dsums), count, int(relu),
+             _p(dx), _p(dres), rows, C, _stream())
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
+
+
+def bn_act(x, gamma, beta, running_mean, running_var, training=True, momentum=0.1, eps=1e-5, relu=False,
+           residual=None, group=None):
+    return _BnAct.apply(x, gamma, beta, running_mean, running_var, residual, bool(training), float(momentum),
+                        float(eps), bool(relu), group)
+
+
+class _MaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _chk(x, 'x', cl=True)
+        N, C, H, W = x.shape
+        OH, OW = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+        y = torch.empty((N, C, OH, OW), dtype=torch.float32, device=x.device).contiguous(memory_format=CL)
+        call('pxl_maxpool3x3s2_fwd', _p(x), _p(y), N, H, W, C, OH, OW, _stream())
+        ctx.save_for_backward(x)
+        ctx.meta = (N, H, W, C, OH, OW)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        N, H, W, C, OH, OW = ctx.meta
+        dy = as_cl(dy)
+        dx = torch.empty_like(x)
+        call('pxl_maxpool3x3s2_bwd', _p(x), _p(None), _p(dy), _p(dx), N, H, W, C, OH, OW, _stream())
+        return dx
+
+
+def maxpool3x3s2(x):
+    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC (resnet.py:72)."""
+    return _MaxPool.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# optimiser / EMA on flat arenas
+# ------------------------------------------------------------------------------------------------
+
+def sgd_ema_(p, g, buf, teacher, lr, momentum, weight_decay, ema_d, first_step):
+    call('pxl_sgd_ema', _p(p), _p(g), _p(buf), _p(teacher), p.numel(), float(lr), float(momentum),
+         float(weight_decay), float(ema_d), int(first_step), _stream())
+
+
+def ema_(teacher, student, ema_d):
+    call('pxl_ema', _p(teacher), _p(student), teacher.numel(), float(ema_d), _stream())
+
+
+def launch_count():
+    return int(_lib.load().pxl_launch_count())
+
+
+def reset_launch_count():
+    _lib.load().pxl_reset_launch_count()
