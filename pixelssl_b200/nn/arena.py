@@ -1,0 +1,147 @@
+"""Flat HBM parameter arena + the fused optimiser/EMA step + the data-parallel wrapper.
+
+Reference mechanism being replaced: ``nn.DataParallel`` (nn/func.py:58-59) re-broadcasting 176 MB
+of parameters every forward, ``torch.optim.SGD`` + a 320-tensor Python EMA loop
+(ssl_mt.py:359-363).  Here: every parameter is a view into ONE contiguous fp32 buffer (same for
+gradients and momentum), SGD+EMA is one kernel per learning-rate group, and multi-GPU is one
+process per GPU with a single NCCL all-reduce of the flat gradient buffer."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class ParamArena:
+    def __init__(self, module):
+        params = [p for p in module.parameters()]
+        self.params = params
+        dev = params[0].device
+        total = sum(p.numel() for p in params)
+        # 16-byte aligned segments so per-parameter kernels may use 128-bit accesses
+        offs, cur = [], 0
+        for p in params:
+            offs.append(cur)
+            cur += (p.numel() + 3) // 4 * 4
+        self.numel = cur
+        self.offsets = offs
+        self.data = torch.zeros(cur, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(cur, dtype=torch.float32, device=dev)
+        self.mom = None
+        self.steps = 0
+        self._index = {}
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                n = p.numel()
+                view = self._view_like(self.data, o, p)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self._view_like(self.grad, o, p)
+                self._index[id(p)] = (o, n)
+
+    @staticmethod
+    def _view_like(flat, off, p):
+        """A view of flat[off:off+numel] with p's shape AND p's physical layout."""
+        n = p.numel()
+        seg = flat[off:off + n]
+        if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
+            o, i, h, w = p.shape
+            return seg.view(o, h, w, i).permute(0, 3, 1, 2)
+        return seg.view(p.shape)
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self._view_like(self.grad, o, p)
+
+    def segments(self, group_params):
+        """Merge the arena ranges of ``group_params`` into maximal contiguous [start, end) runs."""
+        spans = sorted(self._index[id(p)] for p in group_params)
+        runs = []
+        for o, n in spans:
+            end = o + (n + 3) // 4 * 4
+            if runs and runs[-1][1] == o:
+                runs[-1][1] = end
+            else:
+                runs.append([o, end])
+        return [(a, min(b, self.numel)) for a, b in runs]
+
+    def all_reduce_grads(self, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.grad, group=group)
+            self.grad.div_(dist.get_world_size(group))
+
+    def sgd_step(self, optimizer, teacher=None, ema_d=0.0):
+        """torch.optim.SGD.step() semantics (momentum, weight decay, dampening 0, no nesterov) read
+        from ``optimizer.param_groups`` (so LR schedulers keep working), fused with the teacher
+        EMA (ssl_mt.py:359-363) when ``teacher`` (a ParamArena with identical layout) is given."""
+        if self.mom is None:
+            self.mom = torch.zeros_like(self.data)
+        first = self.steps == 0
+        for g in optimizer.param_groups:
+            if g.get('nesterov', False) or g.get('dampening', 0) != 0 or g.get('maximize', False):
+                raise NotImplementedError('fused SGD supports dampening=0, nesterov=False only')
+            mom = g.get('momentum', 0.0)
+            for a, b in self.segments(g['params']):
+                ops.sgd_ema_(self.data[a:b], self.grad[a:b], self.mom[a:b],
+                             teacher.data[a:b] if teacher is not None else None,
+                             g['lr'], mom, g.get('weight_decay', 0.0), ema_d, first or mom == 0)
+        if first:
+            for g in optimizer.param_groups:
+                if g.get('momentum', 0.0) != 0:
+                    for p in g['params']:
+                        o, n = self._index[id(p)]
+                        optimizer.state[p]['momentum_buffer'] = self._view_like(self.mom, o, p)
+        self.steps += 1
+
+
+    def adopt_optimizer_state(self, optimizer):
+        """After ``optimizer.load_state_dict`` (resume): pull the loaded momentum buffers into the
+        flat arena and point the optimizer state back at the arena views."""
+        found = False
+        for g in optimizer.param_groups:
+            for p in g['params']:
+                buf = optimizer.state.get(p, {}).get('momentum_buffer')
+                if buf is not None:
+                    if self.mom is None:
+                        self.mom = torch.zeros_like(self.data)
+                    o, n = self._index[id(p)]
+                    view = self._view_like(self.mom, o, p)
+                    view.copy_(buf)
+                    optimizer.state[p]['momentum_buffer'] = view
+                    found = True
+        if found:
+            self.steps = max(self.steps, 1)
+
+
+class EngineParallel(nn.Module):
+    """Stands where ``nn.DataParallel`` stood (nn/func.py:58): holds the task model as ``.module``.
+    One process drives one GPU; with torch.distributed initialised (world_size > 1) parameters are
+    broadcast from rank 0 at construction, BN layers share statistics over NCCL and
+    ``arena.all_reduce_grads()`` averages gradients."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+        self.arena = None
+
+    def cuda(self, device=None):
+        super().cuda(device)
+        self.arena = ParamArena(self.module)
+        self._setup_distributed()
+        return self
+
+    def _setup_distributed(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.broadcast(self.arena.data, src=0)
+            for b in self.module.buffers():
+                dist.broadcast(b, src=0)
+            from .modules import BatchNorm2d
+            for m in self.module.modules():
+                if isinstance(m, BatchNorm2d):
+                    m.sync_group = dist.group.WORLD
+
+    def forward(self, *inputs, **kwargs):
+        return self.module(*inputs, **kwargs)

@@ -1,0 +1,68 @@
+"""nn.Module shells around the CUDA ops.  They only hold parameters (in the physical layouts the
+kernels want) under the same attribute names as torch's modules, so ``state_dict`` keys and
+shapes equal the reference's checkpoints."""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+CL = torch.channels_last
+
+
+class Conv2d(nn.Module):
+    """nn.Conv2d replacement: weight is logical [Cout,Cin,kh,kw], stored channels_last
+    (= [Cout][kh*kw][Cin], the K-major operand of the implicit GEMM)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size = (kernel_size, kernel_size)
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        w = torch.empty(out_channels, in_channels, kernel_size, kernel_size).contiguous(memory_format=CL)
+        nn.init.kaiming_uniform_(w, a=math.sqrt(5))        # nn.Conv2d default
+        self.weight = nn.Parameter(w)
+        if bias:
+            bound = 1 / math.sqrt(in_channels * kernel_size * kernel_size)
+            self.bias = nn.Parameter(torch.empty(out_channels).uniform_(-bound, bound))
+        else:
+            self.register_parameter('bias', None)
+
+    def forward(self, x):
+        return ops.conv2d(ops.as_cl(x), self.weight, self.bias, self.stride, self.padding, self.dilation)
+
+    def extra_repr(self):
+        return '{in_channels}, {out_channels}, kernel_size={kernel_size}, stride={stride}, padding={padding}, ' \
+               'dilation={dilation}'.format(**self.__dict__)
+
+
+class BatchNorm2d(nn.Module):
+    """SynchronizedBatchNorm2d of the reference (sync_batchnorm/batchnorm.py:180): momentum 0.1,
+    eps 1e-5, affine.  ``forward(x, relu=False, residual=None)`` fuses what follows the BN in
+    Bottleneck.forward.  Across processes the batch statistics are all-reduced over
+    ``sync_group`` (set by EngineParallel when torch.distributed has world_size > 1), which is the
+    reference's cross-replica reduction (batchnorm.py:55-78) over NCCL instead of Python threads."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.weight = nn.Parameter(torch.ones(num_features))
+        self.bias = nn.Parameter(torch.zeros(num_features))
+        self.register_buffer('running_mean', torch.zeros(num_features))
+        self.register_buffer('running_var', torch.ones(num_features))
+        self.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
+        self.sync_group = None
+
+    def forward(self, x, relu=False, residual=None):
+        if self.training:
+            self.num_batches_tracked += 1
+        return ops.bn_act(ops.as_cl(x), self.weight, self.bias, self.running_mean, self.running_var,
+                          training=self.training, momentum=self.momentum, eps=self.eps, relu=relu,
+                          residual=residual, group=self.sync_group if self.training else None)
+
+    def extra_repr(self):
+        return '{num_features}, eps={eps}, momentum={momentum}'.format(**self.__dict__)
+
+
+SynchronizedBatchNorm2d = BatchNorm2d

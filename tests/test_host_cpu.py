@@ -1,0 +1,124 @@
+"""CPU-side tests (-m "not gpu"): the C-ABI library loads and exports every symbol the header
+declares (no compute calls), and the host logic of the engine (argument system, LR schedule,
+ramp-up, CutMix mask generator, flat parameter arena, plugin registration) behaves like the
+reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, 'tests', 'golden')
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from pixelssl_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'pixelssl_b200.h')).read()
+    declared = set(re.findall(r'\b(pxl_[a-z0-9_]+)\s*\(', header))
+    declared -= {'pxl_conv_geom'}
+    assert declared, 'no declarations parsed'
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), 'missing export: ' + name
+    # the ctypes table covers exactly the header
+    assert set(_lib.SIGNATURES) == declared
+    assert _lib.load().pxl_abi_version() == 1
+
+
+def test_ops_fail_loudly_without_cuda():
+    from pixelssl_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(TypeError):
+        ops.mse_consistency_raw(torch.zeros(8), torch.zeros(8))
+
+
+def test_rampup_and_poly_lr_match_golden():
+    from pixelssl_b200.nn import func, lrer
+    g = np.load(os.path.join(G, 'ops.npz'))
+    mine = [func.sigmoid_rampup(c, 30) for c in range(0, 40, 3)] + [func.sigmoid_rampup(5, 0)]
+    np.testing.assert_allclose(mine, g['rampup'], rtol=1e-12)
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([{'params': [p], 'lr': 0.00025}], lr=0.00025, momentum=0.9)
+    sch = lrer.PolynomialLR(opt, epochs=2, iters_per_epoch=5, power=0.9)
+    lrs = [opt.param_groups[0]['lr']]
+    for _ in range(8):
+        opt.step()
+        sch.step()
+        lrs.append(opt.param_groups[0]['lr'])
+    np.testing.assert_allclose(lrs, g['poly_lr'], rtol=1e-12)
+
+
+def test_box_mask_generator_bit_exact():
+    from pixelssl_b200.ssl_algorithm.ssl_cutmix import BoxMaskGenerator
+    g = np.load(os.path.join(G, 'ops.npz'))
+    np.random.seed(1234)
+    masks = BoxMaskGenerator((0.5, 0.5)).produce(4, (65, 97))
+    assert masks.dtype == np.float32 and np.array_equal(masks, g['cutmix_masks'])
+    np.random.seed(99)
+    full = BoxMaskGenerator((0.25, 0.5)).produce(3, (513, 513))
+    assert np.array_equal(full.reshape(3, 513, 513)[:, ::8, ::8], g['cutmix_masks_b'])
+    assert np.array_equal(full.reshape(3, -1).sum(1), g['cutmix_masks_b_sum'])
+    # empty / degenerate: zero masks requested
+    assert BoxMaskGenerator((0.5, 0.5)).produce(0, (9, 9)).shape == (0, 1, 9, 9)
+
+
+def test_build_args_and_autoset_fields():
+    import pixelssl_b200
+    a = pixelssl_b200.build_args({'ssl_algorithm': 'ssl_mt', 'cons_for_labeled': False, 'cons_scale': 1.0,
+                                  'cons_rampup_epochs': 3, 'ema_decay': 0.99, 'lr': 0.00025, 'momentum': 0.9,
+                                  'weight_decay': 0.0005, 'epochs': 20, 'batch_size': 16, 'unlabeled_batch_size': 8,
+                                  'models': {'model': 'deeplabv2'}}, iters_per_epoch=7)
+    assert (a.labeled_batch_size, a.iters_per_epoch, a.is_epoch_lrer, a.num_classes, a.ignore_index) == (8, 7, False, 21, 255)
+    assert a.cons_for_labeled is False and a.models == {'model': 'deeplabv2'}
+    with pytest.raises(SystemExit):     # log_err convention: print + exit
+        pixelssl_b200.create_parser('ssl_unknown')
+
+
+def test_param_arena_layout_and_segments():
+    from pixelssl_b200.nn.arena import ParamArena
+    from pixelssl_b200.nn.modules import Conv2d, BatchNorm2d
+    net = torch.nn.Sequential(Conv2d(3, 8, 3, bias=False), BatchNorm2d(8), Conv2d(8, 5, 1, bias=True))
+    ref = {n: p.detach().clone() for n, p in net.named_parameters()}
+    arena = ParamArena(net)
+    for n, p in net.named_parameters():
+        assert torch.equal(p, ref[n])                      # values preserved
+        assert p.data_ptr() >= arena.data.data_ptr() and p.grad is not None
+        if p.dim() == 4:
+            assert p.is_contiguous(memory_format=torch.channels_last)
+    # a 3x3 weight written through the parameter lands [Cout][kh][kw][Cin] in the flat buffer
+    w = net[0].weight
+    w.data[1, 2, 0, 1] = 42.0
+    assert arena.data[arena.offsets[0] + ((1 * 3 + 0) * 3 + 1) * 3 + 2] == 42.0
+    # gradient accumulation from autograd lands in the flat gradient buffer
+    arena.zero_grad()
+    (w * 2).sum().backward()
+    assert float(arena.grad[:w.numel()].sum()) == 2.0 * w.numel()
+    groups = [list(net[0].parameters()) + list(net[1].parameters()), list(net[2].parameters())]
+    segs = [arena.segments(g) for g in groups]
+    assert segs[0] == [(0, arena.offsets[3])] and segs[1][0][0] == arena.offsets[3]
+    assert sum(b - a for s in segs for a, b in s) == arena.numel
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree only exists in the build container')
+def test_register_into_unmodified_pixelssl():
+    import sys
+    sys.path.insert(0, '/root/reference')
+    import pixelssl
+    import pixelssl_b200
+    pixelssl_b200.register_into_pixelssl(pixelssl)
+    for name in pixelssl_b200.SSL_ALGORITHMS:
+        mod = pixelssl.ssl_algorithm.__dict__[name]
+        assert mod.__name__.startswith('pixelssl_b200.')
+        assert callable(getattr(mod, name)) and callable(mod.add_parser_arguments)
+        assert name in pixelssl.ssl_algorithm.SSL_ALGORITHMS
+    # the reference's own parser builder accepts the engine's algorithm modules
+    from pixelssl import runner
+    parser = runner.create_parser('ssl_mt')
+    ns = parser.parse_args(['--cons-scale', '1.0', '--ema-decay', '0.99'])
+    assert ns.cons_scale == 1.0 and ns.ema_decay == 0.99
