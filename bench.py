@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Benchmark of the PixelSSL sseg SSL-training hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): Mean-Teacher, DeepLab-v2-ResNet101 OS16, per-GPU batch 16
+(8 labeled + 8 unlabeled) of 513x513 synthetic images, 21 classes, cons_for_labeled=False,
+cons_scale 1, ema_decay .99, SGD(2.5e-4, .9, 5e-4) + PolynomialLR - weak scaling over GPUs.
+A "step" is one full ``SSLMT.train_step``: zero_grad, student fwd, CE, teacher fwd, MSE
+consistency, backward, gradient all-reduce (N>1), fused SGD+EMA, LR step.
+
+Printed JSON line (rank 0): see the contract in the task statement.  ``value`` times the step
+with the batch already in HBM; ``e2e`` times the same public call with pinned HOST batches
+(H2D inside the timed region) plus a D2H read of the step's loss.  ``roofline`` is for the
+metric kernel (fused MSE consistency fwd+bwd, 12 B/element), timed live with CUDA events around
+each of its launches inside the timed steps.  ``cpu_baseline`` / ``--impl reference`` time the
+CPU oracle port of the reference step (torch CPU fp32, all host threads) on a bounded sample."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 513
+LBS, UBS = 8, 8
+NUM_CLASSES = 21
+MT_FLOP_PER_IMG = 451e9          # student fwd+bwd 338.4 + teacher fwd 112.8 GFLOP
+
+
+def mt_config():
+    return {'ssl_algorithm': 'ssl_mt', 'cons_for_labeled': False, 'cons_scale': 1.0, 'cons_rampup_epochs': 3,
+            'ema_decay': 0.99, 'lr': 0.00025, 'momentum': 0.9, 'weight_decay': 0.0005, 'epochs': 20,
+            'batch_size': LBS + UBS, 'unlabeled_batch_size': UBS, 'output_stride': 16, 'backbone': 'resnet101',
+            'log_freq': 10 ** 9}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops_sustained', 1400.0), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def synthetic_host_batches(count, rank, pin):
+    import torch
+    g = torch.Generator().manual_seed(1234 + rank)
+    out = []
+    for _ in range(count):
+        img = torch.randn(LBS + UBS, 3, H, W, generator=g)
+        lab = torch.randint(0, NUM_CLASSES, (LBS + UBS, 1, H, W), generator=g).float()
+        ign = torch.rand(LBS + UBS, 1, H, W, generator=g) < 0.05
+        lab[ign] = 255.0
+        lab[LBS:] = -1.0
+        if pin:
+            img, lab = img.pin_memory(), lab.pin_memory()
+        out.append((img, lab))
+    return out
+
+
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import pixelssl_b200
+    from pixelssl_b200 import runner, ops
+    ops.set_conv_precision(args.precision)
+    torch.manual_seed(0)
+    cfg = mt_config()
+    a = runner.build_args(cfg, iters_per_epoch=662)
+    import logging
+    logging.getLogger('PixelSSL').setLevel(logging.ERROR)
+    alg = runner.build_algorithm(a)
+    alg.s_model.train(); alg.t_model.train()
+    total_rampup = a.iters_per_epoch * a.cons_rampup_epochs
+    nb = 4
+    host = synthetic_host_batches(nb, rank, pin=True)
+    dev = [(i.cuda(), l.cuda()) for i, l in host]
+    step_no = [0]
+
+    def step(batch):
+        img, lab = batch
+        alg.train_step((img,), (lab,), step_no[0], total_rampup)
+        alg.s_lrer.step()
+        step_no[0] += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batches, read_loss):
+        for i in range(args.warmup):
+            step(batches[i % nb])
+            if read_loss:
+                float(alg.meters['s_task_loss'].val)
+        barrier()
+        ops.reset_launch_count()
+        ops.kernel_timer_start('pxl_mse_consistency')
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step(batches[i % nb])
+            if read_loss:
+                float(alg.meters['s_task_loss'].val) + float(alg.meters['cons_loss'].val)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        ktimes = ops.kernel_timer_stop('pxl_mse_consistency')
+        launches = ops.launch_count()
+        t = torch.tensor([ms], device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t), ktimes, launches
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_dev, ktimes, launches = timed(dev, read_loss=False)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _, _ = timed(host, read_loss=True)
+
+    imgs = (LBS + UBS) * world * args.steps
+    value = imgs / (ms_dev / 1e3)
+    e2e = imgs / (ms_e2e / 1e3)
+    hbm_peak, tf_peak, peak_src = measured_peaks()
+    n_elem = UBS * NUM_CLASSES * H * W
+    k_ms = sum(ktimes) / max(len(ktimes), 1) if ktimes else float('nan')
+    achieved = 12.0 * n_elem / (k_ms * 1e-3) / 1e9 if ktimes else None
+    out = {
+        'metric': 'images/sec DeepLab-v2-R101 MT 513x513 bs16', 'value': value, 'unit': 'images/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'tf32x3': 'tf32x3'}[args.precision], 'data': 'synthetic',
+        'config': {'workload': 'MT (ssl_mt) DeepLab-v2-ResNet101 OS16, per-GPU batch 16 = 8 labeled + 8 unlabeled, '
+                               '513x513x3 synthetic, 21 classes, cons_for_labeled=False (BASELINE.json configs[1])',
+                   'global_batch': (LBS + UBS) * world, 'parallelism': 'dp%d' % world,
+                   'conv_precision': args.precision, 'weights': 'random init (reference initialisers)',
+                   'l2': 'inputs and activations (>20 GB/step) far exceed the 126 MB L2; no explicit flush'},
+        'e2e': {'value': e2e, 'unit': 'images/s',
+                'h2d_bytes_per_step': (LBS + UBS) * (3 + 1) * H * W * 4, 'd2h_bytes_per_step': 8},
+        'gpu_launches': launches,
+        'clocks': clocks,
+        'roofline': {'kernel': 'mse_vec_kernel<true> (pxl_mse_consistency, fused fwd+bwd)', 'bound': 'hbm',
+                     'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                     'frac': (achieved / hbm_peak) if achieved else None, 'traffic': None,
+                     'algorithmic_bytes_per_launch': 12.0 * n_elem, 'avg_launch_ms': k_ms,
+                     'launches_timed': len(ktimes), 'peak_source': peak_src},
+        'step_tflops': {'algorithmic_flop_per_step_per_gpu': MT_FLOP_PER_IMG * (LBS + UBS),
+                        'achieved_tflops_per_gpu': MT_FLOP_PER_IMG * (LBS + UBS) / (ms_dev / args.steps / 1e3) / 1e12,
+                        'bf16_peak_tflops': tf_peak},
+    }
+    traffic_path = os.path.join(ROOT, 'profiles', 'mse_traffic.json')
+    if os.path.exists(traffic_path):
+        out['roofline']['traffic'] = json.load(open(traffic_path)).get('dram_bytes_per_launch')
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            out['cpu_baseline'] = cpu_reference(steps=2, warmup=1, lbs=1, ubs=1)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_reference(steps, warmup, lbs, ubs):
+    """The reference's CPU path restated by the oracle (torch CPU fp32; the Python reference itself
+    cannot travel to the GPU box), all host threads, on a bounded sample of the workload."""
+    import torch
+    from oracle import sseg_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    s, t = O.init_deeplabv2(0), O.init_deeplabv2(1)
+    mt = O.MTOracle(s, t, lr=0.00025, momentum=0.9, weight_decay=0.0005, max_iters=20 * 662, cons_scale=1.0,
+                    rampup_steps=3 * 662, ema_decay=0.99, cons_for_labeled=False)
+    batches = [O.synthetic_batch(1234 + i, lbs + ubs, lbs, H, W) for i in range(2)]
+    for i in range(warmup):
+        mt.step(batches[i % 2][0], batches[i % 2][1], lbs)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        mt.step(batches[i % 2][0], batches[i % 2][1], lbs)
+    dt = time.perf_counter() - t0
+    return {'value': (lbs + ubs) * steps / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d MT steps (after %d warm-up) of DeepLab-v2-R101 at batch %d+%d (labeled+unlabeled), '
+                      '513x513, torch CPU fp32, %d threads' % (steps, warmup, lbs, ubs, cores),
+            'seconds': dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    cb = cpu_reference(steps=args.steps, warmup=min(args.warmup, 1) if args.steps > 3 else args.warmup, lbs=1, ubs=1)
+    out = {'impl': 'reference', 'metric': 'images/sec DeepLab-v2-R101 MT 513x513 bs16', 'value': cb['value'],
+           'unit': 'images/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', args.gpus)), 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': cb['seconds'] / args.steps * 1e3, 'higher_is_better': True,
+           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': 'MT (ssl_mt) DeepLab-v2-ResNet101 OS16 513x513 synthetic, CPU oracle port of the '
+                                  'reference step; bounded sample: batch 1 labeled + 1 unlabeled per step',
+                      'global_batch': 2, 'parallelism': 'cpu'},
+           'cpu_baseline': cb,
+           'e2e': {'value': cb['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+           'gpu_launches': 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', type=str, default='engine', choices=['engine', 'reference'])
+    ap.add_argument('--precision', type=str, default=os.environ.get('PXL_CONV_PRECISION', 'fp32'),
+                    choices=['fp32', 'tf32', 'tf32x3'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'engine':
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == '__main__':
+    main()

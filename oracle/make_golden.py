@@ -297,11 +297,66 @@ def golden_null_cutmix(pixelssl, sseg_proxy, size=65):
     print('cutmix golden:', rec['task_loss'], rec['cons_loss'])
 
 
+def golden_fp64():
+    """Exact-arithmetic (fp64) evaluation of the SAME steps with the oracle, to measure the
+    reference's own fp32 rounding noise on these (ill-conditioned, random-init) networks.  The GPU
+    engine is held to that yardstick (tests/test_gpu_model.py).  Needs no reference import."""
+    D = torch.float64
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    rec = {}
+    # forward (deeplabv2_forward_129.npz)
+    st = O.to_dtype(O.randomize_bn_affine(O.init_deeplabv2(31, cls_bias_std=0.01), 32), D)
+    img, _ = O.synthetic_batch(200, 2, 2, 129, 129)
+    with torch.no_grad():
+        logits, latent = O.deeplabv2_forward(img.to(D), st, True)
+    rec['fwd_logits'] = logits.float().numpy()
+    rec['fwd_latent_checksum'] = checksums([('l', latent)])
+    # MT steps (mt_steps_97.npz)
+    s = O.to_dtype(O.randomize_bn_affine(O.init_deeplabv2(11, cls_bias_std=0.01), 12), D)
+    t = O.to_dtype(O.randomize_bn_affine(O.init_deeplabv2(21, cls_bias_std=0.01), 22), D)
+    mt = O.MTOracle(s, t, lr=0.00025, momentum=0.9, weight_decay=0.0005, max_iters=10,
+                    cons_scale=1.0, rampup_steps=1, ema_decay=0.99, cons_for_labeled=False)
+    for k in range(3):
+        img, lab = O.synthetic_batch(100 + k, 4, 2, 97, 97)
+        out = mt.step(img.to(D), lab.to(D), 2)
+        for key in ('s_task_loss', 't_task_loss', 'cons_loss'):
+            rec['mt_%s_%d' % (key, k)] = float(out[key])
+        rec['mt_grad_checksum_%d' % k] = checksums([(n, out['grads'][n]) for n in names])
+        rec['mt_s_param_checksum_%d' % k] = checksums([(n, mt.s[n]) for n in names])
+        rec['mt_t_param_checksum_%d' % k] = checksums([(n, mt.t[n]) for n in names])
+        for n in SAMPLE_PARAMS:
+            rec['mt_grad_%d/%s' % (k, n)] = sample_of(out['grads'][n].float())
+    # SupOnly step (null_step_65.npz)
+    s = O.to_dtype(O.randomize_bn_affine(O.init_deeplabv2(41, cls_bias_std=0.01), 42), D)
+    sup = O.MTOracle(s, None, lr=0.00025, momentum=0.9, weight_decay=0.0005, max_iters=10)
+    img, lab = O.synthetic_batch(300, 2, 2, 65, 65)
+    out = sup.step(img.to(D), lab.to(D), 2)
+    rec['null_task_loss'] = float(out['s_task_loss'])
+    rec['null_grad_checksum'] = checksums([(n, out['grads'][n]) for n in names])
+    rec['null_param_checksum'] = checksums([(n, sup.s[n]) for n in names])
+    # CutMix step (cutmix_step_65.npz)
+    s = O.to_dtype(O.randomize_bn_affine(O.init_deeplabv2(51, cls_bias_std=0.01), 52), D)
+    t = O.to_dtype(O.randomize_bn_affine(O.init_deeplabv2(61, cls_bias_std=0.01), 62), D)
+    cm = O.CutMixOracle(s, t, lr=0.00025, momentum=0.9, weight_decay=0.0005, max_iters=10, cons_scale=20.0,
+                        rampup_steps=0, ema_decay=0.99, cons_threshold=0.05)
+    img, lab = O.synthetic_batch(400, 6, 2, 65, 65)
+    out = cm.step(img.to(D), lab.to(D), 2, np.random.RandomState(4321))
+    rec['cutmix_task_loss'], rec['cutmix_cons_loss'] = float(out['task_loss']), float(out['cons_loss'])
+    rec['cutmix_grad_checksum'] = checksums([(n, out['grads'][n]) for n in names])
+    rec['cutmix_s_param_checksum'] = checksums([(n, cm.s[n]) for n in names])
+    rec['cutmix_t_param_checksum'] = checksums([(n, cm.t[n]) for n in names])
+    np.savez_compressed(os.path.join(OUT, 'fp64_truth.npz'), **rec)
+    print('fp64 truth written')
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     pixelssl, sseg_proxy = patch_and_import()
-    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix']
+    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'fp64']
+    if which == ['fp64']:
+        golden_fp64()
+        sys.exit(0)
     if 'ops' in which:
         golden_ops(pixelssl, sseg_proxy)
     if 'forward' in which:
@@ -310,3 +365,5 @@ if __name__ == '__main__':
         golden_mt(pixelssl, sseg_proxy)
     if 'nullcutmix' in which:
         golden_null_cutmix(pixelssl, sseg_proxy)
+    if 'fp64' in which:
+        golden_fp64()

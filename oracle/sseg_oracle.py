@@ -460,6 +460,58 @@ class MTOracle:
         return out
 
 
+class CutMixOracle(MTOracle):
+    """Functional restatement of ``SSLCUTMIX._train``'s loop body (ssl_cutmix.py:140-251) and
+    ``_batch_prehandle`` (:383-432): labeled rows -> student -> CE; unlabeled rows -> teacher
+    (no grad) -> softmax -> halves mixed with the box mask -> one confidence scalar; mixed
+    images -> student -> MSE(softmax, mixed pseudo label) * confidence * rampup * cons_scale."""
+
+    def __init__(self, *a, cons_threshold=0.97, mask_prop_range=(0.5, 0.5), **k):
+        super().__init__(*a, **k)
+        self.thr, self.prop = cons_threshold, mask_prop_range
+
+    def step(self, img, gt, lbs, rng):
+        ubs = img.shape[0] - lbs
+        half = ubs // 2
+        for n in self.names:
+            self.s[n].requires_grad_(True)
+            self.s[n].grad = None
+        masks, _ = box_masks(rng, half, tuple(img.shape[2:]), prop_range=self.prop)
+        mask = torch.from_numpy(masks).to(img.dtype)
+        mix_inp = cutmix_mix(mask, img[lbs:lbs + half], img[lbs + half:lbs + ubs])
+        l_logits, _ = deeplabv2_forward(img[:lbs], self.s, True, self.os, self.blocks)
+        task = sseg_criterion(l_logits, gt[:lbs], self.ignore).mean()
+        with torch.no_grad():
+            t_logits, _ = deeplabv2_forward(img[lbs:lbs + ubs], self.t, True, self.os, self.blocks)
+            t_prob = channel_softmax(t_logits)
+            mp = cutmix_mix(mask, t_prob[:half], t_prob[half:ubs])
+            conf = cutmix_confidence(mp, self.thr).to(img.dtype)
+        u_logits, _ = deeplabv2_forward(mix_inp, self.s, True, self.os, self.blocks)
+        ramp = sigmoid_rampup(self.step_idx, self.rampup_steps)
+        cons = ramp * self.cons_scale * (F.mse_loss(channel_softmax(u_logits), mp) * conf)
+        (task + cons).backward()
+        grads = [self.s[n].grad for n in self.names]
+        out = {'task_loss': task.detach(), 'cons_loss': cons.detach(), 'confidence': conf,
+               'grads': {n: g.detach().clone() for n, g in zip(self.names, grads)}}
+        lrs = [poly_lr(self.base_lr * m, self.cur_iter, self.max_iters, self.power) for m in self.mult]
+        with torch.no_grad():
+            for n in self.names:
+                self.s[n].requires_grad_(False)
+            sgd_momentum_step([self.s[n] for n in self.names], grads, self.bufs, lrs,
+                              self.momentum, self.wd, first_step=(self.step_idx == 0))
+            ema_update([self.t[n] for n in self.names], [self.s[n] for n in self.names],
+                       self.ema_decay, self.step_idx)
+        self.cur_iter += 1
+        self.step_idx += 1
+        return out
+
+
+def to_dtype(state, dtype):
+    """Cast a model state (floating tensors only) - used for the fp64 'exact arithmetic' runs that
+    measure how far the reference's own fp32 evaluation is from the true value."""
+    return {k: (v.to(dtype) if v.is_floating_point() else v.clone()) for k, v in state.items()}
+
+
 def synthetic_batch(seed, batch, lbs, h, w, num_classes=21, ignore_frac=0.05, ignore_index=255):
     """SURVEY.md 8(d) synthetic inputs: randn images (ImageNet-normalised look-alike,
     task/sseg/data.py:99), integer-valued float labels with ~5% ignore pixels on the labeled

@@ -27,6 +27,7 @@ struct MseWorkspace {
     double partial[MSE_MAX_BLOCKS];
     unsigned int ticket;
     unsigned int pad[3];
+    double scalar_acc;      // accumulator of the softmax+MSE kernel, kept zero between launches
 };
 
 extern "C" int64_t pxl_mse_workspace_bytes(void) { return (int64_t)sizeof(MseWorkspace); }
@@ -377,7 +378,7 @@ extern "C" int pxl_softmax_mse(const float* s_logits, const float* t_prob, int n
     const double N = (double)n * C * (double)HW;
     const float gscale = (float)(2.0 * loss_scale / N);
     dim3 grid((unsigned)pxl_cdiv(HW, 256), (unsigned)n);
-    double* acc = &ws->partial[MSE_MAX_BLOCKS - 1];  // kept zero between launches
+    double* acc = &ws->scalar_acc;
     if (prob_out && grad_logits) softmax_mse_kernel<true, true><<<grid, 256, 0, st>>>(s_logits, t_prob, C, HW, gscale, prob_out, grad_logits, acc);
     else if (prob_out) softmax_mse_kernel<true, false><<<grid, 256, 0, st>>>(s_logits, t_prob, C, HW, gscale, prob_out, nullptr, acc);
     else if (grad_logits) softmax_mse_kernel<false, true><<<grid, 256, 0, st>>>(s_logits, t_prob, C, HW, gscale, nullptr, grad_logits, acc);

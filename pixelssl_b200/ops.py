@@ -53,6 +53,31 @@ def as_cl(t):
 
 
 _workspaces = {}
+_ktimers = {}
+
+
+def kernel_timer_start(name):
+    """Record CUDA events (on the launching stream) around every subsequent launch of the named
+    entry point; bench.py uses it to time the metric kernel inside the timed steps."""
+    _ktimers[name] = []
+
+
+def kernel_timer_stop(name):
+    pairs = _ktimers.pop(name, [])
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in pairs]
+
+
+def _timed_call(name, *args):
+    rec = _ktimers.get(name)
+    if rec is None:
+        return call(name, *args)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    rc = call(name, *args)
+    b.record()
+    rec.append((a, b))
+    return rc
 
 
 def _mse_ws(device):
@@ -75,8 +100,8 @@ def mse_consistency_raw(s, t, loss_scale=1.0, want_grad=True):
         raise ValueError('shape mismatch')
     loss = torch.empty(1, dtype=torch.float32, device=s.device)
     grad = torch.empty_like(s) if want_grad else None
-    call('pxl_mse_consistency', _p(s), _p(t), s.numel(), float(loss_scale), _p(loss), _p(grad),
-         _p(_mse_ws(s.device)), _stream())
+    _timed_call('pxl_mse_consistency', _p(s), _p(t), s.numel(), float(loss_scale), _p(loss), _p(grad),
+                _p(_mse_ws(s.device)), _stream())
     return loss, grad
 
 
@@ -231,7 +256,7 @@ def cutmix_confidence(prob, thr):
     n, c, h, w = prob.shape
     cnt = torch.empty(1, dtype=torch.int64, device=prob.device)
     call('pxl_cutmix_confidence', _p(prob), n, c, h * w, float(thr), _p(cnt), _stream())
-    return cnt.to(torch.float32).reshape(()) / float(n * h * w)
+    return (cnt.to(torch.float64).reshape(()) / float(n * h * w)).to(torch.float32)   # correctly rounded count/N
 
 
 # ------------------------------------------------------------------------------------------------

@@ -159,3 +159,42 @@ def test_mt_steps_match_reference_train_body():
             # discontinuous function of fp32 noise; 2e-3 holds on steps 0-1, 2e-2 on step 2
             tol = 2e-3 if k < 2 else 2e-2
             assert np.abs(mine - ref).max() <= tol * np.abs(ref).max() + 1e-12, (k, n)
+
+
+@pytest.mark.slow
+def test_null_and_cutmix_steps_match_reference_train_bodies():
+    """ssl_null.py:78-144 and ssl_cutmix.py:140-251 (masks from the same numpy seed)."""
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    g = load('null_step_65.npz')
+    s = O.randomize_bn_affine(O.init_deeplabv2(41, cls_bias_std=0.01), 42)
+    sup = O.MTOracle(s, None, lr=0.00025, momentum=0.9, weight_decay=0.0005, max_iters=10)
+    img, lab = O.synthetic_batch(300, 2, 2, 65, 65)
+    out = sup.step(img, lab, 2)
+    assert abs(float(out['s_task_loss']) - float(g['task_loss'])) <= 2e-5 * float(g['task_loss'])
+    rel = np.abs(_checks([out['grads'][n] for n in names])[:, 1] - g['grad_checksum'][:, 1]) / g['grad_checksum'][:, 1]
+    assert rel.max() < 1e-3, rel.max()
+    np.testing.assert_allclose(_checks([sup.s[n] for n in names])[:, 1], g['param_checksum'][:, 1], rtol=1e-5)
+
+    g = load('cutmix_step_65.npz')
+    s = O.randomize_bn_affine(O.init_deeplabv2(51, cls_bias_std=0.01), 52)
+    t = O.randomize_bn_affine(O.init_deeplabv2(61, cls_bias_std=0.01), 62)
+    cm = O.CutMixOracle(s, t, lr=0.00025, momentum=0.9, weight_decay=0.0005, max_iters=10, cons_scale=20.0,
+                        rampup_steps=0, ema_decay=0.99, cons_threshold=float(g['cons_threshold']))
+    img, lab = O.synthetic_batch(400, 6, 2, 65, 65)
+    out = cm.step(img, lab, 2, np.random.RandomState(int(g['mask_seed'])))
+    assert abs(float(out['task_loss']) - float(g['task_loss'])) <= 2e-5 * float(g['task_loss'])
+    assert abs(float(out['cons_loss']) - float(g['cons_loss'])) <= 1e-4 * float(g['cons_loss'])
+    rel = np.abs(_checks([out['grads'][n] for n in names])[:, 1] - g['grad_checksum'][:, 1]) / g['grad_checksum'][:, 1]
+    assert rel.max() < 2e-3 and np.median(rel) < 2e-4, (rel.max(), np.median(rel))
+    np.testing.assert_allclose(_checks([cm.s[n] for n in names])[:, 1], g['s_param_checksum'][:, 1], rtol=1e-5)
+    np.testing.assert_allclose(_checks([cm.t[n] for n in names])[:, 1], g['t_param_checksum'][:, 1], rtol=1e-5)
+
+
+def test_reference_fp32_noise_floor_is_recorded():
+    """The yardstick used by the GPU whole-network tests: the reference's own fp32 evaluation vs
+    the oracle in fp64 on the same inputs (tests/golden/fp64_truth.npz)."""
+    t, f, m = load('fp64_truth.npz'), load('deeplabv2_forward_129.npz'), load('mt_steps_97.npz')
+    gap = np.abs(f['logits'] - t['fwd_logits']).max() / np.abs(t['fwd_logits']).max()
+    assert 1e-5 < gap < 1e-3, gap          # ~3.5e-4: fp32 noise amplified ~1e3x by the deep random-init net
+    rel = np.abs(m['grad_checksum_0'][:, 1] - t['mt_grad_checksum_0'][:, 1]) / t['mt_grad_checksum_0'][:, 1]
+    assert 1e-4 < np.median(rel) < 1e-2, np.median(rel)
