@@ -219,7 +219,7 @@ def run_engine(args):
         out['roofline']['traffic'] = json.load(open(traffic_path)).get('dram_bytes_per_launch')
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
-            out['cpu_baseline'] = cpu_reference(steps=2, warmup=1, lbs=1, ubs=1)
+            out['cpu_baseline'] = cpu_reference(steps=2, warmup=1, lbs=1, ubs=1)     # ~15-30 s of CPU work
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -231,7 +231,9 @@ def cpu_reference(steps, warmup, lbs, ubs):
     cannot travel to the GPU box), all host threads, on a bounded sample of the workload."""
     import torch
     from oracle import sseg_oracle as O
-    cores = os.cpu_count() or 1
+    # all host cores up to 32: torch's CPU conv/BN kernels at batch 2 get SLOWER beyond that
+    # (measured on the 128-core GPU box: 112 s/step with 128 threads vs ~5 s/step with 8-32)
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     s, t = O.init_deeplabv2(0), O.init_deeplabv2(1)
     mt = O.MTOracle(s, t, lr=0.00025, momentum=0.9, weight_decay=0.0005, max_iters=20 * 662, cons_scale=1.0,

@@ -166,6 +166,17 @@ int pxl_conv_nhwc(const pxl_conv_geom* geom_host, const int* taps_dydx_host /* 2
 /* dW[co][t][ci] += sum over output pixels of dy[n,oy,ox,co] * in[n, iy, ix, ci]   (accumulates) */
 int pxl_conv_wgrad_nhwc(const pxl_conv_geom* geom_host, const int* taps_dydx_host,
                         const float* in, const float* dy, float* dw, void* stream);
+/* tcgen05 path with explicit operands.  precision 1: in_lo / w_lo ignored (NULL).  precision 2
+ * (3xTF32): in_hi/in_lo and w_hi/w_lo are the tf32 split of the fp32 tensors (pxl_split_tf32):
+ * out = in_hi*w_hi + in_lo*w_hi + in_hi*w_lo accumulated in fp32 (TMEM).  Supports mul == div == 1
+ * and Cin % 32 == 0; anything else returns PXL_ERR_UNSUPPORTED. */
+int pxl_conv_tc_launch(const pxl_conv_geom* geom_host, const int* taps_dydx_host, const float* in_hi,
+                       const float* in_lo, const float* w_hi, const float* w_lo, const float* bias,
+                       float* out, void* stream);
+/* hi = round-to-nearest tf32 of x (low 13 mantissa bits zero), lo = x - hi (exact); n % 4 == 0 */
+int pxl_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+/* watchdog of the mbarrier pipelines: 0 = healthy, else the role that timed out (synchronises) */
+int pxl_conv_tc_status(void);
 /* w [Cout][T][Cin] -> wt [Cin][T][Cout] */
 int pxl_conv_transpose_weights(const float* w, float* wt, int Cout, int T, int Cin, void* stream);
 /* dbias[co] (+)= sum over rows of dy[row, co] (row stride ldo) */

@@ -47,6 +47,9 @@ SIGNATURES = {
     'pxl_maxpool3x3s2_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'pxl_conv_nhwc': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P]),
     'pxl_conv_wgrad_nhwc': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P]),
+    'pxl_conv_tc_launch': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P, P, P]),
+    'pxl_split_tf32': (c_int, [P, P, P, c_int64, P]),
+    'pxl_conv_tc_status': (c_int, []),
     'pxl_conv_transpose_weights': (c_int, [P, P, c_int, c_int, c_int, P]),
     'pxl_bias_grad': (c_int, [P, c_int64, c_int, c_int, P, c_int, P]),
     'pxl_stem_conv7x7s2': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),

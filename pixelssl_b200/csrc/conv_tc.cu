@@ -1,11 +1,432 @@
-// tcgen05 (5th-gen tensor core) convolution kernels.  Placeholder entry points until the
-// TMA + tcgen05 implicit-GEMM lands: they report PXL_ERR_UNSUPPORTED so callers can select the
-// fp32 path explicitly; nothing is silently computed elsewhere.
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a: forward / dgrad.
+//
+//   D[128 output pixels, BN out channels] (fp32, in TMEM) += A[128, 32] * B[BN, 32]^T  per (tap, 32-channel chunk)
+//
+// * A (activations, NHWC) is staged by TMA as a 4-D box {32 ch, BW, BH, 1}: one 128-byte row per
+//   output pixel of a BH x BW spatial tile, shifted by the tap offset; out-of-image coordinates
+//   are zero-filled by the TMA unit, which IS the convolution's zero padding (im2col-free).
+//   1x1 convolutions use the same path with the pixel axis flattened (BW = 128, BH = 1).
+// * B (weights [Cout][tap][Cin], K-major) is a 2-D box {32, BN}.
+// * Both land in shared memory in the canonical K-major SWIZZLE_128B layout and feed
+//   tcgen05.mma.kind::tf32 (UMMA_K = 8 -> four MMAs per stage); accumulators live in TMEM and are
+//   read back with tcgen05.ld by four epilogue warps which add the bias and store NHWC rows.
+// * precision 1: single TF32 pass on the raw fp32 data.  precision 2 ("3xTF32"): operands are
+//   pre-split into hi = tf32(x), lo = x - hi; D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo recovers
+//   fp32-grade products with fp32 accumulation (error ~2^-21 per product).
+// * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+//   warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).  mbarrier full/empty ring.
+//
+// Every mbarrier wait has a watchdog: on expiry the kernel raises a device-side flag and bails
+// out, so a protocol bug can never hang the GPU.
 #include "common.cuh"
+#include <cuda.h>
 
-extern "C" int pxl_conv_tc_impl(const pxl_conv_geom*, const int*, const float*, const float*, const float*, float*, void*) {
-    return PXL_ERR_UNSUPPORTED;
+// ------------------------------------------------------------------------------------------
+// driver entry point for tensor-map encoding (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
 }
+
+// NHWC fp32 tensor viewed as (C, W, H, N), box {32, bw, bh, 1}, 128-byte swizzle, zero OOB fill
+static int make_act_map(CUtensorMap* m, const float* base, int C, int W, int H, int N, int bw, int bh) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return PXL_ERR_UNSUPPORTED;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : PXL_ERR_BAD_ARG;
+}
+
+// weights [rows][K] fp32, box {32, bn}
+static int make_w_map(CUtensorMap* m, const float* base, int64_t K, int rows, int bn) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return PXL_ERR_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : PXL_ERR_BAD_ARG;
+}
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: returns false (and raises *flag) if the barrier never completes
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* flag, int code) {
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        if (mbar_try_wait(bar, parity)) return true;
+        if ((spin & 1023u) == 1023u && *(volatile int*)flag != 0) return false;   // another CTA already failed
+    }
+    atomicCAS(flag, 0, code);
+    return false;
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   start address >> 4 | LBO (unused for swizzled K-major, =1) << 16 | SBO = 1024 B (8 rows x 128 B) >> 4 << 32
+//   | version 1 << 46 | layout SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, M=128, N
+__device__ __forceinline__ uint32_t tf32_idesc(int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+struct TcParams {
+    int Cin, Cout, ldo, ntaps, kchunks;
+    int N, OH, OW;
+    int BW, BH, tilesW, tilesH;
+    int BN, stages, nsplit;
+    short dy[PXL_MAX_TAPS], dx[PXL_MAX_TAPS];
+};
+
+#define TC_A_BYTES (128 * 128)          // 128 rows x 128 B
+
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
+               const TcParams p, const float* __restrict__ bias, float* __restrict__ out, int* __restrict__ err_flag) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[8], empty_bar[8], acc_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    // 1024-byte aligned operand ring
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = p.BN * 128;
+    const int per_op = TC_A_BYTES + b_bytes;                 // A + B of one precision part
+    const int stage_bytes = per_op * (p.nsplit == 3 ? 2 : 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int tw = tile % p.tilesW, th = (tile / p.tilesW) % p.tilesH, n = tile / (p.tilesW * p.tilesH);
+    const int w0 = tw * p.BW, h0 = th * p.BH;
+    const int n0 = blockIdx.y * p.BN;
+    const int iters = p.ntaps * p.kchunks;
+    const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;          // power of two >= 32 (BN in {32,64,128,256})
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            // bytes the TMA unit will deliver per stage: full boxes, OOB parts are zero-filled but counted
+            const uint32_t tx = (uint32_t)((p.BW * p.BH * 128 + b_bytes) * (p.nsplit == 3 ? 2 : 1));
+            bool ok = true;
+            for (int it = 0; it < iters && ok; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                ok = mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 1);
+                if (!ok) break;
+                const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * 32;
+                uint8_t* sa = smem + (size_t)s * stage_bytes;
+                mbar_expect_tx(&full_bar[s], tx);
+                tma_load_4d(sa, &mapA, &full_bar[s], c0, w0 + p.dx[tap], h0 + p.dy[tap], n);
+                tma_load_2d(sa + TC_A_BYTES, &mapB, &full_bar[s], tap * p.Cin + c0, n0);
+                if (p.nsplit == 3) {
+                    tma_load_4d(sa + per_op, &mapAlo, &full_bar[s], c0, w0 + p.dx[tap], h0 + p.dy[tap], n);
+                    tma_load_2d(sa + per_op + TC_A_BYTES, &mapBlo, &full_bar[s], tap * p.Cin + c0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            const uint32_t idesc = tf32_idesc(p.BN);
+            bool ok = true;
+            for (int it = 0; it < iters && ok; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                ok = mbar_wait(&full_bar[s], ph, err_flag, 2);
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t da = kmajor_sw128_desc(sa), db = kmajor_sw128_desc(sa + TC_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)      // UMMA_K = 8 tf32 = 32 B: advance the start address by 2 x 16 B
+                    umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                if (p.nsplit == 3) {
+                    const uint64_t dal = kmajor_sw128_desc(sa + per_op), dbl = kmajor_sw128_desc(sa + per_op + TC_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, dal + 2 * k, db + 2 * k, idesc, 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, da + 2 * k, dbl + 2 * k, idesc, 1);
+                }
+                umma_commit(&empty_bar[s]);      // frees the smem slot once these MMAs have read it
+            }
+            if (ok) umma_commit(&acc_bar);       // accumulator complete -> epilogue
+        }
+    } else {
+        // ================= epilogue: TMEM -> registers -> global (NHWC rows) =================
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;             // tile row = output pixel within the spatial tile
+        const bool ok = __all_sync(0xffffffffu, mbar_wait(&acc_bar, 0, err_flag, 3));
+        tc_fence_after();
+        if (ok) {
+            const int hy = r / p.BW, wx = r - hy * p.BW;
+            const int oy = h0 + hy, ox = w0 + wx;
+            const bool valid = hy < p.BH && oy < p.OH && ox < p.OW;
+            float* orow = out + ((int64_t)(n * p.OH + oy) * p.OW + ox) * p.ldo;
+            for (int j = 0; j < p.BN; j += 32) {
+                float v[32];
+                tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)j, v);   // warp-collective
+                if (!valid) continue;
+                const int cb = n0 + j;
+                if (cb + 31 < p.Cout && (p.ldo & 3) == 0) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                        if (bias) { o.x += __ldg(bias + cb + c); o.y += __ldg(bias + cb + c + 1); o.z += __ldg(bias + cb + c + 2); o.w += __ldg(bias + cb + c + 3); }
+                        *reinterpret_cast<float4*>(orow + cb + c) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (cb + c < p.Cout) orow[cb + c] = v[c] + (bias ? __ldg(bias + cb + c) : 0.f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// tf32 split: hi = x with the low 13 mantissa bits cleared after round-to-nearest, lo = x - hi
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, int64_t n4) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldcs(x + i);
+        float4 h, l;
+        const float* vp = &v.x; float* hp = &h.x; float* lp = &l.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t u;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vp[k]));
+            u &= 0xFFFFE000u;
+            hp[k] = __uint_as_float(u);
+            lp[k] = vp[k] - hp[k];
+        }
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+extern "C" int pxl_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+    if (!x || !hi || !lo || n <= 0 || (n & 3)) return PXL_ERR_BAD_ARG;
+    const int64_t n4 = n / 4;
+    int blocks = (int)(pxl_cdiv(n4, 256 * 2) < PXL_NUM_SMS * 8 ? pxl_cdiv(n4, 256 * 2) : PXL_NUM_SMS * 8);
+    split_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)hi, (float4*)lo, n4);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int* g_err_flag = nullptr;
+
+static void pick_tile(int OH, int OW, bool flat, int& BW, int& BH) {
+    if (flat) { BW = 128; BH = 1; return; }
+    // choose BW x BH <= 128 maximising useful pixels per 128-row MMA tile
+    double best = -1.0;
+    BW = 16; BH = 8;
+    for (int bw = 4; bw <= 128 && bw <= 256; ++bw) {
+        int bh = 128 / bw;
+        if (bh < 1) break;
+        if (bh > 256) bh = 256;
+        const int64_t tiles = (int64_t)((OW + bw - 1) / bw) * ((OH + bh - 1) / bh);
+        const double eff = (double)OH * OW / ((double)tiles * 128.0);
+        if (eff > best + 1e-9) { best = eff; BW = bw; BH = bh; }
+    }
+}
+
+// lo parts: for precision 2 the caller passes hi/lo through `in`/`w` (hi) and the extra pointers
+extern "C" int pxl_conv_tc_launch(const pxl_conv_geom* g, const int* taps, const float* in_hi, const float* in_lo,
+                                  const float* w_hi, const float* w_lo, const float* bias, float* out, void* stream) {
+    if (!g || !taps || !in_hi || !w_hi || !out) return PXL_ERR_BAD_ARG;
+    if (g->mul != 1 || g->div != 1) return PXL_ERR_UNSUPPORTED;           // strided convs stay on the FFMA kernel
+    if (g->Cin % 32 != 0 || g->ntaps > PXL_MAX_TAPS) return PXL_ERR_UNSUPPORTED;
+    const int nsplit = g->precision == 2 ? 3 : 1;
+    if (nsplit == 3 && (!in_lo || !w_lo)) return PXL_ERR_BAD_ARG;
+    bool flat = (g->ntaps == 1 && taps[0] == 0 && taps[1] == 0 && g->OH == g->H && g->OW == g->W);
+    TcParams p;
+    p.Cin = g->Cin; p.Cout = g->Cout; p.ldo = g->ldo; p.ntaps = g->ntaps; p.kchunks = g->Cin / 32;
+    p.nsplit = nsplit;
+    for (int t = 0; t < g->ntaps; ++t) { p.dy[t] = (short)taps[2 * t]; p.dx[t] = (short)taps[2 * t + 1]; }
+    int mapW, mapH, mapN;
+    if (flat) {
+        const int64_t M = (int64_t)g->N * g->H * g->W;
+        if (M >= (1ll << 31)) return PXL_ERR_UNSUPPORTED;
+        p.N = 1; p.OH = 1; p.OW = (int)M;
+        mapW = (int)M; mapH = 1; mapN = 1;
+    } else {
+        p.N = g->N; p.OH = g->OH; p.OW = g->OW;
+        mapW = g->W; mapH = g->H; mapN = g->N;
+    }
+    pick_tile(p.OH, p.OW, flat, p.BW, p.BH);
+    p.tilesW = (p.OW + p.BW - 1) / p.BW; p.tilesH = (p.OH + p.BH - 1) / p.BH;
+    p.BN = g->Cout > 128 ? 256 : (g->Cout > 64 ? 128 : (g->Cout > 32 ? 64 : 32));
+    const int per_op = TC_A_BYTES + p.BN * 128;
+    const int stage_bytes = per_op * (nsplit == 3 ? 2 : 1);
+    const int budget = 200 * 1024;
+    p.stages = budget / stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    if (p.stages < 2) return PXL_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+
+    CUtensorMap mA, mAlo, mB, mBlo;
+    int rc = make_act_map(&mA, in_hi, g->Cin, mapW, mapH, mapN, p.BW, p.BH);
+    if (rc) return rc;
+    rc = make_w_map(&mB, w_hi, (int64_t)g->ntaps * g->Cin, g->Cout, p.BN);
+    if (rc) return rc;
+    if (nsplit == 3) {
+        rc = make_act_map(&mAlo, in_lo, g->Cin, mapW, mapH, mapN, p.BW, p.BH);
+        if (rc) return rc;
+        rc = make_w_map(&mBlo, w_lo, (int64_t)g->ntaps * g->Cin, g->Cout, p.BN);
+        if (rc) return rc;
+    } else {
+        mAlo = mA; mBlo = mB;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!g_err_flag) {
+        cudaError_t e = cudaMalloc(&g_err_flag, sizeof(int));
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemset(g_err_flag, 0, sizeof(int));
+        if (e != cudaSuccess) return (int)e;
+    }
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    dim3 grid((unsigned)((int64_t)p.N * p.tilesH * p.tilesW), (unsigned)((g->Cout + p.BN - 1) / p.BN));
+    conv_tc_kernel<<<grid, 192, smem, st>>>(mA, mAlo, mB, mBlo, p, bias, out, g_err_flag);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// watchdog status: 0 = fine, otherwise the role (1 producer, 2 mma, 3 epilogue) that timed out
+extern "C" int pxl_conv_tc_status(void) {
+    if (!g_err_flag) return 0;
+    int v = 0;
+    if (cudaMemcpy(&v, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return v;
+}
+
+extern "C" int pxl_conv_tc_impl(const pxl_conv_geom* g, const int* taps, const float* in, const float* w,
+                                const float* bias, float* out, void* stream) {
+    if (!g) return PXL_ERR_BAD_ARG;
+    if (g->precision == 2) return PXL_ERR_UNSUPPORTED;     // 3xTF32 needs the split operands: pxl_conv_tc_launch
+    return pxl_conv_tc_launch(g, taps, in, nullptr, w, nullptr, bias, out, stream);
+}
+
 extern "C" int pxl_conv_wgrad_tc_impl(const pxl_conv_geom*, const int*, const float*, const float*, float*, void*) {
     return PXL_ERR_UNSUPPORTED;
 }

@@ -318,37 +318,54 @@ def _ctaps(t):
     return (ctypes.c_int * len(t))(*t)
 
 
+def split_tf32(x):
+    """x (any shape, numel % 4 == 0) -> (hi, lo): hi = tf32(x) with a zero low mantissa, lo = x - hi."""
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    call('pxl_split_tf32', _p(x), _p(hi), _p(lo), x.numel(), _stream())
+    return hi, lo
+
+
+def tc_supported(Cin, mul, div):
+    """Shapes covered by the tcgen05 forward/dgrad kernel (csrc/conv_tc.cu)."""
+    return mul == 1 and div == 1 and Cin % 32 == 0
+
+
 def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, out=None, precision=None):
-    """Launch pxl_conv_nhwc on raw NHWC buffers.  w_packed: [Cout][ntaps][Cin] contiguous."""
+    """Launch the NHWC tap-table convolution on raw buffers.  w_packed: [Cout][ntaps][Cin] contiguous.
+    precision 0: FFMA kernel; 1: tcgen05 single-pass TF32; 2: tcgen05 3xTF32 (operands split on the
+    fly).  Shapes the tensor-core kernel does not cover (strided, Cin % 32 != 0) use the FFMA kernel."""
     ntaps = len(taps) // 2
     prec = _conv_precision if precision is None else precision
     if out is None:
         out = torch.empty((N, ldo, OH, OW), dtype=torch.float32, device=x.device).contiguous(memory_format=CL)
         if ldo != Cout:
             out.zero_()
-    geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
-    try:
-        call('pxl_conv_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(w_packed), _p(bias), _p(out), _stream())
-    except _lib.PxlError as e:
-        if e.code != _lib.PXL_ERR_UNSUPPORTED or prec == 0:
-            raise
-        geom.precision = 0          # shape not covered by the tensor-core kernel: precise FFMA kernel
-        call('pxl_conv_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(w_packed), _p(bias), _p(out), _stream())
+    if prec != 0 and tc_supported(Cin, mul, div):
+        geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
+        if prec == 2:
+            x_hi, x_lo = split_tf32(x)
+            w_hi, w_lo = split_tf32(w_packed)
+            call('pxl_conv_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x_hi), _p(x_lo), _p(w_hi), _p(w_lo),
+                 _p(bias), _p(out), _stream())
+        else:
+            call('pxl_conv_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x), _p(None), _p(w_packed), _p(None),
+                 _p(bias), _p(out), _stream())
+        return out
+    geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, 0)
+    call('pxl_conv_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(w_packed), _p(bias), _p(out), _stream())
     return out
+
+
+def conv_tc_status():
+    """0 when every tcgen05 pipeline so far completed; otherwise the role whose mbarrier wait timed out."""
+    return int(_lib.load().pxl_conv_tc_status())
 
 
 def conv_wgrad_raw(x, dy, dw, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, precision=None):
     """dw[Cout][ntaps][Cin] += ...  (dw must be initialised by the caller)."""
     ntaps = len(taps) // 2
-    prec = _conv_precision if precision is None else precision
-    geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
-    try:
-        call('pxl_conv_wgrad_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(dy), _p(dw), _stream())
-    except _lib.PxlError as e:
-        if e.code != _lib.PXL_ERR_UNSUPPORTED or prec == 0:
-            raise
-        geom.precision = 0
-        call('pxl_conv_wgrad_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(dy), _p(dw), _stream())
+    geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, 0)     # FFMA split-K kernel
+    call('pxl_conv_wgrad_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(dy), _p(dw), _stream())
     return dw
 
 

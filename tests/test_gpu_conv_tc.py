@@ -1,0 +1,103 @@
+"""tcgen05 convolution (csrc/conv_tc.cu) against the FFMA fp32 kernel and the torch-CPU oracle op.
+
+precision 2 (3xTF32: hi/lo operand split, fp32 TMEM accumulation) must agree with fp32 to 1e-5
+relative; precision 1 (single TF32 pass, what cuDNN does by default for the reference on GPU) to
+2e-3.  The mbarrier watchdog must stay silent."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+CL = torch.channels_last
+
+
+@pytest.fixture(scope='module')
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a GPU')
+    from pixelssl_b200 import ops as _ops
+    return _ops
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+CASES = [
+    # N, Cin, H, W, Cout, k, dil
+    (2, 64, 17, 19, 64, 1, 1),
+    (1, 32, 8, 16, 32, 1, 1),         # exactly one 128-row tile
+    (2, 256, 33, 33, 64, 1, 1),
+    (2, 64, 33, 33, 256, 1, 1),
+    (1, 1024, 9, 9, 256, 1, 1),
+    (2, 64, 13, 13, 64, 3, 1),
+    (2, 64, 33, 33, 64, 3, 1),
+    (1, 128, 65, 65, 128, 3, 1),
+    (2, 256, 33, 33, 256, 3, 1),
+    (1, 512, 17, 17, 512, 3, 2),      # layer4 dilation 2
+    (1, 512, 17, 17, 512, 3, 4),
+    (1, 96, 20, 24, 160, 3, 1),       # Cin = 3 chunks, Cout not a power of two
+    (2, 64, 129, 129, 64, 3, 1),      # layer1 conv2 shape (many tiles)
+]
+
+
+@pytest.mark.parametrize('precision,tol', [(2, 1e-5), (1, 2e-3)])
+@pytest.mark.parametrize('case', CASES)
+def test_conv_tc_forward_and_dgrad(ops, case, precision, tol):
+    N, Cin, H, W, Cout, k, dil = case
+    g = torch.Generator().manual_seed(Cin + Cout + H)
+    x = torch.randn(N, Cin, H, W, generator=g).cuda().contiguous(memory_format=CL)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda().contiguous(memory_format=CL)
+    b = torch.randn(Cout, generator=g).cuda()
+    pad = dil * (k // 2)
+    outs = {}
+    for prec in (0, precision):
+        ops._conv_precision = prec
+        xg = x.clone().requires_grad_(True)
+        y = ops.conv2d(xg, w, b, 1, pad, dil)
+        y.backward(torch.ones_like(y) * 0.5 + y.detach() * 0.1)
+        outs[prec] = (y.detach(), xg.grad)
+    ops._conv_precision = 0
+    assert ops.conv_tc_status() == 0, 'mbarrier watchdog fired: role %d' % ops.conv_tc_status()
+    ef, eb = rel(outs[precision][0], outs[0][0]), rel(outs[precision][1], outs[0][1])
+    print('case %s precision %d: fwd %.2e dgrad %.2e' % (case, precision, ef, eb))
+    assert ef <= tol and eb <= tol, (ef, eb)
+    # and against torch CPU for one anchor per kernel size
+    if (N, Cin, H) in ((2, 64, 17), (2, 64, 13)):
+        yc = F.conv2d(x.cpu().contiguous(), w.cpu().contiguous(), b.cpu(), padding=pad, dilation=dil)
+        assert rel(outs[precision][0].cpu(), yc) <= tol
+
+
+@pytest.mark.parametrize('precision,tol', [(2, 1e-5), (1, 2e-3)])
+def test_aspp_head_tc(ops, precision, tol):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 2048, 33, 33, generator=g).cuda().contiguous(memory_format=CL)
+    ws = [(torch.randn(21, 2048, 3, 3, generator=g) * 0.01).cuda().contiguous(memory_format=CL) for _ in range(4)]
+    bs = [(torch.randn(21, generator=g) * 0.1).cuda() for _ in range(4)]
+    res = {}
+    for prec in (0, precision):
+        ops._conv_precision = prec
+        xg = x.clone().requires_grad_(True)
+        y = ops.aspp(xg, ws, bs)
+        gy = torch.zeros_like(y)
+        gy[:, :21] = 0.3
+        y.backward(gy)
+        res[prec] = (y.detach(), xg.grad)
+    ops._conv_precision = 0
+    assert ops.conv_tc_status() == 0
+    assert rel(res[precision][0][:, :21], res[0][0][:, :21]) <= tol
+    assert float(res[precision][0][:, 21:].abs().max()) == 0.0
+    assert rel(res[precision][1], res[0][1]) <= tol
+
+
+def test_tf32_operand_rounding_probe(ops):
+    """Documents what kind::tf32 does with the low 13 mantissa bits of raw fp32 operands."""
+    x = torch.full((1, 32, 8, 16), 1.0 + 2.0 ** -11 + 2.0 ** -12).cuda().contiguous(memory_format=CL)   # low bits set
+    w = torch.zeros(32, 32, 1, 1).cuda().contiguous(memory_format=CL)
+    w[0, 0] = 1.0
+    ops._conv_precision = 1
+    y = ops.conv2d(x, w, None, 1, 0, 1)
+    ops._conv_precision = 0
+    v = float(y[0, 0, 0, 0])
+    print('tf32 probe: 1 + 2^-11 + 2^-12 ->', v, '(truncation gives 1.0, round-to-nearest gives 1 + 2^-10)')
+    assert v in (1.0, 1.0 + 2.0 ** -10, 1.0 + 2.0 ** -11 + 2.0 ** -12)
