@@ -173,6 +173,12 @@ int pxl_conv_wgrad_nhwc(const pxl_conv_geom* geom_host, const int* taps_dydx_hos
 int pxl_conv_tc_launch(const pxl_conv_geom* geom_host, const int* taps_dydx_host, const float* in_hi,
                        const float* in_lo, const float* w_hi, const float* w_lo, const float* bias,
                        float* out, void* stream);
+/* tcgen05 wgrad (accumulates into dw): both operands MN-major via TMA, split over the pixel range,
+ * fp32 RED epilogue.  Same precision / operand convention as pxl_conv_tc_launch; needs mul == div == 1,
+ * Cin % 32 == 0 and ldo % 32 == 0. */
+int pxl_conv_wgrad_tc_launch(const pxl_conv_geom* geom_host, const int* taps_dydx_host, const float* in_hi,
+                             const float* in_lo, const float* dy_hi, const float* dy_lo, float* dw,
+                             void* stream);
 /* hi = round-to-nearest tf32 of x (low 13 mantissa bits zero), lo = x - hi (exact); n % 4 == 0 */
 int pxl_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 /* watchdog of the mbarrier pipelines: 0 = healthy, else the role that timed out (synchronises) */

@@ -48,6 +48,7 @@ SIGNATURES = {
     'pxl_conv_nhwc': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P]),
     'pxl_conv_wgrad_nhwc': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P]),
     'pxl_conv_tc_launch': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P, P, P]),
+    'pxl_conv_wgrad_tc_launch': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P, P]),
     'pxl_split_tf32': (c_int, [P, P, P, c_int64, P]),
     'pxl_conv_tc_status': (c_int, []),
     'pxl_conv_transpose_weights': (c_int, [P, P, c_int, c_int, c_int, P]),

@@ -171,6 +171,7 @@ struct TcParams {
     int N, OH, OW;
     int BW, BH, tilesW, tilesH;
     int BN, stages, nsplit;
+    int nacc;       // TMEM accumulators used round-robin over k-iterations (summed with RN adds in the epilogue)
     short dy[PXL_MAX_TAPS], dx[PXL_MAX_TAPS];
 };
 
@@ -196,7 +197,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int w0 = tw * p.BW, h0 = th * p.BH;
     const int n0 = blockIdx.y * p.BN;
     const int iters = p.ntaps * p.kchunks;
-    const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;          // power of two >= 32 (BN in {32,64,128,256})
+    // The tensor core's fp32 accumulator truncates instead of rounding to nearest (measured: error
+    // grows ~5e-9 * K), so long reductions are spread over `nacc` independent TMEM accumulators.
+    const uint32_t acc_cols = p.BN < 32 ? 32 : p.BN;           // BN in {32,64,128,256}
+    const uint32_t tmem_cols = acc_cols * p.nacc;              // power of two, <= 512
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -244,15 +248,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint64_t da = kmajor_sw128_desc(sa), db = kmajor_sw128_desc(sa + TC_A_BYTES);
+                const uint32_t acc = tmem_d + (uint32_t)(it % p.nacc) * acc_cols;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)      // UMMA_K = 8 tf32 = 32 B: advance the start address by 2 x 16 B
-                    umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                    umma_tf32(acc, da + 2 * k, db + 2 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
                 if (p.nsplit == 3) {
                     const uint64_t dal = kmajor_sw128_desc(sa + per_op), dbl = kmajor_sw128_desc(sa + per_op + TC_A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, dal + 2 * k, db + 2 * k, idesc, 1);
+                    for (int k = 0; k < 4; ++k) umma_tf32(acc, dal + 2 * k, db + 2 * k, idesc, 1);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, da + 2 * k, dbl + 2 * k, idesc, 1);
+                    for (int k = 0; k < 4; ++k) umma_tf32(acc, da + 2 * k, dbl + 2 * k, idesc, 1);
                 }
                 umma_commit(&empty_bar[s]);      // frees the smem slot once these MMAs have read it
             }
@@ -269,9 +274,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int oy = h0 + hy, ox = w0 + wx;
             const bool valid = hy < p.BH && oy < p.OH && ox < p.OW;
             float* orow = out + ((int64_t)(n * p.OH + oy) * p.OW + ox) * p.ldo;
+            const int used = iters < p.nacc ? iters : p.nacc;
             for (int j = 0; j < p.BN; j += 32) {
                 float v[32];
                 tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)j, v);   // warp-collective
+                for (int a = 1; a < used; ++a) {
+                    float u[32];
+                    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)a * acc_cols + (uint32_t)j, u);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] += u[c];
+                }
                 if (!valid) continue;
                 const int cb = n0 + j;
                 if (cb + 31 < p.Cout && (p.ldo & 3) == 0) {
@@ -372,6 +384,8 @@ extern "C" int pxl_conv_tc_launch(const pxl_conv_geom* g, const int* taps, const
     pick_tile(p.OH, p.OW, flat, p.BW, p.BH);
     p.tilesW = (p.OW + p.BW - 1) / p.BW; p.tilesH = (p.OH + p.BH - 1) / p.BH;
     p.BN = g->Cout > 128 ? 256 : (g->Cout > 64 ? 128 : (g->Cout > 32 ? 64 : 32));
+    if (nsplit == 3 && p.BN > 128) p.BN = 128;                 // leave TMEM room for 4 accumulators
+    p.nacc = nsplit == 3 ? 4 : 1;
     const int per_op = TC_A_BYTES + p.BN * 128;
     const int stage_bytes = per_op * (nsplit == 3 ? 2 : 1);
     const int budget = 200 * 1024;
@@ -427,6 +441,283 @@ extern "C" int pxl_conv_tc_impl(const pxl_conv_geom* g, const int* taps, const f
     return pxl_conv_tc_launch(g, taps, in, nullptr, w, nullptr, bias, out, stream);
 }
 
-extern "C" int pxl_conv_wgrad_tc_impl(const pxl_conv_geom*, const int*, const float*, const float*, float*, void*) {
-    return PXL_ERR_UNSUPPORTED;
+// ==========================================================================================
+// wgrad on tcgen05:  dW[co][tap][ci] += sum_pixels dY[pix][co] * X[pix + tap][ci]
+//
+//   D[128 co, BN ci] (TMEM) += A^T[K = pixels, 128 co] * B[K = pixels, BN ci]
+//
+// Both operands are "MN-major" (the reduction index = pixel row is the slow one), which is exactly
+// what NHWC gives: a TMA box {32 channels, BW, BH, 1} is (BW*BH pixel rows) x 128 B and lands as one
+// SWIZZLE_128B_ATOM_32B slab; 4 slabs of dY (128 co) and BN/32 slabs of X (tap-shifted, OOB zero-filled)
+// form a stage.  Each tcgen05.mma.kind::tf32 consumes 8 pixel rows (one 1024-B swizzle atom per
+// slab).  Rows between BW*BH and the 8-aligned allocation are zeroed once and never written.
+// The pixel range is split over gridDim.z CTAs; the epilogue adds the tile into dW with fp32 RED.
+// ==========================================================================================
+struct WgParams {
+    int Cin, Cout, ldo, ntaps;
+    int N, OH, OW, mul;
+    int BW, BH, tilesW, tilesH, rows, rows_alloc;
+    int BN, stages, nsplit, nacc;
+    int tiles_ci, ktiles_per_cta, ktiles_total;
+    short dy[PXL_MAX_TAPS], dx[PXL_MAX_TAPS];
+};
+
+// MN-major tf32 operands only exist in the SWIZZLE_128B_BASE32B layout (cutlass sm100_common.inl:92;
+// cute Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> over 4 rows x 128 B): 128-byte rows, 32-byte swizzle
+// granularity, atoms of 4 K-rows.  LBO = byte distance between 32-element MN slabs, SBO = byte
+// distance between 4-row K atoms (512 B for densely packed rows).  TMA writes this layout with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;       // LayoutType::SWIZZLE_128B_BASE32B
+    return d;
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapDyLo,
+                     const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapXLo,
+                     const WgParams p, float* __restrict__ dw, int* __restrict__ err_flag) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[8], empty_bar[8], acc_bar;
+    __shared__ uint32_t tmem_base_slot;
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+    const int slab_bytes = p.rows_alloc * 128;
+    const int slabsB = p.BN / 32;
+    const int per_op = (4 + slabsB) * slab_bytes;
+    const int stage_bytes = per_op * (p.nsplit == 3 ? 2 : 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_co = blockIdx.x / p.tiles_ci, tile_ci = blockIdx.x % p.tiles_ci;
+    const int co0 = tile_co * 128, ci0 = tile_ci * p.BN;
+    const int tap = blockIdx.y;
+    const int kt0 = blockIdx.z * p.ktiles_per_cta;
+    int kt1 = kt0 + p.ktiles_per_cta;
+    if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+    const int iters = kt1 - kt0;
+    const uint32_t acc_cols = p.BN < 32 ? 32 : p.BN;
+    const uint32_t tmem_cols = acc_cols * p.nacc;
+    // slabs that actually exist (the others stay zero)
+    int nsA = (p.ldo - co0 + 31) / 32; if (nsA > 4) nsA = 4;
+    int nsB = (p.Cin - ci0 + 31) / 32; if (nsB > slabsB) nsB = slabsB;
+
+    // zero the operand ring once: rows the TMA never writes must contribute nothing
+    {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        const int total16 = p.stages * stage_bytes / 16;
+        for (int i = threadIdx.x; i < total16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = z;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+
+    if (iters > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                const uint32_t box_bytes = (uint32_t)(p.rows * 128);
+                const uint32_t tx = box_bytes * (uint32_t)(nsA + nsB) * (p.nsplit == 3 ? 2u : 1u);
+                const int tdy = p.dy[tap], tdx = p.dx[tap];
+                bool ok = true;
+                for (int it = 0; it < iters && ok; ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    ok = mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 11);
+                    if (!ok) break;
+                    const int kt = kt0 + it;
+                    const int tw = kt % p.tilesW, th = (kt / p.tilesW) % p.tilesH, n = kt / (p.tilesW * p.tilesH);
+                    const int w0 = tw * p.BW, h0 = th * p.BH;
+                    uint8_t* sa = smem + (size_t)s * stage_bytes;
+                    mbar_expect_tx(&full_bar[s], tx);
+                    for (int part = 0; part < (p.nsplit == 3 ? 2 : 1); ++part) {
+                        uint8_t* base = sa + (size_t)part * per_op;
+                        const CUtensorMap* mdy = part ? &mapDyLo : &mapDy;
+                        const CUtensorMap* mx = part ? &mapXLo : &mapX;
+                        for (int j = 0; j < nsA; ++j)
+                            tma_load_4d(base + (size_t)j * slab_bytes, mdy, &full_bar[s], co0 + 32 * j, w0, h0, n);
+                        for (int j = 0; j < nsB; ++j)
+                            tma_load_4d(base + (size_t)(4 + j) * slab_bytes, mx, &full_bar[s], ci0 + 32 * j,
+                                        w0 * p.mul + tdx, h0 * p.mul + tdy, n);
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                // D fp32, A/B tf32, both MN-major (bits 15,16), M = 128, N = BN
+                const uint32_t idesc = tf32_idesc(p.BN) | (1u << 15) | (1u << 16);
+                const int kmma = p.rows_alloc / 8;
+                bool ok = true;
+                for (int it = 0; it < iters && ok; ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    ok = mbar_wait(&full_bar[s], ph, err_flag, 12);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t acc = tmem_d + (uint32_t)(it % p.nacc) * acc_cols;
+                    const uint64_t da = mnmajor_sw128_desc(sa, (uint32_t)slab_bytes);
+                    const uint64_t db = mnmajor_sw128_desc(sa + 4 * slab_bytes, (uint32_t)slab_bytes);
+                    for (int k = 0; k < kmma; ++k)       // 8 pixel rows = 1024 B per MMA: +64 (x16 B)
+                        umma_tf32(acc, da + 64 * k, db + 64 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
+                    if (p.nsplit == 3) {
+                        const uint64_t dal = mnmajor_sw128_desc(sa + per_op, (uint32_t)slab_bytes);
+                        const uint64_t dbl = mnmajor_sw128_desc(sa + per_op + 4 * slab_bytes, (uint32_t)slab_bytes);
+                        for (int k = 0; k < kmma; ++k) umma_tf32(acc, dal + 64 * k, db + 64 * k, idesc, 1);
+                        for (int k = 0; k < kmma; ++k) umma_tf32(acc, da + 64 * k, dbl + 64 * k, idesc, 1);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                if (ok) umma_commit(&acc_bar);
+            }
+        } else {
+            const int q = warp & 3;
+            const int co = co0 + q * 32 + lane;
+            const bool ok = __all_sync(0xffffffffu, mbar_wait(&acc_bar, 0, err_flag, 13));
+            tc_fence_after();
+            if (ok) {
+                const int used = iters < p.nacc ? iters : p.nacc;
+                float* drow = dw + ((int64_t)co * p.ntaps + tap) * p.Cin;
+                for (int j = 0; j < p.BN; j += 32) {
+                    float v[32];
+                    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)j, v);
+                    for (int a = 1; a < used; ++a) {
+                        float u[32];
+                        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)a * acc_cols + (uint32_t)j, u);
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] += u[c];
+                    }
+                    if (co >= p.Cout) continue;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int ci = ci0 + j + c;
+                        if (ci < p.Cin) atomicAdd(drow + ci, v[c]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// activation map for wgrad: optional traversal stride (stride-2 convolutions read every 2nd pixel)
+static int make_act_map_strided(CUtensorMap* m, const float* base, int C, int W, int H, int N, int bw, int bh, int estride) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return PXL_ERR_UNSUPPORTED;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+    if (box[1] > 256 || box[2] > 256) return PXL_ERR_UNSUPPORTED;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : PXL_ERR_BAD_ARG;
+}
+
+static void pick_ktile(int OH, int OW, bool flat, int maxrows, int& BW, int& BH) {
+    if (flat) { BW = maxrows; BH = 1; return; }
+    double best = -1.0;
+    BW = 8; BH = maxrows / 8;
+    for (int bw = 1; bw <= maxrows; ++bw) {
+        const int bh = maxrows / bw;
+        if (bh < 1) break;
+        const int alloc = (bw * bh + 7) / 8 * 8;
+        const int64_t tiles = (int64_t)((OW + bw - 1) / bw) * ((OH + bh - 1) / bh);
+        const double eff = (double)OH * OW / ((double)tiles * alloc);
+        if (eff > best + 1e-9) { best = eff; BW = bw; BH = bh; }
+    }
+}
+
+extern "C" int pxl_conv_wgrad_tc_launch(const pxl_conv_geom* g, const int* taps, const float* in_hi, const float* in_lo,
+                                        const float* dy_hi, const float* dy_lo, float* dw, void* stream) {
+    if (!g || !taps || !in_hi || !dy_hi || !dw) return PXL_ERR_BAD_ARG;
+    if (g->div != 1 || (g->mul != 1 && g->mul != 2)) return PXL_ERR_UNSUPPORTED;   // stride 2 via TMA traversal stride
+    if (g->Cin % 32 != 0 || g->ldo % 32 != 0 || g->ntaps > PXL_MAX_TAPS) return PXL_ERR_UNSUPPORTED;
+    const int nsplit = g->precision == 2 ? 3 : 1;
+    if (nsplit == 3 && (!in_lo || !dy_lo)) return PXL_ERR_BAD_ARG;
+    const bool flat = (g->ntaps == 1 && taps[0] == 0 && taps[1] == 0 && g->OH == g->H && g->OW == g->W && g->mul == 1);
+    WgParams p;
+    p.Cin = g->Cin; p.Cout = g->Cout; p.ldo = g->ldo; p.ntaps = g->ntaps; p.mul = g->mul; p.nsplit = nsplit;
+    for (int t = 0; t < g->ntaps; ++t) { p.dy[t] = (short)taps[2 * t]; p.dx[t] = (short)taps[2 * t + 1]; }
+    int mapW, mapH, mapN, inW, inH;
+    if (flat) {
+        const int64_t M = (int64_t)g->N * g->H * g->W;
+        if (M >= (1ll << 31)) return PXL_ERR_UNSUPPORTED;
+        p.N = 1; p.OH = 1; p.OW = (int)M; mapW = (int)M; mapH = 1; mapN = 1; inW = (int)M; inH = 1;
+    } else {
+        p.N = g->N; p.OH = g->OH; p.OW = g->OW; mapW = g->OW; mapH = g->OH; mapN = g->N; inW = g->W; inH = g->H;
+    }
+    const int maxrows = nsplit == 3 ? 32 : 64;
+    pick_ktile(p.OH, p.OW, flat, maxrows, p.BW, p.BH);
+    p.rows = p.BW * p.BH;
+    p.rows_alloc = (p.rows + 7) / 8 * 8;
+    p.tilesW = (p.OW + p.BW - 1) / p.BW; p.tilesH = (p.OH + p.BH - 1) / p.BH;
+    p.BN = g->Cin > 64 ? 128 : (g->Cin > 32 ? 64 : 32);
+    p.nacc = 512 / (p.BN < 32 ? 32 : p.BN); if (p.nacc > 4) p.nacc = 4;
+    p.tiles_ci = (g->Cin + p.BN - 1) / p.BN;
+    const int tiles_co = (g->Cout + 127) / 128;
+    const int stage_bytes = (4 + p.BN / 32) * p.rows_alloc * 128 * (nsplit == 3 ? 2 : 1);
+    p.stages = (200 * 1024) / stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    if (p.stages < 2) return PXL_ERR_UNSUPPORTED;
+    p.ktiles_total = p.N * p.tilesH * p.tilesW;
+    // split the pixel range: enough CTAs to fill the GPU, and at most ~4096 pixel rows per CTA so the
+    // truncating TMEM accumulation stays at fp32 level (the cross-CTA RED adds round to nearest)
+    const int64_t base_ctas = (int64_t)tiles_co * p.tiles_ci * g->ntaps;
+    int64_t split = pxl_cdiv((int64_t)PXL_NUM_SMS * 2, base_ctas);
+    const int64_t by_rows = pxl_cdiv((int64_t)p.ktiles_total * p.rows_alloc, 4096);
+    if (by_rows > split) split = by_rows;
+    if (split > p.ktiles_total) split = p.ktiles_total;
+    if (split < 1) split = 1;
+    if (split > 65535) split = 65535;
+    p.ktiles_per_cta = (int)pxl_cdiv(p.ktiles_total, split);
+    split = pxl_cdiv(p.ktiles_total, p.ktiles_per_cta);
+
+    CUtensorMap mDy, mDyLo, mX, mXLo;
+    int rc = make_act_map_strided(&mDy, dy_hi, g->ldo, mapW, mapH, mapN, p.BW, p.BH, 1);
+    if (rc) return rc;
+    rc = make_act_map_strided(&mX, in_hi, g->Cin, inW, inH, mapN, p.BW, p.BH, g->mul);
+    if (rc) return rc;
+    if (nsplit == 3) {
+        rc = make_act_map_strided(&mDyLo, dy_lo, g->ldo, mapW, mapH, mapN, p.BW, p.BH, 1);
+        if (rc) return rc;
+        rc = make_act_map_strided(&mXLo, in_lo, g->Cin, inW, inH, mapN, p.BW, p.BH, g->mul);
+        if (rc) return rc;
+    } else { mDyLo = mDy; mXLo = mX; }
+    if (!g_err_flag) {
+        cudaError_t e = cudaMalloc(&g_err_flag, sizeof(int));
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemset(g_err_flag, 0, sizeof(int));
+        if (e != cudaSuccess) return (int)e;
+    }
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    dim3 grid((unsigned)(tiles_co * p.tiles_ci), (unsigned)g->ntaps, (unsigned)split);
+    conv_wgrad_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mDy, mDyLo, mX, mXLo, p, dw, g_err_flag);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pxl_conv_wgrad_tc_impl(const pxl_conv_geom* g, const int* taps, const float* in, const float* dy,
+                                      float* dw, void* stream) {
+    if (!g) return PXL_ERR_BAD_ARG;
+    if (g->precision == 2) return PXL_ERR_UNSUPPORTED;     // needs split operands: pxl_conv_wgrad_tc_launch
+    return pxl_conv_wgrad_tc_launch(g, taps, in, nullptr, dy, nullptr, dw, stream);
 }

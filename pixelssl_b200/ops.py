@@ -18,6 +18,7 @@ CL = torch.channels_last
 # conv precision policy (pxl_conv_geom.precision): 0 fp32 FFMA, 1 TF32 tcgen05, 2 3xTF32 tcgen05
 PRECISION = {'fp32': 0, 'tf32': 1, 'tf32x3': 2}
 _conv_precision = 0
+_WGRAD_TC_STRIDES = (1, 2)      # convolution strides the tcgen05 wgrad kernel handles
 
 
 def set_conv_precision(name):
@@ -285,7 +286,7 @@ class _Bilinear(torch.autograd.Function):
         n, C, h, w, H, W, ac, nhwc, ldc = ctx.meta
         g = g.contiguous()
         if nhwc:
-            gin = torch.zeros((n, ldc, h, w), dtype=torch.float32, device=g.device).contiguous(memory_format=CL)
+            gin = torch.empty((n, ldc, h, w), dtype=torch.float32, device=g.device, memory_format=CL).zero_()
         else:
             gin = torch.empty((n, C, h, w), dtype=torch.float32, device=g.device)
         call('pxl_bilinear_bwd', _p(g), _p(gin), n, C, h, w, H, W, ac, nhwc, ldc, _stream())
@@ -337,7 +338,7 @@ def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div,
     ntaps = len(taps) // 2
     prec = _conv_precision if precision is None else precision
     if out is None:
-        out = torch.empty((N, ldo, OH, OW), dtype=torch.float32, device=x.device).contiguous(memory_format=CL)
+        out = torch.empty((N, ldo, OH, OW), dtype=torch.float32, device=x.device, memory_format=CL)
         if ldo != Cout:
             out.zero_()
     if prec != 0 and tc_supported(Cin, mul, div):
@@ -364,6 +365,18 @@ def conv_tc_status():
 def conv_wgrad_raw(x, dy, dw, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, precision=None):
     """dw[Cout][ntaps][Cin] += ...  (dw must be initialised by the caller)."""
     ntaps = len(taps) // 2
+    prec = _conv_precision if precision is None else precision
+    if prec != 0 and div == 1 and mul in _WGRAD_TC_STRIDES and Cin % 32 == 0 and ldo % 32 == 0:
+        geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
+        if prec == 2:
+            x_hi, x_lo = split_tf32(x)
+            d_hi, d_lo = split_tf32(dy)
+            call('pxl_conv_wgrad_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x_hi), _p(x_lo), _p(d_hi), _p(d_lo),
+                 _p(dw), _stream())
+        else:
+            call('pxl_conv_wgrad_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x), _p(None), _p(dy), _p(None),
+                 _p(dw), _stream())
+        return dw
     geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, 0)     # FFMA split-K kernel
     call('pxl_conv_wgrad_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(dy), _p(dw), _stream())
     return dw
@@ -477,7 +490,7 @@ class _Stem(torch.autograd.Function):
         if C != 3 or tuple(weight.shape) != (64, 3, 7, 7):
             raise ValueError('stem expects a 3-channel image and a [64,3,7,7] weight')
         OH, OW = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
-        out = torch.empty((N, 64, OH, OW), dtype=torch.float32, device=img.device).contiguous(memory_format=CL)
+        out = torch.empty((N, 64, OH, OW), dtype=torch.float32, device=img.device, memory_format=CL)
         call('pxl_stem_conv7x7s2', _p(img), _p(weight), _p(out), N, H, W, OH, OW, _stream())
         ctx.save_for_backward(img)
         ctx.meta = (N, H, W, OH, OW)
@@ -488,7 +501,7 @@ class _Stem(torch.autograd.Function):
         (img,) = ctx.saved_tensors
         N, H, W, OH, OW = ctx.meta
         dy = as_cl(dy)
-        dw = torch.zeros((64, 3, 7, 7), dtype=torch.float32, device=dy.device).contiguous(memory_format=CL)
+        dw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=dy.device, memory_format=CL).zero_()
         call('pxl_stem_conv7x7s2_wgrad', _p(img), _p(dy), _p(dw), N, H, W, OH, OW, _stream())
         return None, dw
 
@@ -572,7 +585,7 @@ class _MaxPool(torch.autograd.Function):
         _chk(x, 'x', cl=True)
         N, C, H, W = x.shape
         OH, OW = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
-        y = torch.empty((N, C, OH, OW), dtype=torch.float32, device=x.device).contiguous(memory_format=CL)
+        y = torch.empty((N, C, OH, OW), dtype=torch.float32, device=x.device, memory_format=CL)
         call('pxl_maxpool3x3s2_fwd', _p(x), _p(y), N, H, W, C, OH, OW, _stream())
         ctx.save_for_backward(x)
         ctx.meta = (N, H, W, C, OH, OW)

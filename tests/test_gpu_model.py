@@ -30,7 +30,8 @@ def eng():
         pytest.skip('needs a GPU')
     import pixelssl_b200
     from pixelssl_b200 import ops
-    ops.set_conv_precision('fp32')
+    # PXL_TEST_PRECISION=tf32x3 runs the same whole-network parity tests on the tcgen05 3xTF32 path
+    ops.set_conv_precision(os.environ.get('PXL_TEST_PRECISION', 'fp32'))
     return pixelssl_b200
 
 
