@@ -173,6 +173,20 @@ int pxl_conv_wgrad_nhwc(const pxl_conv_geom* geom_host, const int* taps_dydx_hos
 int pxl_conv_tc_launch(const pxl_conv_geom* geom_host, const int* taps_dydx_host, const float* in_hi,
                        const float* in_lo, const float* w_hi, const float* w_lo, const float* bias,
                        float* out, void* stream);
+/* Extended form used for strided convolutions:
+ *  - geom.mul == 2 (stride-2 forward) is served by the TMA traversal stride;
+ *  - stride-2 dgrad is decomposed by output parity into four stride-1 problems over dY: each launch
+ *    passes the taps of one parity class (offsets already halved), `widx_host[t]` = index of tap t in
+ *    the [rows][w_ntaps][Cin] weight tensor, and stores its OH x OW result at
+ *    (oy*out_mul + out_offy, ox*out_mul + out_offx) of the out_H x out_W output image. */
+typedef struct {
+    int w_ntaps;             /* taps held by the weight tensor (>= geom.ntaps); 0 = geom.ntaps */
+    const int* widx_host;    /* nullable: identity */
+    int out_mul, out_offy, out_offx, out_H, out_W;
+} pxl_conv_tc_ext;
+int pxl_conv_tc_launch_ex(const pxl_conv_geom* geom_host, const int* taps_dydx_host, const pxl_conv_tc_ext* ext_host,
+                          const float* in_hi, const float* in_lo, const float* w_hi, const float* w_lo,
+                          const float* bias, float* out, void* stream);
 /* tcgen05 wgrad (accumulates into dw): both operands MN-major via TMA, split over the pixel range,
  * fp32 RED epilogue.  Same precision / operand convention as pxl_conv_tc_launch; needs mul == div == 1,
  * Cin % 32 == 0 and ldo % 32 == 0. */

@@ -19,6 +19,12 @@ class ConvGeom(ctypes.Structure):
                 ('mul', c_int), ('div', c_int), ('ntaps', c_int), ('precision', c_int)]
 
 
+class ConvTcExt(ctypes.Structure):
+    """mirror of pxl_conv_tc_ext"""
+    _fields_ = [('w_ntaps', c_int), ('widx_host', ctypes.POINTER(c_int)), ('out_mul', c_int),
+                ('out_offy', c_int), ('out_offx', c_int), ('out_H', c_int), ('out_W', c_int)]
+
+
 P = c_void_p
 # name -> (restype, argtypes); must list every symbol of include/pixelssl_b200.h
 SIGNATURES = {
@@ -48,6 +54,7 @@ SIGNATURES = {
     'pxl_conv_nhwc': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P]),
     'pxl_conv_wgrad_nhwc': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P]),
     'pxl_conv_tc_launch': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P, P, P]),
+    'pxl_conv_tc_launch_ex': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), ctypes.POINTER(ConvTcExt), P, P, P, P, P, P, P]),
     'pxl_conv_wgrad_tc_launch': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P, P]),
     'pxl_split_tf32': (c_int, [P, P, P, c_int64, P]),
     'pxl_conv_tc_status': (c_int, []),

@@ -40,13 +40,16 @@ static EncodeTiledFn get_encode() {
 }
 
 // NHWC fp32 tensor viewed as (C, W, H, N), box {32, bw, bh, 1}, 128-byte swizzle, zero OOB fill
-static int make_act_map(CUtensorMap* m, const float* base, int C, int W, int H, int N, int bw, int bh) {
+// estride = traversal stride of the W/H dims (2 for stride-2 convolutions: the box spans 2x the pixels
+// and the TMA unit picks every 2nd one)
+static int make_act_map(CUtensorMap* m, const float* base, int C, int W, int H, int N, int bw, int bh, int estride = 1) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return PXL_ERR_UNSUPPORTED;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {32, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+    if (box[1] > 256 || box[2] > 256) return PXL_ERR_UNSUPPORTED;
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -172,7 +175,9 @@ struct TcParams {
     int BW, BH, tilesW, tilesH;
     int BN, stages, nsplit;
     int nacc;       // TMEM accumulators used round-robin over k-iterations (summed with RN adds in the epilogue)
-    short dy[PXL_MAX_TAPS], dx[PXL_MAX_TAPS];
+    int in_mul;     // input pixel = output pixel * in_mul + tap (stride-2 forward uses the TMA traversal stride)
+    int out_mul, out_offy, out_offx, outH, outW;   // output pixel (oy,ox) is stored at (oy*out_mul+offy, ox*out_mul+offx)
+    short dy[PXL_MAX_TAPS], dx[PXL_MAX_TAPS], widx[PXL_MAX_TAPS];
 };
 
 #define TC_A_BYTES (128 * 128)          // 128 rows x 128 B
@@ -227,11 +232,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * 32;
                 uint8_t* sa = smem + (size_t)s * stage_bytes;
                 mbar_expect_tx(&full_bar[s], tx);
-                tma_load_4d(sa, &mapA, &full_bar[s], c0, w0 + p.dx[tap], h0 + p.dy[tap], n);
-                tma_load_2d(sa + TC_A_BYTES, &mapB, &full_bar[s], tap * p.Cin + c0, n0);
+                const int ax = w0 * p.in_mul + p.dx[tap], ay = h0 * p.in_mul + p.dy[tap];
+                const int bk = p.widx[tap] * p.Cin + c0;
+                tma_load_4d(sa, &mapA, &full_bar[s], c0, ax, ay, n);
+                tma_load_2d(sa + TC_A_BYTES, &mapB, &full_bar[s], bk, n0);
                 if (p.nsplit == 3) {
-                    tma_load_4d(sa + per_op, &mapAlo, &full_bar[s], c0, w0 + p.dx[tap], h0 + p.dy[tap], n);
-                    tma_load_2d(sa + per_op + TC_A_BYTES, &mapBlo, &full_bar[s], tap * p.Cin + c0, n0);
+                    tma_load_4d(sa + per_op, &mapAlo, &full_bar[s], c0, ax, ay, n);
+                    tma_load_2d(sa + per_op + TC_A_BYTES, &mapBlo, &full_bar[s], bk, n0);
                 }
             }
         }
@@ -273,7 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int hy = r / p.BW, wx = r - hy * p.BW;
             const int oy = h0 + hy, ox = w0 + wx;
             const bool valid = hy < p.BH && oy < p.OH && ox < p.OW;
-            float* orow = out + ((int64_t)(n * p.OH + oy) * p.OW + ox) * p.ldo;
+            float* orow = out + ((int64_t)(n * p.outH + oy * p.out_mul + p.out_offy) * p.outW + ox * p.out_mul + p.out_offx) * p.ldo;
             const int used = iters < p.nacc ? iters : p.nacc;
             for (int j = 0; j < p.BN; j += 32) {
                 float v[32];
@@ -358,30 +365,52 @@ static void pick_tile(int OH, int OW, bool flat, int& BW, int& BH) {
     }
 }
 
+extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, const pxl_conv_tc_ext* ext,
+                                     const float* in_hi, const float* in_lo, const float* w_hi, const float* w_lo,
+                                     const float* bias, float* out, void* stream);
+
 // lo parts: for precision 2 the caller passes hi/lo through `in`/`w` (hi) and the extra pointers
 extern "C" int pxl_conv_tc_launch(const pxl_conv_geom* g, const int* taps, const float* in_hi, const float* in_lo,
                                   const float* w_hi, const float* w_lo, const float* bias, float* out, void* stream) {
+    return pxl_conv_tc_launch_ex(g, taps, nullptr, in_hi, in_lo, w_hi, w_lo, bias, out, stream);
+}
+
+extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, const pxl_conv_tc_ext* ext,
+                                     const float* in_hi, const float* in_lo, const float* w_hi, const float* w_lo,
+                                     const float* bias, float* out, void* stream) {
     if (!g || !taps || !in_hi || !w_hi || !out) return PXL_ERR_BAD_ARG;
-    if (g->mul != 1 || g->div != 1) return PXL_ERR_UNSUPPORTED;           // strided convs stay on the FFMA kernel
+    if ((g->mul != 1 && g->mul != 2) || g->div != 1) return PXL_ERR_UNSUPPORTED;
     if (g->Cin % 32 != 0 || g->ntaps > PXL_MAX_TAPS) return PXL_ERR_UNSUPPORTED;
+    const int wtaps = ext && ext->w_ntaps > 0 ? ext->w_ntaps : g->ntaps;    // taps in the weight tensor
     const int nsplit = g->precision == 2 ? 3 : 1;
     if (nsplit == 3 && (!in_lo || !w_lo)) return PXL_ERR_BAD_ARG;
-    bool flat = (g->ntaps == 1 && taps[0] == 0 && taps[1] == 0 && g->OH == g->H && g->OW == g->W);
+    const bool has_out_xform = ext && (ext->out_mul != 1 || ext->out_offy != 0 || ext->out_offx != 0);
+    bool flat = (g->ntaps == 1 && taps[0] == 0 && taps[1] == 0 && g->OH == g->H && g->OW == g->W && g->mul == 1 &&
+                 !has_out_xform);
     TcParams p;
     p.Cin = g->Cin; p.Cout = g->Cout; p.ldo = g->ldo; p.ntaps = g->ntaps; p.kchunks = g->Cin / 32;
     p.nsplit = nsplit;
-    for (int t = 0; t < g->ntaps; ++t) { p.dy[t] = (short)taps[2 * t]; p.dx[t] = (short)taps[2 * t + 1]; }
+    for (int t = 0; t < g->ntaps; ++t) {
+        p.dy[t] = (short)taps[2 * t]; p.dx[t] = (short)taps[2 * t + 1];
+        p.widx[t] = (short)((ext && ext->widx_host) ? ext->widx_host[t] : t);
+        if (p.widx[t] < 0 || p.widx[t] >= wtaps) return PXL_ERR_BAD_ARG;
+    }
+    p.in_mul = g->mul;
+    p.out_mul = ext ? ext->out_mul : 1; p.out_offy = ext ? ext->out_offy : 0; p.out_offx = ext ? ext->out_offx : 0;
     int mapW, mapH, mapN;
     if (flat) {
         const int64_t M = (int64_t)g->N * g->H * g->W;
         if (M >= (1ll << 31)) return PXL_ERR_UNSUPPORTED;
         p.N = 1; p.OH = 1; p.OW = (int)M;
         mapW = (int)M; mapH = 1; mapN = 1;
+        p.outH = 1; p.outW = (int)M;
     } else {
         p.N = g->N; p.OH = g->OH; p.OW = g->OW;
         mapW = g->W; mapH = g->H; mapN = g->N;
+        p.outH = has_out_xform ? ext->out_H : g->OH; p.outW = has_out_xform ? ext->out_W : g->OW;
     }
     pick_tile(p.OH, p.OW, flat, p.BW, p.BH);
+    if (g->mul == 2 && (p.BW > 128 || p.BH > 128)) return PXL_ERR_UNSUPPORTED;
     p.tilesW = (p.OW + p.BW - 1) / p.BW; p.tilesH = (p.OH + p.BH - 1) / p.BH;
     p.BN = g->Cout > 128 ? 256 : (g->Cout > 64 ? 128 : (g->Cout > 32 ? 64 : 32));
     if (nsplit == 3 && p.BN > 128) p.BN = 128;                 // leave TMEM room for 4 accumulators
@@ -395,14 +424,14 @@ extern "C" int pxl_conv_tc_launch(const pxl_conv_geom* g, const int* taps, const
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
 
     CUtensorMap mA, mAlo, mB, mBlo;
-    int rc = make_act_map(&mA, in_hi, g->Cin, mapW, mapH, mapN, p.BW, p.BH);
+    int rc = make_act_map(&mA, in_hi, g->Cin, mapW, mapH, mapN, p.BW, p.BH, g->mul);
     if (rc) return rc;
-    rc = make_w_map(&mB, w_hi, (int64_t)g->ntaps * g->Cin, g->Cout, p.BN);
+    rc = make_w_map(&mB, w_hi, (int64_t)wtaps * g->Cin, g->Cout, p.BN);
     if (rc) return rc;
     if (nsplit == 3) {
-        rc = make_act_map(&mAlo, in_lo, g->Cin, mapW, mapH, mapN, p.BW, p.BH);
+        rc = make_act_map(&mAlo, in_lo, g->Cin, mapW, mapH, mapN, p.BW, p.BH, g->mul);
         if (rc) return rc;
-        rc = make_w_map(&mBlo, w_lo, (int64_t)g->ntaps * g->Cin, g->Cout, p.BN);
+        rc = make_w_map(&mBlo, w_lo, (int64_t)wtaps * g->Cin, g->Cout, p.BN);
         if (rc) return rc;
     } else {
         mAlo = mA; mBlo = mB;

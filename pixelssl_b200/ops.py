@@ -12,7 +12,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ConvGeom, call
+from ._lib import ConvGeom, ConvTcExt, call
 
 CL = torch.channels_last
 # conv precision policy (pxl_conv_geom.precision): 0 fp32 FFMA, 1 TF32 tcgen05, 2 3xTF32 tcgen05
@@ -327,14 +327,20 @@ def split_tf32(x):
 
 
 def tc_supported(Cin, mul, div):
-    """Shapes covered by the tcgen05 forward/dgrad kernel (csrc/conv_tc.cu)."""
-    return mul == 1 and div == 1 and Cin % 32 == 0
+    """Shapes covered by the tcgen05 forward/dgrad kernel (csrc/conv_tc.cu): stride 1 and 2 forward
+    (mul), and the dgrad of a stride-2 convolution (div == 2, decomposed by output parity)."""
+    return Cin % 32 == 0 and ((div == 1 and mul in (1, 2)) or (div == 2 and mul == 1))
+
+
+def _tc_launch(geom, taps, ext, x_parts, w_parts, bias, out):
+    call('pxl_conv_tc_launch_ex', ctypes.byref(geom), _ctaps(taps), ctypes.byref(ext) if ext is not None else None,
+         _p(x_parts[0]), _p(x_parts[1]), _p(w_parts[0]), _p(w_parts[1]), _p(bias), _p(out), _stream())
 
 
 def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, out=None, precision=None):
     """Launch the NHWC tap-table convolution on raw buffers.  w_packed: [Cout][ntaps][Cin] contiguous.
     precision 0: FFMA kernel; 1: tcgen05 single-pass TF32; 2: tcgen05 3xTF32 (operands split on the
-    fly).  Shapes the tensor-core kernel does not cover (strided, Cin % 32 != 0) use the FFMA kernel."""
+    fly).  Shapes the tensor-core kernel does not cover (Cin % 32 != 0, other strides) use the FFMA kernel."""
     ntaps = len(taps) // 2
     prec = _conv_precision if precision is None else precision
     if out is None:
@@ -342,15 +348,33 @@ def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div,
         if ldo != Cout:
             out.zero_()
     if prec != 0 and tc_supported(Cin, mul, div):
-        geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
-        if prec == 2:
-            x_hi, x_lo = split_tf32(x)
-            w_hi, w_lo = split_tf32(w_packed)
-            call('pxl_conv_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x_hi), _p(x_lo), _p(w_hi), _p(w_lo),
-                 _p(bias), _p(out), _stream())
-        else:
-            call('pxl_conv_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x), _p(None), _p(w_packed), _p(None),
-                 _p(bias), _p(out), _stream())
+        x_parts = split_tf32(x) if prec == 2 else (x, None)
+        w_parts = split_tf32(w_packed) if prec == 2 else (w_packed, None)
+        if div == 1:
+            geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, 1, ntaps, prec)
+            _tc_launch(geom, taps, None, x_parts, w_parts, bias, out)
+            return out
+        # dgrad of a stride-2 convolution: output pixel (iy, ix) only receives the taps with
+        # (iy + dy) and (ix + dx) even; per output parity class that is a stride-1 problem over dY
+        classes = []
+        for py in (0, 1):
+            for px in (0, 1):
+                sub, widx = [], []
+                for t in range(ntaps):
+                    dy, dx = taps[2 * t], taps[2 * t + 1]
+                    if (py + dy) % 2 == 0 and (px + dx) % 2 == 0:
+                        sub += [(py + dy) // 2, (px + dx) // 2]
+                        widx.append(t)
+                classes.append((py, px, sub, widx))
+        if any(len(c[3]) == 0 for c in classes):
+            out.zero_()
+        for py, px, sub, widx in classes:
+            ohs, ows = (OH - py + 1) // 2, (OW - px + 1) // 2
+            if not widx or ohs <= 0 or ows <= 0:
+                continue
+            geom = ConvGeom(N, H, W, Cin, ohs, ows, Cout, ldo, 1, 1, len(widx), prec)
+            ext = ConvTcExt(ntaps, (ctypes.c_int * len(widx))(*widx), 2, py, px, OH, OW)
+            _tc_launch(geom, sub, ext, x_parts, w_parts, bias, out)
         return out
     geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, 0)
     call('pxl_conv_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(w_packed), _p(bias), _p(out), _stream())

@@ -73,8 +73,9 @@ def test_conv_tc_forward_and_dgrad(ops, case, precision, tol):
 
 @pytest.mark.parametrize('precision,tol', [(2, 5e-5), (1, 2e-3)])
 @pytest.mark.parametrize('case', [(2, 128, 33, 35, 128, 3), (2, 256, 17, 17, 512, 1), (1, 64, 65, 65, 64, 3)])
-def test_conv_tc_stride2_wgrad(ops, case, precision, tol):
-    """stride-2 convolutions: forward/dgrad stay on the FFMA kernel, wgrad uses the TMA traversal stride."""
+def test_conv_tc_stride2(ops, case, precision, tol):
+    """stride-2 convolutions: forward and wgrad use the TMA traversal stride, dgrad is decomposed by
+    output parity into four stride-1 launches."""
     N, Cin, H, W, Cout, k = case
     g = torch.Generator().manual_seed(H + Cout)
     x = torch.randn(N, Cin, H, W, generator=g).cuda().contiguous(memory_format=CL)
@@ -83,14 +84,15 @@ def test_conv_tc_stride2_wgrad(ops, case, precision, tol):
     for prec in (0, precision):
         ops._conv_precision = prec
         wg = w.clone().requires_grad_(True)
-        y = ops.conv2d(x, wg, None, 2, k // 2, 1)
+        xg = x.clone().requires_grad_(True)
+        y = ops.conv2d(xg, wg, None, 2, k // 2, 1)
         y.backward(torch.ones_like(y) * 0.5 + y.detach() * 0.1)
-        res[prec] = wg.grad
+        res[prec] = (y.detach(), xg.grad, wg.grad)
     ops._conv_precision = 0
     assert ops.conv_tc_status() == 0
-    ew = rel(res[precision], res[0])
-    print('stride-2 case %s precision %d: wgrad %.2e' % (case, precision, ew))
-    assert ew <= tol, ew
+    ef, eb, ew = (rel(res[precision][i], res[0][i]) for i in range(3))
+    print('stride-2 case %s precision %d: fwd %.2e dgrad %.2e wgrad %.2e' % (case, precision, ef, eb, ew))
+    assert ef <= tol and eb <= tol and ew <= tol, (ef, eb, ew)
 
 
 @pytest.mark.parametrize('precision,tol', [(2, 5e-5), (1, 2e-3)])
