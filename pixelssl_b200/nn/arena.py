@@ -49,6 +49,7 @@ class ParamArena:
         return seg.view(p.shape)
 
     def zero_grad(self):
+        ops.new_step()
         self.grad.zero_()
         for p, o in zip(self.params, self.offsets):
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
@@ -94,7 +95,7 @@ class ParamArena:
                         o, n = self._index[id(p)]
                         optimizer.state[p]['momentum_buffer'] = self._view_like(self.mom, o, p)
         self.steps += 1
-
+        ops.new_step()           # parameters changed under torch's feet: drop cached tf32 splits
 
     def adopt_optimizer_state(self, optimizer):
         """After ``optimizer.load_state_dict`` (resume): pull the loaded momentum buffers into the

@@ -319,11 +319,36 @@ def _ctaps(t):
     return (ctypes.c_int * len(t))(*t)
 
 
+_epoch = 0
+ACCUM_WGRAD_INPLACE = True      # wgrad kernels add straight into weight.grad (the flat gradient arena)
+
+
+def new_step():
+    """Called once per training step: invalidates the cached tf32 splits of the weights (the fused
+    SGD kernel updates parameters through raw pointers, invisible to torch's version counters)."""
+    global _epoch
+    _epoch += 1
+
+
 def split_tf32(x):
     """x (any shape, numel % 4 == 0) -> (hi, lo): hi = tf32(x) with a zero low mantissa, lo = x - hi."""
     hi, lo = torch.empty_like(x), torch.empty_like(x)
     call('pxl_split_tf32', _p(x), _p(hi), _p(lo), x.numel(), _stream())
     return hi, lo
+
+
+def split_cached(x):
+    """split_tf32 memoised on the tensor object (an activation feeding two convolutions, a weight
+    used by several launches of one step).  Invalidated by in-place edits and by new_step()."""
+    ent = getattr(x, '_pxl_parts', None)
+    if ent is not None and ent[0] == _epoch and ent[1] == x._version and ent[2] == x.data_ptr():
+        return ent[3]
+    parts = split_tf32(x)
+    try:
+        x._pxl_parts = (_epoch, x._version, x.data_ptr(), parts)
+    except Exception:
+        pass
+    return parts
 
 
 def tc_supported(Cin, mul, div):
@@ -344,12 +369,16 @@ def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div,
     ntaps = len(taps) // 2
     prec = _conv_precision if precision is None else precision
     if out is None:
-        out = torch.empty((N, ldo, OH, OW), dtype=torch.float32, device=x.device, memory_format=CL)
+        dev = x[0].device if isinstance(x, tuple) else x.device
+        out = torch.empty((N, ldo, OH, OW), dtype=torch.float32, device=dev, memory_format=CL)
         if ldo != Cout:
             out.zero_()
     if prec != 0 and tc_supported(Cin, mul, div):
-        x_parts = split_tf32(x) if prec == 2 else (x, None)
-        w_parts = split_tf32(w_packed) if prec == 2 else (w_packed, None)
+        if prec == 2:
+            x_parts = x if isinstance(x, tuple) else split_cached(x)
+            w_parts = w_packed if isinstance(w_packed, tuple) else split_cached(w_packed)
+        else:
+            x_parts, w_parts = (x, None), (w_packed, None)
         if div == 1:
             geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, 1, ntaps, prec)
             _tc_launch(geom, taps, None, x_parts, w_parts, bias, out)
@@ -376,6 +405,10 @@ def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div,
             ext = ConvTcExt(ntaps, (ctypes.c_int * len(widx))(*widx), 2, py, px, OH, OW)
             _tc_launch(geom, sub, ext, x_parts, w_parts, bias, out)
         return out
+    if isinstance(x, tuple):
+        x = x[0] + x[1]
+    if isinstance(w_packed, tuple):
+        w_packed = w_packed[0] + w_packed[1]
     geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, 0)
     call('pxl_conv_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(w_packed), _p(bias), _p(out), _stream())
     return out
@@ -393,14 +426,18 @@ def conv_wgrad_raw(x, dy, dw, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, p
     if prec != 0 and div == 1 and mul in _WGRAD_TC_STRIDES and Cin % 32 == 0 and ldo % 32 == 0:
         geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
         if prec == 2:
-            x_hi, x_lo = split_tf32(x)
-            d_hi, d_lo = split_tf32(dy)
+            x_hi, x_lo = x if isinstance(x, tuple) else split_cached(x)
+            d_hi, d_lo = dy if isinstance(dy, tuple) else split_cached(dy)
             call('pxl_conv_wgrad_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x_hi), _p(x_lo), _p(d_hi), _p(d_lo),
                  _p(dw), _stream())
         else:
             call('pxl_conv_wgrad_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x), _p(None), _p(dy), _p(None),
                  _p(dw), _stream())
         return dw
+    if isinstance(x, tuple):
+        x = x[0] + x[1]
+    if isinstance(dy, tuple):
+        dy = dy[0] + dy[1]
     geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, 0)     # FFMA split-K kernel
     call('pxl_conv_wgrad_nhwc', ctypes.byref(geom), _ctaps(taps), _p(x), _p(dy), _p(dw), _stream())
     return dw
@@ -425,24 +462,44 @@ class _Conv2d(torch.autograd.Function):
         OH = (H + 2 * padding - dilation * (kh - 1) - 1) // stride + 1
         OW = (W + 2 * padding - dilation * (kw - 1) - 1) // stride + 1
         taps = _taps(kh, kw, dilation, padding)
-        out = conv_raw(x, weight, bias, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1)
-        ctx.save_for_backward(x, weight)
+        split = _conv_precision == 2 and tc_supported(Cin, stride, 1)
+        xin = split_cached(x) if split else x
+        win = split_cached(weight) if split else weight
+        out = conv_raw(xin, win, bias, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1)
+        if split:     # keep the split operand for wgrad instead of x (x = hi + lo exactly)
+            ctx.save_for_backward(xin[0], xin[1], weight)
+        else:
+            ctx.save_for_backward(x, weight)
+        ctx.split = split
         ctx.meta = (taps, N, H, W, Cin, OH, OW, Cout, stride, kh * kw, bias is not None)
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        if ctx.split:
+            x_hi, x_lo, weight = ctx.saved_tensors
+            x = (x_hi, x_lo)
+        else:
+            x, weight = ctx.saved_tensors
         taps, N, H, W, Cin, OH, OW, Cout, stride, T, has_bias = ctx.meta
         dy = as_cl(dy)
         dx = dw = db = None
+        dyin = dy
+        if _conv_precision == 2 and Cout % 32 == 0:
+            dyin = split_cached(dy)       # shared by dgrad and wgrad
         if ctx.needs_input_grad[0]:
-            wt = transpose_weights(weight, Cout, T, Cin)
+            if isinstance(dyin, tuple) and tc_supported(Cout, 1, stride):
+                w_hi, w_lo = split_cached(weight)
+                wt = (transpose_weights(w_hi, Cout, T, Cin), transpose_weights(w_lo, Cout, T, Cin))
+            else:
+                wt = transpose_weights(weight, Cout, T, Cin)
             ntaps = [-v for v in taps]
-            dx = conv_raw(dy, wt, None, ntaps, N, OH, OW, Cout, H, W, Cin, Cin, 1, stride)
+            dx = conv_raw(dyin, wt, None, ntaps, N, OH, OW, Cout, H, W, Cin, Cin, 1, stride)
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros_like(weight, memory_format=torch.preserve_format)
-            conv_wgrad_raw(x, dy, dw, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1)
+            inplace = ACCUM_WGRAD_INPLACE and weight.grad is not None and weight.grad.is_contiguous(memory_format=CL)
+            dwbuf = weight.grad if inplace else torch.zeros_like(weight, memory_format=torch.preserve_format)
+            conv_wgrad_raw(x, dyin, dwbuf, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1)
+            dw = None if inplace else dwbuf
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(Cout, dtype=torch.float32, device=dy.device)
             call('pxl_bias_grad', _p(dy), N * OH * OW, Cout, Cout, _p(db), 0, _stream())
