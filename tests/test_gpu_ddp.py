@@ -1,0 +1,96 @@
+"""2-GPU NCCL test: one process per GPU, each with (1 labeled + 1 unlabeled) images, must reproduce
+the single-GPU step on the combined (2 + 2) batch: same losses, same averaged gradients, same BN
+running statistics (the reference synchronises BN statistics across replicas,
+sync_batchnorm/batchnorm.py:55-78).  Skipped unless two GPUs are visible."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _cfg(bs, ubs):
+    return {'ssl_algorithm': 'ssl_mt', 'cons_for_labeled': False, 'cons_scale': 1.0, 'cons_rampup_epochs': 0,
+            'ema_decay': 0.99, 'lr': 0.00025, 'momentum': 0.9, 'weight_decay': 0.0005, 'epochs': 2,
+            'batch_size': bs, 'unlabeled_batch_size': ubs, 'log_freq': 10 ** 6}
+
+
+def _run_step(alg, img, lab):
+    alg._train([((img,), (lab,))], 0)
+    sp = dict(alg.s_model.module.model.named_parameters())
+    grads = torch.cat([p.grad.contiguous().reshape(-1) for p in sp.values()]).cpu()
+    params = alg.s_model.arena.data.cpu().clone()
+    bufs = torch.cat([b.reshape(-1).float() for n, b in alg.s_model.named_buffers() if 'num_batches' not in n]).cpu()
+    return (float(alg.meters['s_task_loss'].val), float(alg.meters['cons_loss'].val), grads, params, bufs)
+
+
+def _worker(rank, world, port, size, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        import logging
+        logging.getLogger('PixelSSL').setLevel(logging.ERROR)
+        from pixelssl_b200 import runner, ops
+        from oracle import sseg_oracle as O
+        ops.set_conv_precision('fp32')
+        alg = runner.build_algorithm(runner.build_args(_cfg(2, 1), iters_per_epoch=5))
+        st = {k: v for k, v in O.randomize_bn_affine(O.init_deeplabv2(71, cls_bias_std=0.01), 72).items()}
+        alg.s_model.load_state_dict({'module.model.' + k: v for k, v in st.items()})
+        alg.t_model.load_state_dict({'module.model.' + k: v for k, v in st.items()})
+        img, lab = O.synthetic_batch(500, 4, 2, size, size)          # global batch [L0, L1, U0, U1]
+        idx = [rank, 2 + rank]
+        out = _run_step(alg, img[idx].contiguous(), lab[idx].contiguous())
+        if rank == 0:
+            q.put(tuple(o if not torch.is_tensor(o) else o.numpy() for o in out))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_step_equals_single_gpu_big_batch():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    size = 65
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, size, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    l2, c2, g2, p2, b2 = q.get(timeout=280)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single GPU, combined batch
+    import logging
+    logging.getLogger('PixelSSL').setLevel(logging.ERROR)
+    from pixelssl_b200 import runner, ops
+    from oracle import sseg_oracle as O
+    ops.set_conv_precision('fp32')
+    alg = runner.build_algorithm(runner.build_args(_cfg(4, 2), iters_per_epoch=5))
+    st = O.randomize_bn_affine(O.init_deeplabv2(71, cls_bias_std=0.01), 72)
+    alg.s_model.load_state_dict({'module.model.' + k: v for k, v in st.items()})
+    alg.t_model.load_state_dict({'module.model.' + k: v for k, v in st.items()})
+    img, lab = O.synthetic_batch(500, 4, 2, size, size)
+    l1, c1, g1, p1, b1 = _run_step(alg, img, lab)
+    g1, p1, b1 = g1.numpy(), p1.numpy(), b1.numpy()
+    # rank-0 loss is the mean over ITS samples; gradients/params/BN buffers must match the big batch
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+    print('ddp vs big batch: grad %.2e params %.2e bn buffers %.2e' % (rel(g2, g1), rel(p2, p1), rel(b2, b1)))
+    assert rel(b2, b1) <= 1e-4        # synchronised batch statistics
+    assert rel(p2, p1) <= 1e-5
+    assert rel(g2, g1) <= 5e-2        # whole-network gradient: fp32-noise floor of this net (see test_gpu_model)
