@@ -53,13 +53,15 @@ class BatchNorm2d(nn.Module):
         self.register_buffer('running_var', torch.ones(num_features))
         self.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
         self.sync_group = None
+        self.multi_replica_formula = False     # clamp(var, eps) instead of var + eps (batchnorm.py:125)
 
     def forward(self, x, relu=False, residual=None):
         if self.training:
             self.num_batches_tracked += 1
         return ops.bn_act(ops.as_cl(x), self.weight, self.bias, self.running_mean, self.running_var,
                           training=self.training, momentum=self.momentum, eps=self.eps, relu=relu,
-                          residual=residual, group=self.sync_group if self.training else None)
+                          residual=residual, group=self.sync_group if self.training else None,
+                          clamp_var=self.multi_replica_formula)
 
     def extra_repr(self):
         return '{num_features}, eps={eps}, momentum={momentum}'.format(**self.__dict__)

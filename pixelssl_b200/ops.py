@@ -601,7 +601,7 @@ class _BnAct(torch.autograd.Function):
     ranks share batch statistics (the reference's cross-replica SyncBN); None = local."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps, relu, group):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps, relu, group, clamp_var):
         _chk(x, 'x', cl=True)
         N, C, H, W = x.shape
         rows = N * H * W
@@ -609,7 +609,7 @@ class _BnAct(torch.autograd.Function):
         y = torch.empty_like(x)
         coeff = torch.empty((4, C), dtype=torch.float32, device=dev)     # mean, invstd, scale, shift
         count = float(rows)
-        clamp = 0
+        clamp = 1 if clamp_var else 0
         if training:
             sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
             call('pxl_bn_stats', _p(x), rows, C, _p(sums), _stream())
@@ -651,13 +651,15 @@ class _BnAct(torch.autograd.Function):
         dres = torch.empty_like(x) if has_res else None
         call('pxl_bn_bwd_dx', _p(x), _p(y), _p(dy), _p(coeff[0]), _p(coeff[1]), _p(gamma), _p(dsums), count, int(relu),
              _p(dx), _p(dres), rows, C, _stream())
-        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
 
 
 def bn_act(x, gamma, beta, running_mean, running_var, training=True, momentum=0.1, eps=1e-5, relu=False,
-           residual=None, group=None):
+           residual=None, group=None, clamp_var=False):
+    """clamp_var: use the reference's multi-replica formula inv_std = clamp(var, eps)^-1/2
+    (batchnorm.py:125) instead of (var + eps)^-1/2; implied when ``group`` spans several ranks."""
     return _BnAct.apply(x, gamma, beta, running_mean, running_var, residual, bool(training), float(momentum),
-                        float(eps), bool(relu), group)
+                        float(eps), bool(relu), group, bool(clamp_var))
 
 
 class _MaxPool(torch.autograd.Function):
