@@ -221,6 +221,39 @@ int pxl_sgd_ema(float* p, const float* g, float* buf, float* teacher, int64_t n,
                 float momentum, float weight_decay, float ema_d, int first_step, void* stream);
 int pxl_ema(float* teacher, const float* student, int64_t n, float ema_d, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * AdvSSL / GCT / CCT tails
+ * ------------------------------------------------------------------------------------------- */
+/* planar [n,C,HW] <-> NHWC [n,HW,ldc] lanes [coff, coff+C): inputs of FCDiscriminator.forward
+ * (ssl_adv.py:472-488) and FlawDetector.forward (ssl_gct.py:566-570, cat(image, softmax)) */
+int pxl_planar_to_nhwc(const float* in, float* out, int n, int C, int64_t HW, int ldc, int coff, void* stream);
+int pxl_nhwc_to_planar(const float* in, float* out, int n, int C, int64_t HW, int ldc, int coff, void* stream);
+/* one-hot of the float labels into NHWC lanes (ignore / out-of-range -> all zero):
+ * ssladv_convert_task_gt_to_fcd_input, sslgct_prepare_task_gt_for_fdgt (task/sseg/func.py:157-192) */
+int pxl_onehot_nhwc(const float* labels, float* out, int64_t pixels, int C, int ldc, int coff, void* stream);
+/* LeakyReLU(slope) forward/backward (ssl_adv.py:478, ssl_gct.py:563); n % 4 == 0 */
+int pxl_leaky_relu_fwd(const float* x, float* y, int64_t n, float slope, void* stream);
+int pxl_leaky_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, float slope, void* stream);
+/* FCDiscriminatorCriterion (ssl_adv.py:496-503) fused with ssladv_preprocess_fcd_criterion
+ * (task/sseg/func.py:137-155): BCE-with-logits against the constant `target`, pixels whose task label
+ * (nullable) equals ignore_index contribute bce(0,0)=ln2 and no gradient; per_sample = mean over HW */
+int pxl_bce_logits_masked(const float* pred, const float* labels, float target, int ignore_index, int n,
+                          int64_t HW, float* per_sample, float* grad, const float* upstream,
+                          float upstream_const, void* stream);
+/* torch.optim.Adam step (no amsgrad) over a flat arena: ssl_adv.py:101-102, ssl_gct.py:153-154 */
+int pxl_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+             float eps, float weight_decay, int step, void* stream);
+/* GaussianBlurLayer (nn/module/gaussian_blur.py:18-64) on [n,H,W] maps as two 1-D reflect-padded
+ * passes with the 1-D kernel weights_1d[k] (device); FlawmapHandler / FDGTGenerator, ssl_gct.py:624-728 */
+int pxl_gauss_blur_sep(const float* in, float* tmp, float* out, int n, int H, int W, int k,
+                       const float* weights_1d, float clamp_min, void* stream);
+/* ReflectionPad2d(1) + MaxPool2d(3,1): FDGTGenerator.dilate, ssl_gct.py:708-712 */
+int pxl_dilate3x3_reflect(const float* in, float* out, int n, int H, int W, void* stream);
+/* per-sample (x-min)/(max-min+eps); zero_below >= 0: zero the map first when its max <= zero_below,
+ * with min/max taken before zeroing (FlawmapHandler quirk, ssl_gct.py:648-654) */
+int pxl_minmax_norm(const float* in, float* out, int n, int64_t HW, float eps, float zero_below,
+                    float clamp_min, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

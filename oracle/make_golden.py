@@ -297,6 +297,33 @@ def golden_null_cutmix(pixelssl, sseg_proxy, size=65):
     print('cutmix golden:', rec['task_loss'], rec['cons_loss'])
 
 
+def golden_adv(pixelssl, sseg_proxy, size=65):
+    """One SSLADV._train step (ssl_adv.py:118-283): lbs 2 + ubs 2, adversarial terms on both."""
+    from oracle import adv_oracle as A
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    args = make_args(pixelssl, sseg_proxy, 'ssl_adv',
+                     {'adv_for_labeled': True, 'labeled_adv_scale': 0.01, 'unlabeled_adv_scale': 0.001,
+                      'discriminator_lr': 1e-4, 'discriminator_scale': 1.0, 'unlabeled_for_discriminator': True}, 4, 2)
+    alg = build_algorithm(pixelssl, args, 'ssl_adv')
+    load_state(alg.model, O.randomize_bn_affine(O.init_deeplabv2(81, cls_bias_std=0.01), 82))
+    alg.d_model.load_state_dict({'module.' + k: v.clone() for k, v in A.init_fcd(83).items()}, strict=True)
+    img, lab = O.synthetic_batch(600, 4, 2, size, size)
+    alg._train([((img.clone(),), (lab.clone(),))], 0)
+    sp = dict(alg.model.module.model.named_parameters())
+    dp = dict(alg.d_model.module.named_parameters())
+    dnames = [n for n, _ in A.fcd_shapes()]
+    rec = {'size': size}
+    for k in ('task_loss', 'labeled_adv_loss', 'unlabeled_adv_loss', 'fake_d_loss', 'real_d_loss'):
+        rec[k] = float(alg.meters[k].val)
+    rec['grad_checksum'] = checksums([(n, sp[n].grad) for n in names])
+    rec['param_checksum'] = checksums([(n, sp[n]) for n in names])
+    rec['d_grad_checksum'] = checksums([(n, dp[n].grad) for n in dnames])
+    rec['d_param_checksum'] = checksums([(n, dp[n]) for n in dnames])
+    rec['d_lr'] = alg.d_optimizer.param_groups[0]['lr']
+    np.savez_compressed(os.path.join(OUT, 'adv_step_%d.npz' % size), **rec)
+    print('adv golden:', {k: rec[k] for k in rec if 'loss' in k})
+
+
 def golden_fp64():
     """Exact-arithmetic (fp64) evaluation of the SAME steps with the oracle, to measure the
     reference's own fp32 rounding noise on these (ill-conditioned, random-init) networks.  The GPU
@@ -353,7 +380,7 @@ if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     pixelssl, sseg_proxy = patch_and_import()
-    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'fp64']
+    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 'fp64']
     if which == ['fp64']:
         golden_fp64()
         sys.exit(0)
@@ -365,5 +392,7 @@ if __name__ == '__main__':
         golden_mt(pixelssl, sseg_proxy)
     if 'nullcutmix' in which:
         golden_null_cutmix(pixelssl, sseg_proxy)
+    if 'adv' in which:
+        golden_adv(pixelssl, sseg_proxy)
     if 'fp64' in which:
         golden_fp64()

@@ -1,3 +1,326 @@
-// GCT / AdvSSL tail kernels (separable reflect-pad Gaussian blur, 3x3 dilate, min-max normalise,
-// masked BCE-with-logits).  Filled in as those rows of SURVEY.md section 8 are built.
+// Tail kernels of the adversarial / GCT / CCT algorithms: layout changes between the planar class
+// maps and the NHWC convolution inputs, LeakyReLU, masked BCE-with-logits, one-hot of the labels,
+// Adam on a flat arena, separable reflect-padded Gaussian blur, 3x3 dilation, per-sample min-max
+// normalisation.  All HBM-bound, one pass per tensor.
 #include "common.cuh"
+#include <math_constants.h>
+
+// ------------------------------------------------------------------------------------------
+// planar [n, C, HW]  <->  NHWC [n, HW, ldc] (lanes >= C zero-filled).  32 x 32 smem transpose tiles.
+//   feeds FCDiscriminator / FlawDetector inputs (ssl_adv.py:148, ssl_gct.py:566-570)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+planar_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int64_t HW, int ldc, int coff) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {          // r: channel, tx: pixel (coalesced planar read)
+        const int c = c0 + r;
+        const int64_t p = p0 + tx;
+        tile[r][tx] = (c < C && p < HW) ? __ldg(in + ((int64_t)n * C + c) * HW + p) : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {          // r: pixel, tx: channel (coalesced NHWC write)
+        const int64_t p = p0 + r;
+        const int c = c0 + tx;
+        if (p < HW && c < C) out[((int64_t)n * HW + p) * ldc + coff + c] = tile[tx][r];
+    }
+}
+
+// coff: first destination lane (lets two planar tensors be concatenated along channels)
+extern "C" int pxl_planar_to_nhwc(const float* in, float* out, int n, int C, int64_t HW, int ldc, int coff, void* stream) {
+    if (!in || !out || n <= 0 || C <= 0 || HW <= 0 || coff < 0 || coff + C > ldc || n > 65535) return PXL_ERR_BAD_ARG;
+    dim3 grid((unsigned)pxl_cdiv(HW, 32), (unsigned)pxl_cdiv(C, 32), (unsigned)n);
+    planar_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, HW, ldc, coff);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+nhwc_to_planar_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int64_t HW, int ldc, int coff) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {          // r: pixel, tx: channel
+        const int64_t p = p0 + r;
+        const int c = c0 + tx;
+        tile[r][tx] = (p < HW && c < C) ? __ldg(in + ((int64_t)n * HW + p) * ldc + coff + c) : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {          // r: channel, tx: pixel
+        const int c = c0 + r;
+        const int64_t p = p0 + tx;
+        if (c < C && p < HW) out[((int64_t)n * C + c) * HW + p] = tile[tx][r];
+    }
+}
+
+extern "C" int pxl_nhwc_to_planar(const float* in, float* out, int n, int C, int64_t HW, int ldc, int coff, void* stream) {
+    if (!in || !out || n <= 0 || C <= 0 || HW <= 0 || coff < 0 || coff + C > ldc || n > 65535) return PXL_ERR_BAD_ARG;
+    dim3 grid((unsigned)pxl_cdiv(HW, 32), (unsigned)pxl_cdiv(C, 32), (unsigned)n);
+    nhwc_to_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, HW, ldc, coff);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// one-hot of float labels into NHWC lanes [coff, coff+C); ignore / out-of-range labels -> all zero
+//   task/sseg/func.py:157-168 (AdvSSL real input), :179-192 (GCT)
+__global__ void __launch_bounds__(256)
+onehot_nhwc_kernel(const float* __restrict__ labels, float* __restrict__ out, int64_t total, int C, int ldc, int coff) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const float lf = __ldg(labels + i);
+        float* o = out + i * ldc + coff;
+        for (int c = 0; c < C; ++c) o[c] = (lf == (float)c) ? 1.f : 0.f;
+    }
+}
+
+extern "C" int pxl_onehot_nhwc(const float* labels, float* out, int64_t pixels, int C, int ldc, int coff, void* stream) {
+    if (!labels || !out || pixels <= 0 || C <= 0 || coff < 0 || coff + C > ldc) return PXL_ERR_BAD_ARG;
+    int blocks = (int)(pxl_cdiv(pixels, 256) < PXL_NUM_SMS * 8 ? pxl_cdiv(pixels, 256) : PXL_NUM_SMS * 8);
+    onehot_nhwc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(labels, out, pixels, C, ldc, coff);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// LeakyReLU (slope 0.2: ssl_adv.py:478, ssl_gct.py:549-563; slope 0 = ReLU) forward / backward
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+leaky_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4, float slope) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = x[i];
+        v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+        v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+        y[i] = v;
+    }
+}
+__global__ void __launch_bounds__(256)
+leaky_bwd_kernel(const float4* __restrict__ y, const float4* __restrict__ dy, float4* __restrict__ dx, int64_t n4, float slope) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 o = y[i];
+        float4 d = dy[i];
+        d.x = o.x > 0.f ? d.x : d.x * slope; d.y = o.y > 0.f ? d.y : d.y * slope;
+        d.z = o.z > 0.f ? d.z : d.z * slope; d.w = o.w > 0.f ? d.w : d.w * slope;
+        dx[i] = d;
+    }
+}
+static int ew_blocks(int64_t n4) { return (int)(pxl_cdiv(n4, 256 * 2) < PXL_NUM_SMS * 8 ? pxl_cdiv(n4, 256 * 2) : PXL_NUM_SMS * 8); }
+
+extern "C" int pxl_leaky_relu_fwd(const float* x, float* y, int64_t n, float slope, void* stream) {
+    if (!x || !y || n <= 0 || (n & 3)) return PXL_ERR_BAD_ARG;
+    leaky_fwd_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, n / 4, slope);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+extern "C" int pxl_leaky_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, float slope, void* stream) {
+    if (!y || !dy || !dx || n <= 0 || (n & 3)) return PXL_ERR_BAD_ARG;
+    leaky_bwd_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)y, (const float4*)dy, (float4*)dx, n / 4, slope);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// masked BCE-with-logits: FCDiscriminatorCriterion (ssl_adv.py:496-503) after
+// ssladv_preprocess_fcd_criterion (task/sseg/func.py:137-155): target = `target` everywhere, pixels
+// whose task label == ignore_index have BOTH prediction and target multiplied by 0, i.e. they
+// contribute bce(0, 0) = ln 2 (not 0) and no gradient.  per_sample[i] = mean over H*W.
+// ------------------------------------------------------------------------------------------
+template <bool WRITE_GRAD>
+__global__ void __launch_bounds__(256)
+bce_masked_kernel(const float* __restrict__ pred, const float* __restrict__ labels, float target, int ignore_index,
+                  int64_t HW, float* __restrict__ per_sample, float* __restrict__ grad,
+                  const float* __restrict__ upstream, float upstream_const) {
+    const int b = blockIdx.y;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float loss = 0.f;
+    if (p < HW) {
+        const int64_t i = (int64_t)b * HW + p;
+        bool keep = true;
+        if (labels) keep = !(__ldg(labels + i) == (float)ignore_index);
+        const float x = keep ? __ldg(pred + i) : 0.f;
+        const float z = keep ? target : 0.f;
+        loss = fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x)));
+        if (WRITE_GRAD) {
+            const float g = (upstream ? upstream[b] : upstream_const) / (float)HW;
+            const float sig = 1.f / (1.f + expf(-x));
+            grad[i] = keep ? g * (sig - z) : 0.f;
+        }
+    }
+    __shared__ float wp[8];
+    loss = warp_sum(loss);
+    if ((threadIdx.x & 31) == 0) wp[threadIdx.x >> 5] = loss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += wp[i];
+        atomicAdd(per_sample + b, s / (float)HW);
+    }
+}
+
+extern "C" int pxl_bce_logits_masked(const float* pred, const float* labels, float target, int ignore_index, int n,
+                                     int64_t HW, float* per_sample, float* grad, const float* upstream,
+                                     float upstream_const, void* stream) {
+    if (!pred || !per_sample || n <= 0 || HW <= 0 || n > 65535) return PXL_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(per_sample, 0, sizeof(float) * n, st);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)pxl_cdiv(HW, 256), (unsigned)n);
+    if (grad) bce_masked_kernel<true><<<grid, 256, 0, st>>>(pred, labels, target, ignore_index, HW, per_sample, grad, upstream, upstream_const);
+    else bce_masked_kernel<false><<<grid, 256, 0, st>>>(pred, labels, target, ignore_index, HW, per_sample, nullptr, nullptr, 0.f);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam semantics, no amsgrad) over a flat arena: the FC discriminator / flaw
+// detector optimiser (ssl_adv.py:101-102, ssl_gct.py:153-154: betas (0.9, 0.99))
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float grad = g[i];
+        const float pv = p[i];
+        if (wd != 0.f) grad = fmaf(wd, pv, grad);
+        const float mi = m[i] + (1.f - b1) * (grad - m[i]);          // lerp, like torch
+        const float vi = b2 * v[i] + (1.f - b2) * grad * grad;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pv - (lr / bc1) * (mi / denom);
+    }
+}
+
+extern "C" int pxl_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, int step, void* stream) {
+    if (!p || !g || !m || !v || n <= 0 || step < 1) return PXL_ERR_BAD_ARG;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    int blocks = (int)(pxl_cdiv(n, 256 * 4) < PXL_NUM_SMS * 8 ? pxl_cdiv(n, 256 * 4) : PXL_NUM_SMS * 8);
+    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2));
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Gaussian blur of single-channel maps [n, H, W]: ReflectionPad2d(k/2) + k x k depthwise conv
+// (nn/module/gaussian_blur.py:30-64).  The reference's k x k kernel is exactly outer(v, v), so the
+// blur is run as two 1-D passes (k up to 179 at 713^2: 90x fewer FLOPs than the direct form).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+template <bool VERT>
+__global__ void __launch_bounds__(256)
+blur1d_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int k, const float* __restrict__ wts,
+              float clamp_min) {
+    extern __shared__ float sw[];
+    for (int i = threadIdx.x; i < k; i += blockDim.x) sw[i] = __ldg(wts + i);
+    __syncthreads();
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const float* ip = in + (int64_t)b * H * W;
+    const int r = k / 2;
+    float acc = 0.f;
+    if (VERT) {
+        for (int t = 0; t < k; ++t) acc = fmaf(sw[t], __ldg(ip + (int64_t)reflect(y + t - r, H) * W + x), acc);
+    } else {
+        const float* row = ip + (int64_t)y * W;
+        for (int t = 0; t < k; ++t) acc = fmaf(sw[t], fmaxf(__ldg(row + reflect(x + t - r, W)), clamp_min), acc);
+    }
+    out[(int64_t)b * H * W + (int64_t)y * W + x] = acc;
+}
+
+// clamp_min: input values below it are raised to it first (FlawmapHandler zeroes negatives before
+// blurring, ssl_gct.py:645); pass -INFINITY to disable
+extern "C" int pxl_gauss_blur_sep(const float* in, float* tmp, float* out, int n, int H, int W, int k,
+                                  const float* weights_1d, float clamp_min, void* stream) {
+    if (!in || !tmp || !out || !weights_1d || n <= 0 || H <= 0 || W <= 0 || k <= 0 || !(k & 1)) return PXL_ERR_BAD_ARG;
+    if (k / 2 >= H || k / 2 >= W || n > 65535) return PXL_ERR_UNSUPPORTED;      // single reflection only, like ReflectionPad2d
+    dim3 grid((unsigned)pxl_cdiv(W, 32), (unsigned)pxl_cdiv(H, 8), (unsigned)n);
+    cudaStream_t st = (cudaStream_t)stream;
+    blur1d_kernel<false><<<grid, 256, k * sizeof(float), st>>>(in, tmp, H, W, k, weights_1d, clamp_min);
+    PXL_CHECK_LAUNCH();
+    blur1d_kernel<true><<<grid, 256, k * sizeof(float), st>>>(tmp, out, H, W, k, weights_1d, -3.0e38f);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// 3x3 max filter with reflection padding 1 (ssl_gct.py:708-712: ReflectionPad2d(1) + MaxPool2d(3, 1))
+__global__ void __launch_bounds__(256)
+dilate3x3_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const float* ip = in + (int64_t)b * H * W;
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx)
+            m = fmaxf(m, __ldg(ip + (int64_t)reflect(y + dy, H) * W + reflect(x + dx, W)));
+    out[(int64_t)b * H * W + (int64_t)y * W + x] = m;
+}
+
+extern "C" int pxl_dilate3x3_reflect(const float* in, float* out, int n, int H, int W, void* stream) {
+    if (!in || !out || n <= 0 || H < 2 || W < 2 || n > 65535) return PXL_ERR_BAD_ARG;
+    dim3 grid((unsigned)pxl_cdiv(W, 32), (unsigned)pxl_cdiv(H, 8), (unsigned)n);
+    dilate3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, H, W);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// per-sample min-max normalisation (x - min) / (max - min + eps); zero_below: if the sample's max
+// is <= zero_below the whole map is zeroed first (FlawmapHandler, ssl_gct.py:641-657; < 0 disables)
+__global__ void __launch_bounds__(512)
+minmax_norm_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t HW, float eps, float zero_below,
+                   float clamp_min) {
+    const int b = blockIdx.x;
+    const float* ip = in + (int64_t)b * HW;
+    float* op = out + (int64_t)b * HW;
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) {
+        float v = __ldg(ip + i);
+        if (v < clamp_min) v = clamp_min;
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    __shared__ float smn[16], smx[16];
+    mn = -warp_max(-mn); mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    mn = smn[0]; mx = smx[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) { mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
+    // reference quirk kept: min/max are taken BEFORE the map is zeroed (ssl_gct.py:648-654), so a
+    // zeroed map becomes the constant -min / (max - min + eps), not 0
+    const bool zero = (zero_below >= 0.f) && (mx <= zero_below);
+    const float denom = mx - mn + eps;
+    for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) {
+        float v = __ldg(ip + i);
+        if (v < clamp_min) v = clamp_min;
+        if (zero) v = 0.f;
+        op[i] = (v - mn) / denom;
+    }
+}
+
+// clamp_min: values below it are raised to it first (FlawmapHandler clamps negatives to 0; pass
+// -inf to disable).  in == out allowed.
+extern "C" int pxl_minmax_norm(const float* in, float* out, int n, int64_t HW, float eps, float zero_below,
+                               float clamp_min, void* stream) {
+    if (!in || !out || n <= 0 || HW <= 0) return PXL_ERR_BAD_ARG;
+    minmax_norm_kernel<<<n, 512, 0, (cudaStream_t)stream>>>(in, out, HW, eps, zero_below, clamp_min);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}

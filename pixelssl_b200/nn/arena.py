@@ -97,6 +97,29 @@ class ParamArena:
         self.steps += 1
         ops.new_step()           # parameters changed under torch's feet: drop cached tf32 splits
 
+    def adam_step(self, optimizer):
+        """torch.optim.Adam.step() semantics (no amsgrad) on the flat arena: the FC discriminator /
+        flaw detector optimiser (ssl_adv.py:101-102, ssl_gct.py:153-154)."""
+        if getattr(self, 'exp_avg', None) is None:
+            self.exp_avg = torch.zeros_like(self.data)
+            self.exp_avg_sq = torch.zeros_like(self.data)
+        self.steps += 1
+        for g in optimizer.param_groups:
+            if g.get('amsgrad', False) or g.get('maximize', False):
+                raise NotImplementedError('fused Adam supports amsgrad=False only')
+            b1, b2 = g['betas']
+            for a, b in self.segments(g['params']):
+                ops.adam_(self.data[a:b], self.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], g['lr'], b1, b2,
+                          g['eps'], g.get('weight_decay', 0.0), self.steps)
+            for p in g['params']:
+                st = optimizer.state[p]
+                if 'exp_avg' not in st:
+                    o, n = self._index[id(p)]
+                    st['exp_avg'] = self._view_like(self.exp_avg, o, p)
+                    st['exp_avg_sq'] = self._view_like(self.exp_avg_sq, o, p)
+                st['step'] = torch.tensor(float(self.steps))
+        ops.new_step()
+
     def adopt_optimizer_state(self, optimizer):
         """After ``optimizer.load_state_dict`` (resume): pull the loaded momentum buffers into the
         flat arena and point the optimizer state back at the arena views."""

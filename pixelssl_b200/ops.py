@@ -708,3 +708,211 @@ def launch_count():
 
 def reset_launch_count():
     _lib.load().pxl_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------
+# AdvSSL / GCT / CCT tails
+# ------------------------------------------------------------------------------------------------
+
+class _PlanarToNhwc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ldc, coff, out):
+        _chk(x, 'x')
+        n, c, h, w = x.shape
+        if out is None:
+            out = torch.empty((n, ldc, h, w), dtype=torch.float32, device=x.device, memory_format=CL)
+            if ldc != c:
+                out.zero_()
+        call('pxl_planar_to_nhwc', _p(x), _p(out), n, c, h * w, ldc, coff, _stream())
+        ctx.meta = (n, c, h, w, ldc, coff)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, h, w, ldc, coff = ctx.meta
+        g = as_cl(g)
+        dx = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device)
+        call('pxl_nhwc_to_planar', _p(g), _p(dx), n, c, h * w, ldc, coff, _stream())
+        return dx, None, None, None
+
+
+def planar_to_nhwc(x, ldc=None, coff=0):
+    """planar [n,C,H,W] -> channels_last [n,ldc,H,W] with the C channels in lanes [coff, coff+C) and
+    zeros elsewhere (the conv input of FCDiscriminator / FlawDetector)."""
+    c = x.shape[1]
+    if ldc is None:
+        ldc = (c + 31) // 32 * 32
+    return _PlanarToNhwc.apply(x.contiguous(), int(ldc), int(coff), None)
+
+
+class _CatPlanarToNhwc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ldc, *tensors):
+        n, _, h, w = tensors[0].shape
+        out = torch.empty((n, ldc, h, w), dtype=torch.float32, device=tensors[0].device, memory_format=CL)
+        chans = [t.shape[1] for t in tensors]
+        if sum(chans) != ldc:
+            out.zero_()
+        off = 0
+        for t in tensors:
+            _chk(t, 'cat input')
+            call('pxl_planar_to_nhwc', _p(t), _p(out), n, t.shape[1], h * w, ldc, off, _stream())
+            off += t.shape[1]
+        ctx.meta = (n, h, w, ldc, chans)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, h, w, ldc, chans = ctx.meta
+        g = as_cl(g)
+        grads, off = [], 0
+        for i, c in enumerate(chans):
+            if ctx.needs_input_grad[1 + i]:
+                dx = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device)
+                call('pxl_nhwc_to_planar', _p(g), _p(dx), n, c, h * w, ldc, off, _stream())
+                grads.append(dx)
+            else:
+                grads.append(None)
+            off += c
+        return (None,) + tuple(grads)
+
+
+def cat_planar_to_nhwc(tensors, ldc=None):
+    """torch.cat(tensors, dim=1) of planar maps written straight into one zero-padded NHWC tensor
+    (FlawDetector.forward, ssl_gct.py:566-567)."""
+    ctot = sum(t.shape[1] for t in tensors)
+    if ldc is None:
+        ldc = (ctot + 31) // 32 * 32
+    return _CatPlanarToNhwc.apply(int(ldc), *[t.contiguous() for t in tensors])
+
+
+def onehot_nhwc(labels, num_classes, ldc=None):
+    """One-hot of float labels [n,1,H,W] as channels_last [n,ldc,H,W]; ignore pixels are all-zero."""
+    _chk(labels, 'labels')
+    n, _, h, w = labels.shape
+    if ldc is None:
+        ldc = (num_classes + 31) // 32 * 32
+    out = torch.empty((n, ldc, h, w), dtype=torch.float32, device=labels.device, memory_format=CL).zero_()
+    call('pxl_onehot_nhwc', _p(labels), _p(out), n * h * w, num_classes, ldc, 0, _stream())
+    return out
+
+
+class _LeakyRelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, slope):
+        y = torch.empty_like(x)
+        call('pxl_leaky_relu_fwd', _p(x), _p(y), x.numel(), float(slope), _stream())
+        ctx.save_for_backward(y)
+        ctx.slope = float(slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        g = g.contiguous(memory_format=CL) if y.is_contiguous(memory_format=CL) and y.dim() == 4 else g.contiguous()
+        dx = torch.empty_like(y)
+        call('pxl_leaky_relu_bwd', _p(y), _p(g), _p(dx), y.numel(), ctx.slope, _stream())
+        return dx, None
+
+
+def leaky_relu(x, slope=0.2):
+    """nn.LeakyReLU(slope) (slope 0 = ReLU); x.numel() % 4 == 0."""
+    return _LeakyRelu.apply(x, slope)
+
+
+class _BceMasked(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, labels, target, ignore_index):
+        _chk(pred, 'pred')
+        n = pred.shape[0]
+        hw = pred.numel() // n
+        per = torch.empty(n, dtype=torch.float32, device=pred.device)
+        call('pxl_bce_logits_masked', _p(pred), _p(labels), float(target), int(ignore_index), n, hw, _p(per), _p(None),
+             _p(None), 0.0, _stream())
+        ctx.save_for_backward(pred, labels)
+        ctx.meta = (float(target), int(ignore_index), n, hw)
+        return per
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, labels = ctx.saved_tensors
+        target, ignore, n, hw = ctx.meta
+        per = torch.empty(n, dtype=torch.float32, device=pred.device)
+        grad = torch.empty_like(pred)
+        g = g.contiguous().float()
+        call('pxl_bce_logits_masked', _p(pred), _p(labels), target, ignore, n, hw, _p(per), _p(grad), _p(g), 0.0, _stream())
+        return grad, None, None, None
+
+
+def bce_logits_masked(pred, labels, target, ignore_index=255):
+    """FCDiscriminatorCriterion(ssladv_preprocess_fcd_criterion(pred, labels, is_real=target))
+    -> per-sample loss [n] (ssl_adv.py:496-503 + task/sseg/func.py:137-155).  labels may be None."""
+    if labels is not None:
+        labels = labels.contiguous()
+    return _BceMasked.apply(pred.contiguous(), labels, float(target), int(ignore_index))
+
+
+def adam_(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
+    call('pxl_adam', _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+         float(weight_decay), int(step), _stream())
+
+
+_blur_weights = {}
+
+
+def gaussian_kernel_1d(k, device):
+    """1-D factor v of GaussianBlurLayer's k x k kernel (= outer(v, v)): scipy's gaussian_filter1d of a
+    delta with sigma = 0.3*((k-1)/2 - 1) + 0.8, truncate 4 sigma, 'reflect' boundary
+    (nn/module/gaussian_blur.py:52-64), evaluated here in closed form."""
+    key = (k, str(device))
+    if key not in _blur_weights:
+        import math
+        sigma = 0.3 * ((k - 1) * 0.5 - 1) + 0.8
+        radius = int(4.0 * sigma + 0.5)
+        xs = range(-radius, radius + 1)
+        phi = [math.exp(-0.5 / (sigma * sigma) * x * x) for x in xs]
+        tot = sum(phi)
+        phi = [p / tot for p in phi]
+        # correlate a delta at k//2 of a length-k signal with 'reflect' (d c b a | a b c d | d c b a) padding
+        c = k // 2
+        v = [0.0] * k
+        for i in range(k):
+            acc = 0.0
+            for j, wgt in zip(xs, phi):
+                pos = i + j
+                # scipy 'reflect': mirror about the edge sample boundary (half-sample symmetric)
+                while pos < 0 or pos >= k:
+                    pos = -pos - 1 if pos < 0 else 2 * k - 1 - pos
+                if pos == c:
+                    acc += wgt
+            v[i] = acc
+        _blur_weights[key] = torch.tensor(v, dtype=torch.float64).to(torch.float32).to(device)
+    return _blur_weights[key]
+
+
+def gaussian_blur(x, k, clamp_min=None):
+    """GaussianBlurLayer(1, k) on [n,1,H,W] maps (no autograd: the reference only blurs detached maps)."""
+    _chk(x, 'x')
+    n, c, h, w = x.shape
+    if c != 1:
+        raise ValueError('gaussian_blur expects single-channel maps')
+    tmp, out = torch.empty_like(x), torch.empty_like(x)
+    call('pxl_gauss_blur_sep', _p(x), _p(tmp), _p(out), n, h, w, int(k), _p(gaussian_kernel_1d(k, x.device)),
+         float(-3.0e38 if clamp_min is None else clamp_min), _stream())
+    return out
+
+
+def dilate3x3_reflect(x):
+    _chk(x, 'x')
+    n, c, h, w = x.shape
+    out = torch.empty_like(x)
+    call('pxl_dilate3x3_reflect', _p(x), _p(out), n * c, h, w, _stream())
+    return out
+
+
+def minmax_norm(x, eps=1e-9, zero_below=-1.0):
+    _chk(x, 'x')
+    n = x.shape[0]
+    out = torch.empty_like(x)
+    call('pxl_minmax_norm', _p(x), _p(out), n, x.numel() // n, float(eps), float(zero_below), -3.0e38, _stream())
+    return out

