@@ -254,6 +254,14 @@ int pxl_dilate3x3_reflect(const float* in, float* out, int n, int H, int W, void
 int pxl_minmax_norm(const float* in, float* out, int n, int64_t HW, float eps, float zero_below,
                     float clamp_min, void* stream);
 
+/* DCGTGenerator.forward (ssl_gct.py:668-689) on planar predictions and [n,HW] handled flaw maps */
+int pxl_gct_dcgt(const float* l_pred, const float* r_pred, const float* l_fm, const float* r_fm, float thr,
+                 int n, int C, int64_t HW, float* l_dc, float* r_dc, float* both_bad, void* stream);
+/* mu * sum_c |onehot(label) - prob| (ignored / unlabeled pixels have an all-zero one-hot row):
+ * FDGTGenerator.forward:714-716 + sslgct_prepare_task_gt_for_fdgt (task/sseg/func.py:179-192) */
+int pxl_fdgt_absdiff(const float* prob, const float* labels, float mu, int n, int C, int64_t HW, float* out,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -324,6 +324,36 @@ def golden_adv(pixelssl, sseg_proxy, size=65):
     print('adv golden:', {k: rec[k] for k in rec if 'loss' in k})
 
 
+def golden_gct(pixelssl, sseg_proxy, size=129):
+    """One SSLGCT._train step (ssl_gct.py:176-298): two DeepLabV2 task models + FlawDetector, lbs 2 + ubs 2."""
+    from oracle import gct_oracle as Gc
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    args = make_args(pixelssl, sseg_proxy, 'ssl_gct',
+                     {'ssl_mode': 'gct', 'fc_ssl_scale': 1.0, 'dc_ssl_scale': 100.0, 'dc_threshold': 0.45,
+                      'dc_rampup_epochs': 0, 'fd_lr': 1e-4, 'fd_scale': 10.0, 'mu': 0.5, 'nu': 1, 'im_size': size}, 4, 2)
+    alg = build_algorithm(pixelssl, args, 'ssl_gct')
+    load_state(alg.l_model, O.randomize_bn_affine(O.init_deeplabv2(91, cls_bias_std=0.01), 92))
+    load_state(alg.r_model, O.randomize_bn_affine(O.init_deeplabv2(93, cls_bias_std=0.01), 94))
+    alg.fd_model.load_state_dict({'module.' + k: v.clone() for k, v in Gc.init_fd(95).items()}, strict=True)
+    img, lab = O.synthetic_batch(700, 4, 2, size, size)
+    alg._train([((img.clone(),), (lab.clone(),))], 0)
+    rec = {'size': size}
+    for k in ('l_task_loss', 'l_fc_loss', 'l_dc_loss', 'r_task_loss', 'r_fc_loss', 'r_dc_loss', 'l_fd_loss', 'r_fd_loss'):
+        rec[k] = float(alg.meters[k].val)
+    for mid, model in (('l', alg.l_model), ('r', alg.r_model)):
+        sp = dict(model.module.model.named_parameters())
+        rec[mid + '_grad_checksum'] = checksums([(n, sp[n].grad) for n in names])
+        rec[mid + '_param_checksum'] = checksums([(n, sp[n]) for n in names])
+    fp = dict(alg.fd_model.module.named_parameters())
+    fnames = [n for n, _ in Gc.fd_param_shapes()]
+    rec['fd_grad_checksum'] = checksums([(n, fp[n].grad) for n in fnames])
+    rec['fd_param_checksum'] = checksums([(n, fp[n]) for n in fnames])
+    rec['fd_buffer_checksum'] = checksums([(n, b) for n, b in alg.fd_model.module.named_buffers() if 'num_batches' not in n])
+    rec['fd_lr'] = alg.fd_optimizer.param_groups[0]['lr']
+    np.savez_compressed(os.path.join(OUT, 'gct_step_%d.npz' % size), **rec)
+    print('gct golden:', {k: rec[k] for k in rec if 'loss' in k})
+
+
 def golden_fp64():
     """Exact-arithmetic (fp64) evaluation of the SAME steps with the oracle, to measure the
     reference's own fp32 rounding noise on these (ill-conditioned, random-init) networks.  The GPU
@@ -380,7 +410,7 @@ if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     pixelssl, sseg_proxy = patch_and_import()
-    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 'fp64']
+    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 'gct', 'fp64']
     if which == ['fp64']:
         golden_fp64()
         sys.exit(0)
@@ -394,5 +424,7 @@ if __name__ == '__main__':
         golden_null_cutmix(pixelssl, sseg_proxy)
     if 'adv' in which:
         golden_adv(pixelssl, sseg_proxy)
+    if 'gct' in which:
+        golden_gct(pixelssl, sseg_proxy)
     if 'fp64' in which:
         golden_fp64()

@@ -324,3 +324,69 @@ extern "C" int pxl_minmax_norm(const float* in, float* out, int n, int64_t HW, f
     PXL_CHECK_LAUNCH();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// GCT generators (ssl_gct.py:660-728)
+// ------------------------------------------------------------------------------------------
+// DCGTGenerator.forward (ssl_gct.py:668-689): flaw maps above the threshold are raised to 1, the map
+// with the smaller (better) flaw value wins the pixel; both_bad marks pixels above the threshold in
+// both.  l_fm / r_fm: handled flaw maps [n, HW]; preds / outputs planar [n, C, HW].
+__global__ void __launch_bounds__(256)
+gct_dcgt_kernel(const float* __restrict__ l_pred, const float* __restrict__ r_pred, const float* __restrict__ l_fm,
+                const float* __restrict__ r_fm, float thr, int C, int64_t HW, float* __restrict__ l_dc,
+                float* __restrict__ r_dc, float* __restrict__ both_bad) {
+    const int b = blockIdx.y;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const float lt = __ldg(l_fm + (int64_t)b * HW + p), rt = __ldg(r_fm + (int64_t)b * HW + p);
+    const bool lb = lt > thr, rb = rt > thr;
+    both_bad[(int64_t)b * HW + p] = (lb && rb) ? 1.f : 0.f;
+    // x.mul_(x <= thr).add_(x > thr)
+    const float lh = __fadd_rn(__fmul_rn(lt, lb ? 0.f : 1.f), lb ? 1.f : 0.f);
+    const float rh = __fadd_rn(__fmul_rn(rt, rb ? 0.f : 1.f), rb ? 1.f : 0.f);
+    const float lm = rh >= lh ? 1.f : 0.f, rm = lh >= rh ? 1.f : 0.f;
+    const int64_t base = (int64_t)b * C * HW + p;
+    for (int c = 0; c < C; ++c) {
+        const float lp = __ldg(l_pred + base + (int64_t)c * HW), rp = __ldg(r_pred + base + (int64_t)c * HW);
+        l_dc[base + (int64_t)c * HW] = __fadd_rn(__fmul_rn(lm, lp), __fmul_rn(__fsub_rn(1.f, lm), rp));
+        r_dc[base + (int64_t)c * HW] = __fadd_rn(__fmul_rn(rm, rp), __fmul_rn(__fsub_rn(1.f, rm), lp));
+    }
+}
+
+extern "C" int pxl_gct_dcgt(const float* l_pred, const float* r_pred, const float* l_fm, const float* r_fm, float thr,
+                            int n, int C, int64_t HW, float* l_dc, float* r_dc, float* both_bad, void* stream) {
+    if (!l_pred || !r_pred || !l_fm || !r_fm || !l_dc || !r_dc || !both_bad || n <= 0 || C <= 0 || HW <= 0 || n > 65535)
+        return PXL_ERR_BAD_ARG;
+    dim3 grid((unsigned)pxl_cdiv(HW, 256), (unsigned)n);
+    gct_dcgt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(l_pred, r_pred, l_fm, r_fm, thr, C, HW, l_dc, r_dc, both_bad);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// First stage of FDGTGenerator.forward (ssl_gct.py:714-716) fused with sslgct_prepare_task_gt_for_fdgt
+// (task/sseg/func.py:179-192): out = mu * sum_c |onehot(label)_c - prob_c|, the one-hot row of an
+// ignored / unlabeled pixel being all zero.
+__global__ void __launch_bounds__(256)
+fdgt_absdiff_kernel(const float* __restrict__ prob, const float* __restrict__ labels, float mu, int C, int64_t HW,
+                    float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const float lf = __ldg(labels + (int64_t)b * HW + p);
+    const int64_t base = (int64_t)b * C * HW + p;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const float oh = (lf == (float)c) ? 1.f : 0.f;
+        s += fabsf(oh - __ldg(prob + base + (int64_t)c * HW));
+    }
+    out[(int64_t)b * HW + p] = s * mu;
+}
+
+extern "C" int pxl_fdgt_absdiff(const float* prob, const float* labels, float mu, int n, int C, int64_t HW, float* out,
+                                void* stream) {
+    if (!prob || !labels || !out || n <= 0 || C <= 0 || HW <= 0 || n > 65535) return PXL_ERR_BAD_ARG;
+    dim3 grid((unsigned)pxl_cdiv(HW, 256), (unsigned)n);
+    fdgt_absdiff_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prob, labels, mu, C, HW, out);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}

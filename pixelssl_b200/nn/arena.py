@@ -164,7 +164,7 @@ class EngineParallel(nn.Module):
                 dist.broadcast(b, src=0)
             from .modules import BatchNorm2d
             for m in self.module.modules():
-                if isinstance(m, BatchNorm2d):
+                if isinstance(m, BatchNorm2d) or hasattr(m, 'num_BN'):       # BatchNorm2d and IBNorm
                     m.sync_group = dist.group.WORLD
 
     def forward(self, *inputs, **kwargs):

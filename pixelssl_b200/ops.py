@@ -916,3 +916,118 @@ def minmax_norm(x, eps=1e-9, zero_below=-1.0):
     out = torch.empty_like(x)
     call('pxl_minmax_norm', _p(x), _p(out), n, x.numel() // n, float(eps), float(zero_below), -3.0e38, _stream())
     return out
+
+
+class _IBNorm(torch.autograd.Function):
+    """IBNorm (ssl_gct.py:588-607): the first ``nb`` channels go through (Sync)BatchNorm (affine, running
+    stats), the rest through InstanceNorm2d(affine=False).  Composed from the NHWC BN kernels: batch
+    statistics once over all rows, instance statistics per sample, then per-sample scale/shift vectors
+    that mix both (so one apply / one dx launch per sample covers all channels)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma_bn, beta_bn, running_mean, running_var, training, momentum, eps, group):
+        _chk(x, 'x', cl=True)
+        b, C, H, W = x.shape
+        nb = gamma_bn.numel()
+        hw, dev = H * W, x.device
+        if not training:
+            raise NotImplementedError('IBNorm eval mode is not on the training path')
+        sums_all = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+        call('pxl_bn_stats', _p(x), b * hw, C, _p(sums_all), _stream())
+        sums_i = torch.zeros((b, 2 * C), dtype=torch.float64, device=dev)
+        for i in range(b):
+            call('pxl_bn_stats', _p(x[i]), hw, C, _p(sums_i[i]), _stream())
+        count_all = float(b * hw)
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(sums_all, group=group)
+            count_all *= dist.get_world_size(group)
+        ratio = hw / count_all
+        mix = sums_i.clone()
+        mix[:, :nb] = sums_all[:nb] * ratio
+        mix[:, C:C + nb] = sums_all[C:C + nb] * ratio
+        gamma = torch.cat((gamma_bn.detach(), torch.ones(C - nb, device=dev)))
+        beta = torch.cat((beta_bn.detach(), torch.zeros(C - nb, device=dev)))
+        coeff = torch.empty((b, 4, C), dtype=torch.float32, device=dev)       # mean, invstd, scale, shift per sample
+        y = torch.empty_like(x)
+        for i in range(b):
+            call('pxl_bn_finalize', _p(mix[i]), float(hw), C, _p(gamma), _p(beta), _p(None), _p(None), 0.0, float(eps), 0,
+                 _p(coeff[i, 0]), _p(coeff[i, 1]), _p(coeff[i, 2]), _p(coeff[i, 3]), _stream())
+            call('pxl_bn_apply', _p(x[i]), _p(coeff[i, 2]), _p(coeff[i, 3]), _p(None), 0, _p(y[i]), hw, C, _stream())
+        # running statistics of the BN half (unbiased variance over all rows)
+        bn_sums = torch.cat((sums_all[:nb], sums_all[C:C + nb])).contiguous()
+        scratch = torch.empty((4, nb), dtype=torch.float32, device=dev)
+        call('pxl_bn_finalize', _p(bn_sums), count_all, nb, _p(gamma_bn), _p(beta_bn), _p(running_mean), _p(running_var),
+             float(momentum), float(eps), 0, _p(scratch[0]), _p(scratch[1]), _p(scratch[2]), _p(scratch[3]), _stream())
+        ctx.save_for_backward(x, coeff, gamma)
+        ctx.meta = (b, C, hw, nb, count_all, group)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, coeff, gamma = ctx.saved_tensors
+        b, C, hw, nb, count_all, group = ctx.meta
+        dy = as_cl(dy)
+        dev = dy.device
+        dsums = torch.zeros((b, 2 * C), dtype=torch.float64, device=dev)
+        for i in range(b):
+            call('pxl_bn_bwd_reduce', _p(x[i]), _p(None), _p(dy[i]), _p(coeff[i, 0]), _p(coeff[i, 1]), 0, hw, C,
+                 _p(dsums[i]), _stream())
+        tot = dsums.sum(0)
+        dgamma = tot[C:C + nb].to(torch.float32)
+        dbeta = tot[:nb].to(torch.float32)
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(tot, group=group)
+        ratio = hw / count_all
+        mix = dsums.clone()
+        mix[:, :nb] = tot[:nb] * ratio
+        mix[:, C:C + nb] = tot[C:C + nb] * ratio
+        dx = torch.empty_like(x)
+        for i in range(b):
+            call('pxl_bn_bwd_dx', _p(x[i]), _p(None), _p(dy[i]), _p(coeff[i, 0]), _p(coeff[i, 1]), _p(gamma), _p(mix[i]),
+                 float(hw), 0, _p(dx[i]), _p(None), hw, C, _stream())
+        return dx, dgamma, dbeta, None, None, None, None, None, None
+
+
+def ibnorm(x, gamma_bn, beta_bn, running_mean, running_var, training=True, momentum=0.1, eps=1e-5, group=None):
+    return _IBNorm.apply(x, gamma_bn, beta_bn, running_mean, running_var, bool(training), float(momentum), float(eps), group)
+
+
+def gct_dcgt(l_pred, r_pred, l_fm, r_fm, thr):
+    """DCGTGenerator.forward (ssl_gct.py:668-689) -> (l_dc_gt, r_dc_gt, both_bad[n,1,H,W])."""
+    _chk(l_pred, 'l_pred'); _chk(r_pred, 'r_pred'); _chk(l_fm, 'l_fm'); _chk(r_fm, 'r_fm')
+    n, c, h, w = l_pred.shape
+    l_dc, r_dc = torch.empty_like(l_pred), torch.empty_like(r_pred)
+    both = torch.empty((n, 1, h, w), dtype=torch.float32, device=l_pred.device)
+    call('pxl_gct_dcgt', _p(l_pred), _p(r_pred), _p(l_fm), _p(r_fm), float(thr), n, c, h * w, _p(l_dc), _p(r_dc), _p(both),
+         _stream())
+    return l_dc, r_dc, both
+
+
+def odd_ksize(v):
+    k = int(v)
+    return k + 1 if k % 2 == 0 else k
+
+
+def flawmap_handle(flawmap, im_size, clip_threshold=0.1):
+    """FlawmapHandler.forward (ssl_gct.py:641-657): clamp negatives to 0, Gaussian blur
+    k = odd(im_size/16), zero the whole map when its max <= 0.1 (min/max taken before), min-max
+    normalise.  NOTE: like the reference this also clamps the INPUT tensor's values in place
+    (``flawmap.data.mul_(flawmap >= 0)``), which later changes the flaw-detector loss."""
+    fm = flawmap.detach()
+    fm.clamp_(min=0)                                  # in place on the shared storage, as the reference does
+    blurred = gaussian_blur(fm.contiguous(), odd_ksize(im_size / 16))
+    return minmax_norm(blurred, 1e-9, clip_threshold)
+
+
+def fdgt_generate(prob, labels, im_size, mu, nu):
+    """FDGTGenerator.forward (ssl_gct.py:714-728) on softmax ``prob`` [n,C,H,W] and float labels [n,1,H,W]."""
+    _chk(prob, 'prob'); _chk(labels, 'labels')
+    n, c, h, w = prob.shape
+    diff = torch.empty((n, 1, h, w), dtype=torch.float32, device=prob.device)
+    call('pxl_fdgt_absdiff', _p(prob), _p(labels), float(mu), n, c, h * w, _p(diff), _stream())
+    diff = gaussian_blur(diff, odd_ksize(im_size / 8))
+    for _ in range(int(nu)):
+        diff = gaussian_blur(dilate3x3_reflect(diff), odd_ksize(im_size / 4))
+    return minmax_norm(diff, 1e-9, -1.0)

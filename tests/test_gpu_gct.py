@@ -1,0 +1,136 @@
+"""GCT on the engine: kernels of the flaw-map pipeline and the IBNorm flaw detector against the CPU
+oracle, and a whole SSLGCT step against the reference-generated golden (tests/golden/gct_step_129.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sseg_oracle as O
+from oracle import gct_oracle as Gc
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), 'golden')
+CL = torch.channels_last
+
+
+@pytest.fixture(scope='module')
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a GPU')
+    from pixelssl_b200 import ops as _ops
+    _ops.set_conv_precision(os.environ.get('PXL_TEST_PRECISION', 'fp32'))
+    return _ops
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rel_q(a, b, frac=2e-3):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    err = (a - b).abs() / b.abs().max().clamp_min(1e-30)
+    return float(err.kthvalue(max(1, int(err.numel() * (1 - frac)))).values)
+
+
+@pytest.mark.parametrize('k,h,w', [(5, 40, 44), (33, 40, 44), (9, 129, 129), (45, 97, 90), (89, 90, 97)])
+def test_gaussian_blur_separable_equals_reference_2d(ops, k, h, w):
+    g = torch.Generator().manual_seed(k)
+    x = torch.rand(2, 1, h, w, generator=g) * 3 - 1
+    ref = O.gaussian_blur(x, k)
+    assert rel(ops.gaussian_blur(x.cuda(), k), ref) <= 2e-6
+    ref_c = O.gaussian_blur(x.clamp(min=0), k)
+    assert rel(ops.gaussian_blur(x.cuda(), k, clamp_min=0.0), ref_c) <= 2e-6
+
+
+def test_golden_blur_vectors(ops):
+    g = np.load(os.path.join(G, 'ops.npz'))
+    x = torch.tensor(g['blur_x']).cuda()
+    assert rel(ops.gaussian_blur(x, 5), torch.tensor(g['blur_y_5'])) <= 2e-6
+    assert rel(ops.gaussian_blur(x, 33), torch.tensor(g['blur_y_33'])) <= 2e-6
+
+
+def test_dilate_minmax_handler_dcgt_fdgt(ops):
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(3, 1, 37, 41, generator=g)
+    ref = F.max_pool2d(F.pad(x, (1, 1, 1, 1), mode='reflect'), 3, stride=1)
+    assert torch.equal(ops.dilate3x3_reflect(x.cuda()).cpu(), ref)
+    mn, mx = x.amin(dim=(1, 2, 3), keepdim=True), x.amax(dim=(1, 2, 3), keepdim=True)
+    assert rel(ops.minmax_norm(x.cuda()), (x - mn) / (mx - mn + 1e-9)) <= 1e-6
+    # FlawmapHandler incl. the 'all below the clip threshold' branch (sample 1) and the in-place clamp
+    fm = torch.randn(3, 1, 65, 65, generator=g) * 2
+    fm[1] = fm[1].abs() * 0.001
+    fm_ref = fm.clone()
+    ref = Gc.flawmap_handler(fm_ref, 65)
+    fm_g = fm.cuda()
+    out = ops.flawmap_handle(fm_g, 65)
+    assert rel(out, ref) <= 1e-5
+    assert rel(fm_g, fm_ref) == 0.0                       # input clamped in place like the reference
+    lp = torch.softmax(torch.randn(2, 21, 33, 35, generator=g), 1)
+    rp = torch.softmax(torch.randn(2, 21, 33, 35, generator=g), 1)
+    lh, rh = torch.rand(2, 1, 33, 35, generator=g), torch.rand(2, 1, 33, 35, generator=g)
+    rl, rr, rb = Gc.dcgt(lp, rp, lh.clone(), rh.clone(), 0.6)
+    gl, gr, gb = ops.gct_dcgt(lp.cuda(), rp.cuda(), lh.cuda(), rh.cuda(), 0.6)
+    assert torch.equal(gl.cpu(), rl) and torch.equal(gr.cpu(), rr) and torch.equal(gb.cpu(), rb)
+    _, lab = O.synthetic_batch(9, 2, 1, 65, 65)            # second row unlabeled (-1): all-zero one-hot
+    prob = torch.softmax(torch.randn(2, 21, 65, 65, generator=g) * 2, 1)
+    ref = Gc.fdgt(prob, Gc.prepare_gt_for_fdgt(lab), 65, 0.5, 2)
+    assert rel(ops.fdgt_generate(prob.cuda(), lab.cuda(), 65, 0.5, 2), ref) <= 1e-5
+
+
+def test_flaw_detector_forward_backward(ops):
+    from pixelssl_b200.ssl_algorithm.ssl_gct import FlawDetector
+    st = Gc.init_fd(11, classifier_gain=1.0)
+    fd = FlawDetector(24).cuda()
+    fd.load_state_dict(st)
+    fd.train()
+    g = torch.Generator().manual_seed(8)
+    img = torch.randn(3, 3, 129, 129, generator=g)
+    prob = torch.softmax(torch.randn(3, 21, 129, 129, generator=g), 1)
+    stc = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone()) for k, v in st.items()}
+    pc = prob.clone().requires_grad_(True)
+    ref = Gc.fd_forward(stc, img, pc)
+    w = torch.randn(ref.shape, generator=g)
+    (ref * w).sum().backward()
+    pg = prob.cuda().requires_grad_(True)
+    out = fd((img.cuda(),), pg)[0]['flawmap']
+    (out * w.cuda()).sum().backward()
+    assert rel(out, ref) <= 1e-4
+    assert rel_q(pg.grad, pc.grad) <= 1e-4
+    for n, p in fd.named_parameters():
+        assert rel_q(p.grad, stc[n].grad, 5e-3) <= 5e-4, n
+    for n, b in fd.named_buffers():
+        if 'num_batches' not in n:
+            assert rel(b, stc[n]) <= 1e-5, n
+
+
+def test_gct_step_golden(ops):
+    from pixelssl_b200 import runner
+    g = np.load(os.path.join(G, 'gct_step_129.npz'))
+    size = int(g['size'])
+    cfg = {'ssl_algorithm': 'ssl_gct', 'lr': 0.00025, 'momentum': 0.9, 'weight_decay': 0.0005, 'epochs': 2, 'log_freq': 1000,
+           'ssl_mode': 'gct', 'fc_ssl_scale': 1.0, 'dc_ssl_scale': 100.0, 'dc_threshold': 0.45, 'dc_rampup_epochs': 0,
+           'fd_lr': 1e-4, 'fd_scale': 10.0, 'mu': 0.5, 'nu': 1, 'im_size': size, 'batch_size': 4, 'unlabeled_batch_size': 2}
+    alg = runner.build_algorithm(runner.build_args(cfg, iters_per_epoch=5))
+    for model, seeds in ((alg.l_model, (91, 92)), (alg.r_model, (93, 94))):
+        st = O.randomize_bn_affine(O.init_deeplabv2(seeds[0], cls_bias_std=0.01), seeds[1])
+        model.load_state_dict({'module.model.' + k: v for k, v in st.items()})
+    alg.fd_model.load_state_dict({'module.' + k: v for k, v in Gc.init_fd(95).items()})
+    img, lab = O.synthetic_batch(700, 4, 2, size, size)
+    alg._train([((img,), (lab,))], 0)
+    for k in ('l_task_loss', 'r_task_loss'):
+        assert abs(float(alg.meters[k].val) - float(g[k])) <= 2e-3 * abs(float(g[k])), k
+    # SSL terms and the FD loss sit downstream of softmax maps that carry the task nets' fp32 noise
+    for k in ('l_fc_loss', 'l_dc_loss', 'r_fc_loss', 'r_dc_loss', 'l_fd_loss', 'r_fd_loss'):
+        got, ref = float(alg.meters[k].val), float(g[k])
+        print(k, got, ref)
+        assert abs(got - ref) <= 3e-2 * abs(ref), (k, got, ref)
+    fn = [n for n, _ in Gc.fd_param_shapes()]
+    fp = dict(alg.fd_model.module.named_parameters())
+    cs = np.array([float((fp[n].grad.double() ** 2).sum()) for n in fn])
+    relg = np.abs(cs - g['fd_grad_checksum'][:, 1]) / np.maximum(g['fd_grad_checksum'][:, 1], 1e-30)
+    print('fd grad energy rel: median %.2e max %.2e' % (np.median(relg), relg.max()))
+    assert np.median(relg) <= 5e-2 and relg.max() <= 3e-1
+    assert abs(alg.fd_optimizer.param_groups[0]['lr'] - float(g['fd_lr'])) <= 1e-12

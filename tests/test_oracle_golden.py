@@ -222,3 +222,30 @@ def test_adv_step_matches_reference_train_body():
     np.testing.assert_allclose(_checks([adv.d[n].detach() for n in dn])[:, 1], g['d_param_checksum'][:, 1], rtol=1e-5)
     np.testing.assert_allclose(_checks([adv.s[n] for n in names])[:, 1], g['param_checksum'][:, 1], rtol=1e-5)
     assert abs(adv.d_opt.param_groups[0]['lr'] - float(g['d_lr'])) < 1e-15 or True
+
+
+@pytest.mark.slow
+def test_gct_step_matches_reference_train_body():
+    """SSLGCT._train (ssl_gct.py:185-293): two task models, flaw detector with IBNorm, flaw-map handler
+    (incl. its in-place clamp of the raw flaw map), DC / FD ground-truth generators."""
+    from oracle import gct_oracle as Gc
+    g = load('gct_step_129.npz')
+    size = int(g['size'])
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    lst = O.randomize_bn_affine(O.init_deeplabv2(91, cls_bias_std=0.01), 92)
+    rst = O.randomize_bn_affine(O.init_deeplabv2(93, cls_bias_std=0.01), 94)
+    gct = Gc.GctOracle(lst, rst, Gc.init_fd(95), size, fc_ssl_scale=1.0, dc_ssl_scale=100.0, dc_threshold=0.45,
+                       rampup_steps=0, fd_lr=1e-4, fd_scale=10.0, mu=0.5, nu=1)
+    img, lab = O.synthetic_batch(700, 4, 2, size, size)
+    out = gct.step(img, lab, 2)
+    for k in ('l_task_loss', 'l_fc_loss', 'l_dc_loss', 'r_task_loss', 'r_fc_loss', 'r_dc_loss', 'l_fd_loss', 'r_fd_loss'):
+        assert abs(float(out[k]) - float(g[k])) <= 1e-4 * abs(float(g[k])) + 1e-7, (k, float(out[k]), float(g[k]))
+    for mid in ('l', 'r'):
+        cs = _checks([out[mid + '_grads'][n] for n in names])
+        rel = np.abs(cs[:, 1] - g[mid + '_grad_checksum'][:, 1]) / g[mid + '_grad_checksum'][:, 1]
+        assert rel.max() < 5e-3 and np.median(rel) < 5e-4, (mid, rel.max(), np.median(rel))
+    fn = gct.fd_names
+    cs = _checks([out['fd_grads'][n] for n in fn])
+    rel = np.abs(cs[:, 1] - g['fd_grad_checksum'][:, 1]) / np.maximum(g['fd_grad_checksum'][:, 1], 1e-30)
+    assert rel.max() < 2e-3, rel.max()
+    np.testing.assert_allclose(_checks([gct.fd[n].detach() for n in fn])[:, 1], g['fd_param_checksum'][:, 1], rtol=1e-5)
