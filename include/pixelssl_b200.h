@@ -262,6 +262,17 @@ int pxl_gct_dcgt(const float* l_pred, const float* r_pred, const float* l_fm, co
 int pxl_fdgt_absdiff(const float* prob, const float* labels, float mu, int n, int C, int64_t HW, float* out,
                      void* stream);
 
+/* nn.PixelShuffle(2) on NHWC (C output channels, lanes up to ldo zero-filled); inverse != 0 = backward.
+ * _pspnet.py:40-54, ssl_cct.py:501-516 */
+int pxl_pixel_shuffle2_nhwc(const float* in, float* out, int N, int h, int w, int C, int ldi, int ldo,
+                            int inverse, void* stream);
+/* CCT feature perturbations on the NHWC latent (ssl_cct.py:542-745): out = x * pixel_mask[n,hw] *
+ * chan_scale[n,c] * (1 + elem_noise[hw,c]), every factor nullable */
+int pxl_perturb_nhwc(const float* x, const float* pixel_mask, const float* chan_scale, const float* elem_noise,
+                     float* out, int N, int64_t HW, int C, void* stream);
+int pxl_channel_mean_nhwc(const float* x, float* out, int64_t pixels, int C, void* stream);
+int pxl_argmax_nonzero_mask(const float* logits, float* mask, int n, int C, int64_t HW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -354,6 +354,37 @@ def golden_gct(pixelssl, sseg_proxy, size=129):
     print('gct golden:', {k: rec[k] for k in rec if 'loss' in k})
 
 
+def golden_cct(pixelssl, sseg_proxy, size=65):
+    """One SSLCCT._train step (ssl_cct.py:226-301) with one decoder of every kind, lbs 2 + ubs 2."""
+    from oracle import cct_oracle as C
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    args = make_args(pixelssl, sseg_proxy, 'ssl_cct',
+                     {'cons_scale': 30.0, 'cons_rampup_epochs': 0, 'ad_lr_scale': 10.0, 'vat_dec_num': 1, 'drop_dec_num': 1,
+                      'cut_dec_num': 1, 'context_dec_num': 1, 'object_dec_num': 1, 'fd_dec_num': 1, 'fn_dec_num': 1,
+                      'vat_dec_xi': 1e-6, 'vat_dec_eps': 2.0, 'drop_dec_rate': 0.5, 'cut_dec_erase': 0.4,
+                      'fn_dec_uniform': 0.3}, 4, 2)
+    alg = build_algorithm(pixelssl, args, 'ssl_cct')
+    st = O.randomize_bn_affine(O.init_deeplabv2(101, cls_bias_std=0.01), 102)
+    dec = C.init_decoders(103, 7)
+    sd = {'module.main_model.model.' + k: v.clone() for k, v in st.items()}
+    sd.update({'module.' + k: v.clone() for k, v in dec.items()})
+    missing = alg.model.load_state_dict(sd, strict=True)
+    img, lab = O.synthetic_batch(800, 4, 2, size, size)
+    random.seed(7); np.random.seed(8); torch.manual_seed(9)
+    alg._train([((img.clone(),), (lab.clone(),))], 0)
+    sp = dict(alg.model.module.main_model.model.named_parameters())
+    dp = dict(alg.model.module.named_parameters())
+    dnames = [n for i in range(7) for n, _ in C.decoder_param_shapes(i)]
+    rec = {'size': size, 'task_loss': float(alg.meters['task_loss'].val), 'cons_loss': float(alg.meters['cons_loss'].val)}
+    rec['grad_checksum'] = checksums([(n, sp[n].grad) for n in names])
+    rec['param_checksum'] = checksums([(n, sp[n]) for n in names])
+    rec['dec_grad_checksum'] = checksums([(n, dp[n].grad) for n in dnames])
+    rec['dec_param_checksum'] = checksums([(n, dp[n]) for n in dnames])
+    rec['lrs'] = np.array([g['lr'] for g in alg.optimizer.param_groups])
+    np.savez_compressed(os.path.join(OUT, 'cct_step_%d.npz' % size), **rec)
+    print('cct golden:', rec['task_loss'], rec['cons_loss'], rec['lrs'])
+
+
 def golden_fp64():
     """Exact-arithmetic (fp64) evaluation of the SAME steps with the oracle, to measure the
     reference's own fp32 rounding noise on these (ill-conditioned, random-init) networks.  The GPU
@@ -410,7 +441,7 @@ if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     pixelssl, sseg_proxy = patch_and_import()
-    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 'gct', 'fp64']
+    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 'gct', 'cct', 'fp64']
     if which == ['fp64']:
         golden_fp64()
         sys.exit(0)
@@ -426,5 +457,7 @@ if __name__ == '__main__':
         golden_adv(pixelssl, sseg_proxy)
     if 'gct' in which:
         golden_gct(pixelssl, sseg_proxy)
+    if 'cct' in which:
+        golden_cct(pixelssl, sseg_proxy)
     if 'fp64' in which:
         golden_fp64()

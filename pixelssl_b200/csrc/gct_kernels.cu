@@ -390,3 +390,117 @@ extern "C" int pxl_fdgt_absdiff(const float* prob, const float* labels, float mu
     PXL_CHECK_LAUNCH();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// CCT auxiliary-decoder pieces (ssl_cct.py:501-745, _pspnet.py:40-54)
+// ------------------------------------------------------------------------------------------
+// nn.PixelShuffle(2) on NHWC: out[n, 2y+i, 2x+j, c] = in[n, y, x, c*4 + i*2 + j], c < C; output lanes
+// [C, ldo) are zero-filled.  dir != 0 runs the inverse (the backward pass).
+__global__ void __launch_bounds__(256)
+pixel_shuffle2_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int h, int w, int C, int ldi, int ldo, int inverse) {
+    const int64_t total = (int64_t)N * (2 * h) * (2 * w) * ldo;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int c = (int)(idx % ldo);
+        int64_t p = idx / ldo;
+        const int X = (int)(p % (2 * w)); p /= (2 * w);
+        const int Y = (int)(p % (2 * h));
+        const int n = (int)(p / (2 * h));
+        const int64_t small = (((int64_t)n * h + (Y >> 1)) * w + (X >> 1)) * ldi + c * 4 + (Y & 1) * 2 + (X & 1);
+        if (!inverse) out[idx] = c < C ? __ldg(in + small) : 0.f;
+        else if (c < C) out[small] = __ldg(in + idx);       // here `in` is the big tensor, `out` the small one
+    }
+}
+
+extern "C" int pxl_pixel_shuffle2_nhwc(const float* in, float* out, int N, int h, int w, int C, int ldi, int ldo,
+                                       int inverse, void* stream) {
+    if (!in || !out || N <= 0 || h <= 0 || w <= 0 || C <= 0 || ldi < 4 * C || ldo < C) return PXL_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (inverse && ldi > 4 * C) {           // padding lanes of the small gradient tensor must be zero
+        cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N * h * w * ldi, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const int64_t total = (int64_t)N * 4 * h * w * ldo;
+    int blocks = (int)(pxl_cdiv(total, 256) < PXL_NUM_SMS * 16 ? pxl_cdiv(total, 256) : PXL_NUM_SMS * 16);
+    pixel_shuffle2_kernel<<<blocks, 256, 0, st>>>(in, out, N, h, w, C, ldi, ldo, inverse);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// out = x * pixel_mask[n, hw] * chan_scale[n, c] * (1 + elem_noise[hw, c])   (each factor optional)
+//   pixel mask: CutOut / context / object masking / feature drop; channel scale: Dropout2d;
+//   element noise: FeatureNoiseDecoder (x.mul(noise) + x, noise shared over the batch)
+__global__ void __launch_bounds__(256)
+perturb_kernel(const float4* __restrict__ x, const float* __restrict__ pmask, const float* __restrict__ cscale,
+               const float4* __restrict__ noise, float4* __restrict__ out, int64_t n4, int c4, int64_t HW) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int c = (int)(i % c4);
+        const int64_t pix = i / c4;          // n * HW + hw
+        float4 v = x[i];
+        if (pmask) { const float m = __ldg(pmask + pix); v.x *= m; v.y *= m; v.z *= m; v.w *= m; }
+        if (cscale) {
+            const int64_t n = pix / HW;
+            const float4 s = __ldg(reinterpret_cast<const float4*>(cscale) + n * c4 + c);
+            v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+        }
+        if (noise) {
+            const float4 e = __ldg(noise + (pix % HW) * c4 + c);
+            v.x = fmaf(v.x, e.x, v.x); v.y = fmaf(v.y, e.y, v.y); v.z = fmaf(v.z, e.z, v.z); v.w = fmaf(v.w, e.w, v.w);
+        }
+        out[i] = v;
+    }
+}
+
+extern "C" int pxl_perturb_nhwc(const float* x, const float* pixel_mask, const float* chan_scale, const float* elem_noise,
+                                float* out, int N, int64_t HW, int C, void* stream) {
+    if (!x || !out || N <= 0 || HW <= 0 || C <= 0 || (C & 3)) return PXL_ERR_BAD_ARG;
+    const int64_t n4 = (int64_t)N * HW * (C / 4);
+    perturb_kernel<<<ew_blocks(n4), 256, 0, (cudaStream_t)stream>>>((const float4*)x, pixel_mask, chan_scale,
+                                                                   (const float4*)elem_noise, (float4*)out, n4, C / 4, HW);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// mean over channels per pixel of an NHWC tensor: FeatureDropDecoder attention (ssl_cct.py:721)
+__global__ void __launch_bounds__(256)
+channel_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t pixels, int C) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = warp; p < pixels; p += nwarps) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += __ldg(x + p * C + c);
+        s = warp_sum(s);
+        if (lane == 0) out[p] = s / (float)C;
+    }
+}
+
+extern "C" int pxl_channel_mean_nhwc(const float* x, float* out, int64_t pixels, int C, void* stream) {
+    if (!x || !out || pixels <= 0 || C <= 0) return PXL_ERR_BAD_ARG;
+    int blocks = (int)(pxl_cdiv(pixels, 8) < PXL_NUM_SMS * 8 ? pxl_cdiv(pixels, 8) : PXL_NUM_SMS * 8);
+    channel_mean_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, pixels, C);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// (argmax_c logits > 0) as a float mask [n, HW]: guided masking / cutout of the CCT decoders
+// (ssl_cct.py:609, 666, 693).  argmax returns the FIRST maximum, so class 0 wins ties.
+__global__ void __launch_bounds__(256)
+argmax_nonzero_kernel(const float* __restrict__ logits, float* __restrict__ mask, int C, int64_t HW) {
+    const int b = blockIdx.y;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const float* lg = logits + (int64_t)b * C * HW + p;
+    const float v0 = __ldg(lg);
+    float m = -CUDART_INF_F;
+    for (int c = 1; c < C; ++c) m = fmaxf(m, __ldg(lg + (int64_t)c * HW));
+    mask[(int64_t)b * HW + p] = m > v0 ? 1.f : 0.f;
+}
+
+extern "C" int pxl_argmax_nonzero_mask(const float* logits, float* mask, int n, int C, int64_t HW, void* stream) {
+    if (!logits || !mask || n <= 0 || C <= 0 || HW <= 0 || n > 65535) return PXL_ERR_BAD_ARG;
+    dim3 grid((unsigned)pxl_cdiv(HW, 256), (unsigned)n);
+    argmax_nonzero_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, mask, C, HW);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}

@@ -453,10 +453,13 @@ class _Conv2d(torch.autograd.Function):
     """nn.Conv2d on NHWC (resnet.py:18-25 etc.).  weight logical [Cout,Cin,kh,kw] channels_last."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, dilation):
+    def forward(ctx, x, weight, bias, stride, padding, dilation, out_lanes=0):
         _chk(x, 'x', cl=True); _chk(weight, 'weight', cl=True)
         N, Cin, H, W = x.shape
         Cout, Cin2, kh, kw = weight.shape
+        if out_lanes and out_lanes > Cout:
+            return _Conv2d._forward_padded(ctx, x, weight, bias, stride, padding, dilation, out_lanes)
+        ctx.padded = False
         if Cin2 != Cin:
             raise ValueError('channel mismatch')
         OH = (H + 2 * padding - dilation * (kh - 1) - 1) // stride + 1
@@ -475,7 +478,45 @@ class _Conv2d(torch.autograd.Function):
         return out
 
     @staticmethod
+    def _forward_padded(ctx, x, weight, bias, stride, padding, dilation, ldo):
+        """Output written with ``ldo`` > Cout channel lanes (extra lanes zero) so that the consumer can be
+        a tensor-core convolution with Cin % 32 == 0.  Used by the 21-channel decoder heads."""
+        N, Cin, H, W = x.shape
+        Cout, _, kh, kw = weight.shape
+        OH = (H + 2 * padding - dilation * (kh - 1) - 1) // stride + 1
+        OW = (W + 2 * padding - dilation * (kw - 1) - 1) // stride + 1
+        taps = _taps(kh, kw, dilation, padding)
+        out = conv_raw(x, weight, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, stride, 1)
+        ctx.save_for_backward(x, weight)
+        ctx.padded, ctx.split = True, False
+        ctx.meta = (taps, N, H, W, Cin, OH, OW, Cout, stride, kh * kw, bias is not None, ldo)
+        return out
+
+    @staticmethod
+    def _backward_padded(ctx, dy):
+        x, weight = ctx.saved_tensors
+        taps, N, H, W, Cin, OH, OW, Cout, stride, T, has_bias, ldo = ctx.meta
+        dy = as_cl(dy)                       # [N, ldo, OH, OW]; lanes >= Cout carry zeros
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wp = torch.zeros((ldo, T, Cin), dtype=torch.float32, device=dy.device)
+            wp[:Cout] = weight.permute(0, 2, 3, 1).reshape(Cout, T, Cin)
+            wt = transpose_weights(wp, ldo, T, Cin)
+            dx = conv_raw(dy, wt, None, [-v for v in taps], N, OH, OW, ldo, H, W, Cin, Cin, 1, stride)
+        if ctx.needs_input_grad[1]:
+            dwp = torch.zeros((Cout, T, Cin), dtype=torch.float32, device=dy.device)
+            conv_wgrad_raw(x, dy, dwp, taps, N, H, W, Cin, OH, OW, Cout, ldo, stride, 1)
+            kh = int(round(T ** 0.5))
+            dw = dwp.reshape(Cout, kh, T // kh, Cin).permute(0, 3, 1, 2)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(Cout, dtype=torch.float32, device=dy.device)
+            call('pxl_bias_grad', _p(dy), N * OH * OW, Cout, ldo, _p(db), 0, _stream())
+        return dx, dw, db, None, None, None, None
+
+    @staticmethod
     def backward(ctx, dy):
+        if ctx.padded:
+            return _Conv2d._backward_padded(ctx, dy)
         if ctx.split:
             x_hi, x_lo, weight = ctx.saved_tensors
             x = (x_hi, x_lo)
@@ -503,11 +544,12 @@ class _Conv2d(torch.autograd.Function):
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(Cout, dtype=torch.float32, device=dy.device)
             call('pxl_bias_grad', _p(dy), N * OH * OW, Cout, Cout, _p(db), 0, _stream())
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1):
-    return _Conv2d.apply(x, weight, bias, int(stride), int(padding), int(dilation))
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, out_lanes=0):
+    """out_lanes > Cout: the output tensor gets that many channel lanes (the extra ones zero)."""
+    return _Conv2d.apply(x, weight, bias, int(stride), int(padding), int(dilation), int(out_lanes))
 
 
 class _Aspp(torch.autograd.Function):
@@ -786,6 +828,32 @@ def cat_planar_to_nhwc(tensors, ldc=None):
     return _CatPlanarToNhwc.apply(int(ldc), *[t.contiguous() for t in tensors])
 
 
+class _NhwcToPlanar(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, C):
+        _chk(x, 'x', cl=True)
+        n, ldc, h, w = x.shape
+        out = torch.empty((n, C, h, w), dtype=torch.float32, device=x.device)
+        call('pxl_nhwc_to_planar', _p(x), _p(out), n, C, h * w, ldc, 0, _stream())
+        ctx.meta = (n, C, h, w, ldc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, C, h, w, ldc = ctx.meta
+        g = g.contiguous()
+        dx = torch.empty((n, ldc, h, w), dtype=torch.float32, device=g.device, memory_format=CL)
+        if ldc != C:
+            dx.zero_()
+        call('pxl_planar_to_nhwc', _p(g), _p(dx), n, C, h * w, ldc, 0, _stream())
+        return dx, None
+
+
+def nhwc_to_planar(x, channels):
+    """First ``channels`` lanes of a channels_last tensor as a planar [n,channels,H,W] tensor."""
+    return _NhwcToPlanar.apply(as_cl(x), int(channels))
+
+
 def onehot_nhwc(labels, num_classes, ldc=None):
     """One-hot of float labels [n,1,H,W] as channels_last [n,ldc,H,W]; ignore pixels are all-zero."""
     _chk(labels, 'labels')
@@ -1031,3 +1099,86 @@ def fdgt_generate(prob, labels, im_size, mu, nu):
     for _ in range(int(nu)):
         diff = gaussian_blur(dilate3x3_reflect(diff), odd_ksize(im_size / 4))
     return minmax_norm(diff, 1e-9, -1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# CCT / PSPNet decoder pieces
+# ------------------------------------------------------------------------------------------------
+
+class _PixelShuffle2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, C, ldo):
+        _chk(x, 'x', cl=True)
+        n, ldi, h, w = x.shape
+        out = torch.empty((n, ldo, 2 * h, 2 * w), dtype=torch.float32, device=x.device, memory_format=CL)
+        call('pxl_pixel_shuffle2_nhwc', _p(x), _p(out), n, h, w, C, ldi, ldo, 0, _stream())
+        ctx.meta = (n, h, w, C, ldi, ldo)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, h, w, C, ldi, ldo = ctx.meta
+        g = as_cl(g)
+        dx = torch.empty((n, ldi, h, w), dtype=torch.float32, device=g.device, memory_format=CL)
+        call('pxl_pixel_shuffle2_nhwc', _p(g), _p(dx), n, h, w, C, ldi, ldo, 1, _stream())
+        return dx, None, None
+
+
+def pixel_shuffle2(x, out_channels, ldo=None):
+    """nn.PixelShuffle(2) on a channels_last tensor whose first 4*out_channels lanes are real; the
+    result has ``ldo`` lanes (default: out_channels rounded up to 32) with zeros beyond out_channels."""
+    if ldo is None:
+        ldo = (out_channels + 31) // 32 * 32
+    return _PixelShuffle2.apply(as_cl(x), int(out_channels), int(ldo))
+
+
+class _Perturb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pixel_mask, chan_scale, elem_noise):
+        _chk(x, 'x', cl=True)
+        n, c, h, w = x.shape
+        out = torch.empty_like(x)
+        call('pxl_perturb_nhwc', _p(x), _p(pixel_mask), _p(chan_scale), _p(elem_noise), _p(out), n, h * w, c, _stream())
+        ctx.save_for_backward(pixel_mask, chan_scale, elem_noise)
+        ctx.meta = (n, c, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pixel_mask, chan_scale, elem_noise = ctx.saved_tensors
+        n, c, h, w = ctx.meta
+        g = as_cl(g)
+        dx = torch.empty_like(g)
+        call('pxl_perturb_nhwc', _p(g), _p(pixel_mask), _p(chan_scale), _p(elem_noise), _p(dx), n, h * w, c, _stream())
+        return dx, None, None, None
+
+
+def perturb(x, pixel_mask=None, chan_scale=None, elem_noise=None):
+    """x * pixel_mask[n,1,H,W] * chan_scale[n,C] * (1 + elem_noise[C,H,W]) on a channels_last feature map
+    (CCT perturbations, ssl_cct.py:588, 651, 700-707, 726-727, 743-744).  elem_noise is given in the
+    reference's [C,H,W] order and re-laid out to NHWC here."""
+    if pixel_mask is not None:
+        pixel_mask = pixel_mask.contiguous()
+    if chan_scale is not None:
+        chan_scale = chan_scale.contiguous()
+    if elem_noise is not None:
+        elem_noise = elem_noise.permute(1, 2, 0).contiguous()
+    return _Perturb.apply(as_cl(x), pixel_mask, chan_scale, elem_noise)
+
+
+def channel_mean(x):
+    """torch.mean(x, dim=1, keepdim=True) of a channels_last tensor -> [n,1,H,W] (no autograd)."""
+    _chk(x, 'x', cl=True)
+    n, c, h, w = x.shape
+    out = torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device)
+    call('pxl_channel_mean_nhwc', _p(x), _p(out), n * h * w, c, _stream())
+    return out
+
+
+def argmax_nonzero_mask(logits):
+    """(logits.argmax(1) > 0).float() -> [n,1,H,W] for planar logits."""
+    _chk(logits, 'logits')
+    n, c, h, w = logits.shape
+    out = torch.empty((n, 1, h, w), dtype=torch.float32, device=logits.device)
+    call('pxl_argmax_nonzero_mask', _p(logits), _p(out), n, c, h * w, _stream())
+    return out

@@ -249,3 +249,29 @@ def test_gct_step_matches_reference_train_body():
     rel = np.abs(cs[:, 1] - g['fd_grad_checksum'][:, 1]) / np.maximum(g['fd_grad_checksum'][:, 1], 1e-30)
     assert rel.max() < 2e-3, rel.max()
     np.testing.assert_allclose(_checks([gct.fd[n].detach() for n in fn])[:, 1], g['fd_param_checksum'][:, 1], rtol=1e-5)
+
+
+@pytest.mark.slow
+def test_cct_step_matches_reference_train_body():
+    """SSLCCT._train + WrappedCCTModel.forward + the seven auxiliary decoders (ssl_cct.py:226-745),
+    random draws reproduced from the same python / numpy / torch seeds."""
+    import random
+    from oracle import cct_oracle as C
+    g = load('cct_step_65.npz')
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    st = O.randomize_bn_affine(O.init_deeplabv2(101, cls_bias_std=0.01), 102)
+    cct = C.CctOracle(st, C.init_decoders(103, 7), C.KINDS, cons_scale=30.0, rampup_steps=0, ad_lr_scale=10.0,
+                      lr=0.00025, momentum=0.9, weight_decay=0.0005, max_iters=10)
+    img, lab = O.synthetic_batch(800, 4, 2, 65, 65)
+    random.seed(7); np.random.seed(8); torch.manual_seed(9)
+    out = cct.step(img, lab, 2)
+    assert abs(float(out['task_loss']) - float(g['task_loss'])) <= 2e-5 * float(g['task_loss'])
+    assert abs(float(out['cons_loss']) - float(g['cons_loss'])) <= 1e-4 * float(g['cons_loss'])
+    cs = _checks([out['grads'][n] for n in names])
+    rel = np.abs(cs[:, 1] - g['grad_checksum'][:, 1]) / g['grad_checksum'][:, 1]
+    assert rel.max() < 5e-3 and np.median(rel) < 5e-4, (rel.max(), np.median(rel))
+    cs = _checks([out['dec_grads'][n] for n in cct.dec_names])
+    rel = np.abs(cs[:, 1] - g['dec_grad_checksum'][:, 1]) / np.maximum(g['dec_grad_checksum'][:, 1], 1e-30)
+    assert rel.max() < 2e-3, rel.max()
+    np.testing.assert_allclose(_checks([cct.dec[n] for n in cct.dec_names])[:, 1], g['dec_param_checksum'][:, 1], rtol=1e-5)
+    np.testing.assert_allclose(_checks([cct.s[n] for n in names])[:, 1], g['param_checksum'][:, 1], rtol=1e-5)
