@@ -273,6 +273,15 @@ int pxl_perturb_nhwc(const float* x, const float* pixel_mask, const float* chan_
 int pxl_channel_mean_nhwc(const float* x, float* out, int64_t pixels, int C, void* stream);
 int pxl_argmax_nonzero_mask(const float* logits, float* mask, int n, int C, int64_t HW, void* stream);
 
+/* PSPNet pyramid pooling on NHWC (task/sseg/module/_pspnet.py:57-102): nn.AdaptiveAvgPool2d(bin)
+ * forward (x [N,H,W,C] -> y [N,bin,bin,C]) / backward (x = dy, y = dx); bilinear NHWC -> lanes
+ * [coff, coff+C) of a wider NHWC tensor (backward: in = grad of the wide tensor, out = grad of the small
+ * one); channel-concat copy into / out of a lane range. */
+int pxl_adaptive_avgpool_nhwc(const float* x, float* y, int N, int H, int W, int C, int bin, int backward, void* stream);
+int pxl_bilinear_nhwc(const float* in, float* out, int N, int h, int w, int C, int H, int W, int ldo, int coff,
+                      int align_corners, int backward, void* stream);
+int pxl_copy_lanes_nhwc(const float* src, float* dst, int64_t rows, int C, int ld, int coff, int extract, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

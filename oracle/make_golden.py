@@ -385,6 +385,22 @@ def golden_cct(pixelssl, sseg_proxy, size=65):
     print('cct golden:', rec['task_loss'], rec['cons_loss'], rec['lrs'])
 
 
+def golden_pspnet(pixelssl, size=97, batch=2):
+    """Reference _PSPNet (ResNet-50, OS16) forward in train mode on oracle-initialised weights."""
+    sys.path.insert(0, os.path.join(REF, 'task', 'sseg'))
+    from module import _pspnet
+    net = _pspnet._PSPNet('resnet50', 16, 21, True, False, None)
+    st = O.randomize_bn_affine(O.init_pspnet(111), 112)
+    net.load_state_dict({k: v.clone() for k, v in st.items()}, strict=True)
+    net.train()
+    img, _ = O.synthetic_batch(900, batch, batch, size, size)
+    logits, px = net(img)
+    rec = {'size': size, 'batch': batch, 'logits': logits.detach().numpy(), 'latent_checksum': checksums([('l', px.detach())]),
+           'running_checksum': checksums([(n, b) for n, b in net.named_buffers() if 'num_batches' not in n])}
+    np.savez_compressed(os.path.join(OUT, 'pspnet_forward_%d.npz' % size), **rec)
+    print('pspnet golden: logits', tuple(logits.shape), float(logits.abs().max()))
+
+
 def golden_fp64():
     """Exact-arithmetic (fp64) evaluation of the SAME steps with the oracle, to measure the
     reference's own fp32 rounding noise on these (ill-conditioned, random-init) networks.  The GPU
@@ -441,7 +457,7 @@ if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     pixelssl, sseg_proxy = patch_and_import()
-    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 'gct', 'cct', 'fp64']
+    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 'gct', 'cct', 'pspnet', 'fp64']
     if which == ['fp64']:
         golden_fp64()
         sys.exit(0)
@@ -459,5 +475,7 @@ if __name__ == '__main__':
         golden_gct(pixelssl, sseg_proxy)
     if 'cct' in which:
         golden_cct(pixelssl, sseg_proxy)
+    if 'pspnet' in which:
+        golden_pspnet(pixelssl)
     if 'fp64' in which:
         golden_fp64()

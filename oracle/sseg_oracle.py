@@ -523,3 +523,67 @@ def synthetic_batch(seed, batch, lbs, h, w, num_classes=21, ignore_frac=0.05, ig
     lab[ign] = float(ignore_index)
     lab[lbs:] = -1.0
     return img, lab
+
+
+# ----------------------------------------------------------------------------------------------
+# PSPNet (task/sseg/module/_pspnet.py)
+# ----------------------------------------------------------------------------------------------
+
+R50_BLOCKS = (3, 4, 6, 3)
+PSP_BINS = (1, 2, 3, 6)
+
+
+def pspnet_param_shapes(num_classes=21, output_stride=16, blocks=R50_BLOCKS):
+    """(name, shape, kind) in ``_PSPNet.parameters()`` order: backbone, psp (4 stages + bottleneck), decoder."""
+    out = [(n, s, k) for n, s, k in deeplabv2_param_shapes(num_classes, output_stride, blocks) if n.startswith('backbone.')]
+    for i in range(4):
+        out += [('psp.stages.%d.1.weight' % i, (512, 2048, 1, 1), 'psp_conv'),
+                ('psp.stages.%d.2.weight' % i, (512,), 'bn_w'), ('psp.stages.%d.2.bias' % i, (512,), 'bn_b')]
+    out += [('psp.bottleneck.0.weight', (512, 4096, 3, 3), 'psp_conv'),
+            ('psp.bottleneck.1.weight', (512,), 'bn_w'), ('psp.bottleneck.1.bias', (512,), 'bn_b'),
+            ('decoder.0.weight', (num_classes, 512, 1, 1), 'dec_conv')]
+    for j in (1, 2, 3):
+        out += [('decoder.%d.conv.weight' % j, (num_classes * 4, num_classes, 1, 1), 'dec_conv'),
+                ('decoder.%d.conv.bias' % j, (num_classes * 4,), 'dec_bias')]
+    return out
+
+
+def init_pspnet(seed, num_classes=21, output_stride=16, blocks=R50_BLOCKS):
+    g = torch.Generator().manual_seed(seed)
+    st = {}
+    for name, shape, kind in pspnet_param_shapes(num_classes, output_stride, blocks):
+        if kind == 'conv':
+            st[name] = torch.randn(shape, generator=g) * math.sqrt(2.0 / (shape[2] * shape[3] * shape[0]))
+        elif kind in ('psp_conv', 'dec_conv'):
+            st[name] = torch.randn(shape, generator=g) * math.sqrt(2.0 / (shape[1] * shape[2] * shape[3]))
+        elif kind == 'dec_bias':
+            st[name] = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+        elif kind == 'bn_w':
+            st[name] = torch.ones(shape)
+        else:
+            st[name] = torch.zeros(shape)
+    bn_names = [n[:-len('.weight')] for n, s, k in pspnet_param_shapes(num_classes, output_stride, blocks) if k == 'bn_w']
+    for n in bn_names:
+        c = st[n + '.weight'].numel()
+        st[n + '.running_mean'] = torch.zeros(c)
+        st[n + '.running_var'] = torch.ones(c)
+        st[n + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+    return st
+
+
+def pspnet_forward(img, state, training=True, output_stride=16, blocks=R50_BLOCKS):
+    """_PSPNet.forward (_pspnet.py:122-128) + _PSPModule.forward (:96-102) + upsample / PixelShuffle (:15-54)."""
+    bx = resnet_forward(img, state, training, output_stride, blocks)
+    h, w = bx.shape[2:]
+    pyramids = [bx]
+    for i, b in enumerate(PSP_BINS):
+        y = F.adaptive_avg_pool2d(bx, b)
+        y = F.conv2d(y, state['psp.stages.%d.1.weight' % i])
+        y = F.relu(batch_norm(y, state, 'psp.stages.%d.2' % i, training))
+        pyramids.append(F.interpolate(y, size=(h, w), mode='bilinear', align_corners=False))
+    x = F.conv2d(torch.cat(pyramids, dim=1), state['psp.bottleneck.0.weight'], padding=1)
+    px = F.relu(batch_norm(x, state, 'psp.bottleneck.1', training))
+    x = F.conv2d(px, state['decoder.0.weight'])
+    for j in (1, 2, 3):
+        x = F.pixel_shuffle(F.relu(F.conv2d(x, state['decoder.%d.conv.weight' % j], state['decoder.%d.conv.bias' % j])), 2)
+    return F.interpolate(x, size=img.shape[2:], mode='bilinear', align_corners=True), px

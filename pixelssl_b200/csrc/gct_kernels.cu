@@ -504,3 +504,185 @@ extern "C" int pxl_argmax_nonzero_mask(const float* logits, float* mask, int n, 
     PXL_CHECK_LAUNCH();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// PSPNet pyramid pooling pieces on NHWC (task/sseg/module/_pspnet.py:57-102)
+// ------------------------------------------------------------------------------------------
+// nn.AdaptiveAvgPool2d(bin): window [floor(i*H/bin), ceil((i+1)*H/bin))
+__global__ void __launch_bounds__(256)
+adaptive_pool_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H, int W, int c4, int bin) {
+    const int64_t total = (int64_t)N * bin * bin * c4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % c4);
+        int64_t p = i / c4;
+        const int bx = (int)(p % bin); p /= bin;
+        const int by = (int)(p % bin);
+        const int n = (int)(p / bin);
+        const int y0 = (by * H) / bin, y1 = ((by + 1) * H + bin - 1) / bin;
+        const int x0 = (bx * W) / bin, x1 = ((bx + 1) * W + bin - 1) / bin;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int yy = y0; yy < y1; ++yy)
+            for (int xx = x0; xx < x1; ++xx) {
+                const float4 v = __ldg(x + ((int64_t)(n * H + yy) * W + xx) * c4 + c);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+        const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
+        y[i] = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+    }
+}
+
+// backward: each input pixel gathers from the (at most 2 x 2) bins whose window contains it
+__global__ void __launch_bounds__(256)
+adaptive_pool_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dx, int N, int H, int W, int c4, int bin) {
+    const int64_t total = (int64_t)N * H * W * c4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % c4);
+        int64_t p = i / c4;
+        const int xx = (int)(p % W); p /= W;
+        const int yy = (int)(p % H);
+        const int n = (int)(p / H);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int by = 0; by < bin; ++by) {
+            const int y0 = (by * H) / bin, y1 = ((by + 1) * H + bin - 1) / bin;
+            if (yy < y0 || yy >= y1) continue;
+            for (int bx = 0; bx < bin; ++bx) {
+                const int x0 = (bx * W) / bin, x1 = ((bx + 1) * W + bin - 1) / bin;
+                if (xx < x0 || xx >= x1) continue;
+                const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
+                const float4 g = __ldg(dy + ((int64_t)(n * bin + by) * bin + bx) * c4 + c);
+                s.x += g.x * inv; s.y += g.y * inv; s.z += g.z * inv; s.w += g.w * inv;
+            }
+        }
+        dx[i] = s;
+    }
+}
+
+extern "C" int pxl_adaptive_avgpool_nhwc(const float* x, float* y, int N, int H, int W, int C, int bin, int backward, void* stream) {
+    if (!x || !y || N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || bin <= 0) return PXL_ERR_BAD_ARG;
+    const int64_t total = backward ? (int64_t)N * H * W * (C / 4) : (int64_t)N * bin * bin * (C / 4);
+    int blocks = (int)(pxl_cdiv(total, 256) < PXL_NUM_SMS * 8 ? pxl_cdiv(total, 256) : PXL_NUM_SMS * 8);
+    // backward: x = dy [N,bin,bin,C], y = dx [N,H,W,C]
+    if (backward) adaptive_pool_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C / 4, bin);
+    else adaptive_pool_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C / 4, bin);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// bilinear resize NHWC -> NHWC lanes [coff, coff+C) of a wider tensor (the pyramid branches are
+// written straight into the 4096-lane concat buffer, _pspnet.py:96-101); same index arithmetic as ATen
+__device__ __forceinline__ float src_idx(float scale, int dst, bool ac) {
+    if (ac) return scale * (float)dst;
+    const float s = scale * ((float)dst + 0.5f) - 0.5f;
+    return s < 0.f ? 0.f : s;
+}
+
+__global__ void __launch_bounds__(256)
+bilinear_nhwc_fwd_kernel(const float4* __restrict__ in, float* __restrict__ out, int N, int h, int w, int c4, int H, int W,
+                         int ldo, int coff, float sh, float sw, bool ac) {
+    const int64_t total = (int64_t)N * H * W * c4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % c4);
+        int64_t p = i / c4;
+        const int X = (int)(p % W); p /= W;
+        const int Y = (int)(p % H);
+        const int n = (int)(p / H);
+        const float fy = src_idx(sh, Y, ac), fx = src_idx(sw, X, ac);
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float ly1 = fy - (float)y0, lx1 = fx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+        const float4 a = __ldg(in + ((int64_t)(n * h + y0) * w + x0) * c4 + c), b = __ldg(in + ((int64_t)(n * h + y0) * w + x1) * c4 + c);
+        const float4 d = __ldg(in + ((int64_t)(n * h + y1) * w + x0) * c4 + c), e = __ldg(in + ((int64_t)(n * h + y1) * w + x1) * c4 + c);
+        float4 r;
+        r.x = ly0 * (lx0 * a.x + lx1 * b.x) + ly1 * (lx0 * d.x + lx1 * e.x);
+        r.y = ly0 * (lx0 * a.y + lx1 * b.y) + ly1 * (lx0 * d.y + lx1 * e.y);
+        r.z = ly0 * (lx0 * a.z + lx1 * b.z) + ly1 * (lx0 * d.z + lx1 * e.z);
+        r.w = ly0 * (lx0 * a.w + lx1 * b.w) + ly1 * (lx0 * d.w + lx1 * e.w);
+        *reinterpret_cast<float4*>(out + ((int64_t)(n * H + Y) * W + X) * ldo + coff + 4 * c) = r;
+    }
+}
+
+// backward: one thread per (input pixel, channel quad) gathers every output pixel in its support
+__global__ void __launch_bounds__(256)
+bilinear_nhwc_bwd_kernel(const float* __restrict__ gout, float4* __restrict__ gin, int N, int h, int w, int c4, int H, int W,
+                         int ldo, int coff, float sh, float sw, bool ac) {
+    const int64_t total = (int64_t)N * h * w * c4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % c4);
+        int64_t p = i / c4;
+        const int xi = (int)(p % w); p /= w;
+        const int yi = (int)(p % h);
+        const int n = (int)(p / h);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int Y = 0; Y < H; ++Y) {
+            const float fy = src_idx(sh, Y, ac);
+            const int y0 = (int)fy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
+            const float ly1 = fy - (float)y0;
+            float wy = 0.f;
+            if (y0 == yi) wy += 1.f - ly1;
+            if (y1 == yi) wy += ly1;
+            if (y0 != yi && y1 != yi) continue;
+            for (int X = 0; X < W; ++X) {
+                const float fx = src_idx(sw, X, ac);
+                const int x0 = (int)fx, x1 = x0 + (x0 < w - 1 ? 1 : 0);
+                if (x0 != xi && x1 != xi) continue;
+                const float lx1 = fx - (float)x0;
+                float wx = 0.f;
+                if (x0 == xi) wx += 1.f - lx1;
+                if (x1 == xi) wx += lx1;
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gout + ((int64_t)(n * H + Y) * W + X) * ldo + coff + 4 * c));
+                const float ww = wy * wx;
+                s.x += g.x * ww; s.y += g.y * ww; s.z += g.z * ww; s.w += g.w * ww;
+            }
+        }
+        gin[i] = s;
+    }
+}
+
+static inline float rs_scale(int in, int out, int ac) {
+    if (ac) return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    return (float)in / (float)out;
+}
+
+extern "C" int pxl_bilinear_nhwc(const float* in, float* out, int N, int h, int w, int C, int H, int W, int ldo, int coff,
+                                 int align_corners, int backward, void* stream) {
+    if (!in || !out || N <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || (ldo & 3) || (coff & 3) || coff + C > ldo)
+        return PXL_ERR_BAD_ARG;
+    const float sh = rs_scale(h, H, align_corners), sw = rs_scale(w, W, align_corners);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!backward) {
+        const int64_t total = (int64_t)N * H * W * (C / 4);
+        int blocks = (int)(pxl_cdiv(total, 256) < PXL_NUM_SMS * 8 ? pxl_cdiv(total, 256) : PXL_NUM_SMS * 8);
+        bilinear_nhwc_fwd_kernel<<<blocks, 256, 0, st>>>((const float4*)in, out, N, h, w, C / 4, H, W, ldo, coff, sh, sw, align_corners != 0);
+    } else {      // in = grad of the wide output [N,H,W,ldo], out = grad of the small input [N,h,w,C]
+        const int64_t total = (int64_t)N * h * w * (C / 4);
+        int blocks = (int)(pxl_cdiv(total, 256) < PXL_NUM_SMS * 8 ? pxl_cdiv(total, 256) : PXL_NUM_SMS * 8);
+        bilinear_nhwc_bwd_kernel<<<blocks, 256, 0, st>>>(in, (float4*)out, N, h, w, C / 4, H, W, ldo, coff, sh, sw, align_corners != 0);
+    }
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// copy a dense NHWC tensor into / out of lanes [coff, coff+C) of a wider one (channel concat)
+__global__ void __launch_bounds__(256)
+copy_lanes_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int64_t rows, int c4, int ld4, int coff4, int extract) {
+    const int64_t total = rows * c4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t r = i / c4;
+        const int c = (int)(i % c4);
+        if (!extract) dst[r * ld4 + coff4 + c] = src[i];
+        else dst[i] = src[r * ld4 + coff4 + c];
+    }
+}
+
+extern "C" int pxl_copy_lanes_nhwc(const float* src, float* dst, int64_t rows, int C, int ld, int coff, int extract, void* stream) {
+    if (!src || !dst || rows <= 0 || C <= 0 || (C & 3) || (ld & 3) || (coff & 3) || coff + C > ld) return PXL_ERR_BAD_ARG;
+    const int64_t total = rows * (C / 4);
+    copy_lanes_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const float4*)src, (float4*)dst, rows, C / 4, ld / 4, coff / 4, extract);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}

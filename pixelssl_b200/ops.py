@@ -1182,3 +1182,67 @@ def argmax_nonzero_mask(logits):
     out = torch.empty((n, 1, h, w), dtype=torch.float32, device=logits.device)
     call('pxl_argmax_nonzero_mask', _p(logits), _p(out), n, c, h * w, _stream())
     return out
+
+
+class _AdaptiveAvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bin_size):
+        _chk(x, 'x', cl=True)
+        n, c, h, w = x.shape
+        y = torch.empty((n, c, bin_size, bin_size), dtype=torch.float32, device=x.device, memory_format=CL)
+        call('pxl_adaptive_avgpool_nhwc', _p(x), _p(y), n, h, w, c, bin_size, 0, _stream())
+        ctx.meta = (n, c, h, w, bin_size)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, h, w, bin_size = ctx.meta
+        g = as_cl(g)
+        dx = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device, memory_format=CL)
+        call('pxl_adaptive_avgpool_nhwc', _p(g), _p(dx), n, h, w, c, bin_size, 1, _stream())
+        return dx, None
+
+
+def adaptive_avg_pool(x, bin_size):
+    """nn.AdaptiveAvgPool2d(bin_size) on a channels_last tensor (_pspnet.py:90)."""
+    return _AdaptiveAvgPool.apply(as_cl(x), int(bin_size))
+
+
+class _PyramidConcat(torch.autograd.Function):
+    """torch.cat([features] + [F.interpolate(branch, (h, w), 'bilinear', align_corners=False) ...], 1)
+    (_pspnet.py:96-101) written straight into one NHWC buffer."""
+
+    @staticmethod
+    def forward(ctx, features, *branches):
+        _chk(features, 'features', cl=True)
+        n, c0, H, W = features.shape
+        chans = [c0] + [b.shape[1] for b in branches]
+        ld = sum(chans)
+        out = torch.empty((n, ld, H, W), dtype=torch.float32, device=features.device, memory_format=CL)
+        call('pxl_copy_lanes_nhwc', _p(features), _p(out), n * H * W, c0, ld, 0, 0, _stream())
+        off = c0
+        for b in branches:
+            _chk(b, 'branch', cl=True)
+            call('pxl_bilinear_nhwc', _p(b), _p(out), n, b.shape[2], b.shape[3], b.shape[1], H, W, ld, off, 0, 0, _stream())
+            off += b.shape[1]
+        ctx.meta = (n, H, W, ld, chans, [tuple(b.shape[2:]) for b in branches])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, H, W, ld, chans, sizes = ctx.meta
+        g = as_cl(g)
+        dev = g.device
+        df = torch.empty((n, chans[0], H, W), dtype=torch.float32, device=dev, memory_format=CL)
+        call('pxl_copy_lanes_nhwc', _p(g), _p(df), n * H * W, chans[0], ld, 0, 1, _stream())
+        grads, off = [df], chans[0]
+        for c, (h, w) in zip(chans[1:], sizes):
+            db = torch.empty((n, c, h, w), dtype=torch.float32, device=dev, memory_format=CL)
+            call('pxl_bilinear_nhwc', _p(g), _p(db), n, h, w, c, H, W, ld, off, 0, 1, _stream())
+            grads.append(db)
+            off += c
+        return tuple(grads)
+
+
+def pyramid_concat(features, branches):
+    return _PyramidConcat.apply(as_cl(features), *[as_cl(b) for b in branches])

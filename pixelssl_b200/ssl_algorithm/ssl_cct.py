@@ -25,7 +25,7 @@ from .. import ops
 from ..utils import CLASSIFICATION, logger, cmd, tool
 from ..nn import func
 from ..nn.arena import EngineParallel
-from ..nn.modules import Conv2d
+from ..nn.modules import Conv2d, PixelShuffle, upsample
 from . import ssl_base
 
 
@@ -60,31 +60,6 @@ def ssl_cct(args, model_dict, optimizer_dict, lrer_dict, criterion_dict, task_fu
 # ------------------------------------------------------------------------------------------------
 # decoder building blocks (ssl_cct.py:501-539; shared with the PSPNet head, _pspnet.py:15-54)
 # ------------------------------------------------------------------------------------------------
-
-class PixelShuffle(nn.Module):
-    """conv1x1 C -> 4C (bias, ICNR init) + ReLU + nn.PixelShuffle(2)."""
-
-    def __init__(self, n_channels, scale=2):
-        super().__init__()
-        assert scale == 2
-        self.n_channels = n_channels
-        self.conv = Conv2d(n_channels, n_channels * 4, 1, bias=True)
-        k = nn.init.kaiming_normal_(torch.zeros(n_channels, n_channels, 1, 1)).transpose(0, 1)
-        k = k.contiguous().view(n_channels, n_channels, -1).repeat(1, 1, 4)
-        self.conv.weight.data.copy_(k.contiguous().view(n_channels, n_channels * 4, 1, 1).transpose(0, 1))
-
-    def forward(self, x):
-        y = ops.leaky_relu(self.conv(x), 0.0)
-        return ops.pixel_shuffle2(y, self.n_channels)
-
-
-def upsample(in_channels, out_channels, upscale):
-    layers = [Conv2d(in_channels, out_channels, 1, bias=False, out_lanes=(out_channels + 31) // 32 * 32)]
-    nn.init.kaiming_normal_(layers[0].weight.data, nonlinearity='relu')
-    for _ in range(int(math.log(upscale, 2))):
-        layers.append(PixelShuffle(out_channels, scale=2))
-    return nn.Sequential(*layers)
-
 
 def _nearest_mask(mask_full, size):
     """F.interpolate(mask, size, mode='nearest') of a [n,1,H,W] {0,1} mask (small, torch op)."""

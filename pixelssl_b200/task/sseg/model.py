@@ -6,7 +6,7 @@ import torch.nn as nn
 
 from ... import ops
 from ...utils import logger, cmd
-from .module import deeplab_v2
+from .module import deeplab_v2, pspnet as pspnet_module
 
 
 def add_parser_arguments(parser):
@@ -17,6 +17,10 @@ def add_parser_arguments(parser):
 
 def deeplabv2():
     return DeepLabV2
+
+
+def pspnet():
+    return PSPNet
 
 
 class LazyActivation:
@@ -70,6 +74,35 @@ class DeepLabV2(TaskModel):
         resulter, debugger = {}, {}
         if not len(inp) == 1:
             logger.log_err('Semantic segmentation model DeepLab requires only one input\n'
+                           'However, {0} inputs are given\n'.format(len(inp)))
+        pred, latent = self.model(inp[0])
+        resulter['pred'] = (pred,)
+        resulter['activated_pred'] = LazyActivation(pred)
+        resulter['ssls4l_rc_inp'] = pred
+        resulter['sslcct_ad_inp'] = latent
+        return resulter, debugger
+
+
+class PSPNet(TaskModel):
+    """task/sseg/model.py:84-125."""
+
+    def __init__(self, args):
+        super().__init__(args)
+        if args.backbone not in ('resnet50', 'resnet101', 'resnet101-coco'):
+            logger.log_err('PSPNet does not support the backbone: {0}\n'.format(args.backbone))
+        self.model = pspnet_module.PSPNet(backbone=args.backbone, output_stride=args.output_stride,
+                                          num_classes=args.num_classes, sync_bn=True, freeze_bn=args.freeze_bn,
+                                          pretrained_backbone_url=getattr(args, 'pretrained_backbone', None))
+        self.param_groups = [
+            {'params': [p for p in self.model.get_backbone_params() if p.requires_grad], 'lr': args.lr},
+            {'params': [p for p in self.model.get_psp_params() if p.requires_grad], 'lr': args.lr * 10},
+            {'params': [p for p in self.model.get_decoder_params() if p.requires_grad], 'lr': args.lr * 10},
+        ]
+
+    def forward(self, inp):
+        resulter, debugger = {}, {}
+        if not len(inp) == 1:
+            logger.log_err('Semantic segmentation model PSPNet requires only one input\n'
                            'However, {0} inputs are given\n'.format(len(inp)))
         pred, latent = self.model(inp[0])
         resulter['pred'] = (pred,)

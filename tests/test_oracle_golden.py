@@ -275,3 +275,14 @@ def test_cct_step_matches_reference_train_body():
     assert rel.max() < 2e-3, rel.max()
     np.testing.assert_allclose(_checks([cct.dec[n] for n in cct.dec_names])[:, 1], g['dec_param_checksum'][:, 1], rtol=1e-5)
     np.testing.assert_allclose(_checks([cct.s[n] for n in names])[:, 1], g['param_checksum'][:, 1], rtol=1e-5)
+
+
+def test_pspnet_forward_matches_reference():
+    g = load('pspnet_forward_97.npz')
+    st = O.randomize_bn_affine(O.init_pspnet(111), 112)
+    img, _ = O.synthetic_batch(900, int(g['batch']), int(g['batch']), int(g['size']), int(g['size']))
+    with torch.no_grad():
+        logits, px = O.pspnet_forward(img, st, training=True)
+    assert np.abs(logits.numpy() - g['logits']).max() / np.abs(g['logits']).max() < 1e-5
+    cs = np.array([float(px.double().sum()), float((px.double() ** 2).sum())])
+    np.testing.assert_allclose(cs, g['latent_checksum'][0], rtol=1e-5)
