@@ -275,7 +275,7 @@ def main():
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='engine', choices=['engine', 'reference'])
-    ap.add_argument('--precision', type=str, default=os.environ.get('PXL_CONV_PRECISION', 'fp32'),
+    ap.add_argument('--precision', type=str, default=os.environ.get('PXL_CONV_PRECISION', 'tf32x3'),
                     choices=['fp32', 'tf32', 'tf32x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -182,7 +182,10 @@ int pxl_conv_tc_launch(const pxl_conv_geom* geom_host, const int* taps_dydx_host
 typedef struct {
     int w_ntaps;             /* taps held by the weight tensor (>= geom.ntaps); 0 = geom.ntaps */
     const int* widx_host;    /* nullable: identity */
-    int out_mul, out_offy, out_offx, out_H, out_W;
+    int out_mul, out_offy, out_offx, out_H, out_W;   /* out_mul == 0 is read as "no output transform" */
+    double* bn_stats;        /* nullable DEVICE pointer [2*Cout] fp64: the epilogue adds sum(y), sum(y^2) per
+                              * output channel (the statistics pass of the BatchNorm that follows,
+                              * sync_batchnorm/batchnorm.py:60-62) */
 } pxl_conv_tc_ext;
 int pxl_conv_tc_launch_ex(const pxl_conv_geom* geom_host, const int* taps_dydx_host, const pxl_conv_tc_ext* ext_host,
                           const float* in_hi, const float* in_lo, const float* w_hi, const float* w_lo,

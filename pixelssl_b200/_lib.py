@@ -22,7 +22,8 @@ class ConvGeom(ctypes.Structure):
 class ConvTcExt(ctypes.Structure):
     """mirror of pxl_conv_tc_ext"""
     _fields_ = [('w_ntaps', c_int), ('widx_host', ctypes.POINTER(c_int)), ('out_mul', c_int),
-                ('out_offy', c_int), ('out_offx', c_int), ('out_H', c_int), ('out_W', c_int)]
+                ('out_offy', c_int), ('out_offx', c_int), ('out_H', c_int), ('out_W', c_int),
+                ('bn_stats', c_void_p)]
 
 
 P = c_void_p

@@ -20,6 +20,7 @@
 // out, so a protocol bug can never hang the GPU.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 // ------------------------------------------------------------------------------------------
 // driver entry point for tensor-map encoding (no link-time dependency on libcuda)
@@ -175,6 +176,7 @@ struct TcParams {
     int BW, BH, tilesW, tilesH;
     int BN, stages, nsplit;
     int nacc;       // TMEM accumulators used round-robin over k-iterations (summed with RN adds in the epilogue)
+    int a_inkernel; // 3xTF32 only: A arrives as raw fp32 and is split hi/lo in shared memory by the epilogue warps
     int in_mul;     // input pixel = output pixel * in_mul + tap (stride-2 forward uses the TMA traversal stride)
     int out_mul, out_offy, out_offx, outH, outW;   // output pixel (oy,ox) is stored at (oy*out_mul+offy, ox*out_mul+offx)
     short dy[PXL_MAX_TAPS], dx[PXL_MAX_TAPS], widx[PXL_MAX_TAPS];
@@ -185,9 +187,10 @@ struct TcParams {
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
-               const TcParams p, const float* __restrict__ bias, float* __restrict__ out, int* __restrict__ err_flag) {
+               const TcParams p, const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats,
+               int* __restrict__ err_flag) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[8], empty_bar[8], acc_bar;
+    __shared__ uint64_t full_bar[8], empty_bar[8], ready_bar[8], acc_bar;
     __shared__ uint32_t tmem_base_slot;
 
     // 1024-byte aligned operand ring
@@ -208,7 +211,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t tmem_cols = acc_cols * p.nacc;              // power of two, <= 512
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128); }
         mbar_init(&acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -222,7 +225,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ================= TMA producer =================
         if (lane == 0) {
             // bytes the TMA unit will deliver per stage: full boxes, OOB parts are zero-filled but counted
-            const uint32_t tx = (uint32_t)((p.BW * p.BH * 128 + b_bytes) * (p.nsplit == 3 ? 2 : 1));
+            uint32_t tx = (uint32_t)((p.BW * p.BH * 128 + b_bytes) * (p.nsplit == 3 ? 2 : 1));
+            if (p.a_inkernel) tx -= (uint32_t)(p.BW * p.BH * 128);      // no A_lo box: it is produced in shared memory
             bool ok = true;
             for (int it = 0; it < iters && ok; ++it) {
                 const int s = it % p.stages;
@@ -237,7 +241,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 tma_load_4d(sa, &mapA, &full_bar[s], c0, ax, ay, n);
                 tma_load_2d(sa + TC_A_BYTES, &mapB, &full_bar[s], bk, n0);
                 if (p.nsplit == 3) {
-                    tma_load_4d(sa + per_op, &mapAlo, &full_bar[s], c0, ax, ay, n);
+                    if (!p.a_inkernel) tma_load_4d(sa + per_op, &mapAlo, &full_bar[s], c0, ax, ay, n);
                     tma_load_2d(sa + per_op + TC_A_BYTES, &mapBlo, &full_bar[s], bk, n0);
                 }
             }
@@ -250,7 +254,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int it = 0; it < iters && ok; ++it) {
                 const int s = it % p.stages;
                 const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                ok = mbar_wait(&full_bar[s], ph, err_flag, 2);
+                ok = mbar_wait(p.a_inkernel ? &ready_bar[s] : &full_bar[s], ph, err_flag, 2);
                 if (!ok) break;
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
@@ -274,6 +278,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ================= epilogue: TMEM -> registers -> global (NHWC rows) =================
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;             // tile row = output pixel within the spatial tile
+        if (p.a_inkernel) {
+            // ---- operand transform: raw fp32 A tile -> (hi in place, lo) ; elementwise, so the TMA
+            // swizzle is preserved.  Thread t owns the 16-byte chunks t, t+128, ... (conflict-free).
+            const int t = threadIdx.x - 64;
+            bool okt = true;
+            for (int it = 0; it < iters && okt; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                okt = mbar_wait(&full_bar[s], ph, err_flag, 4);
+                if (!okt) break;
+                float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+                float4* a_lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + per_op);
+#pragma unroll
+                for (int c = 0; c < TC_A_BYTES / 16 / 128; ++c) {
+                    const float4 v = a_hi[t + c * 128];
+                    float4 h, l;
+                    const float* vp = &v.x; float* hp = &h.x; float* lp = &l.x;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        uint32_t u;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vp[e]));
+                        u &= 0xFFFFE000u;
+                        hp[e] = __uint_as_float(u);
+                        lp[e] = vp[e] - hp[e];
+                    }
+                    a_hi[t + c * 128] = h;
+                    a_lo[t + c * 128] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
+            }
+        }
         const bool ok = __all_sync(0xffffffffu, mbar_wait(&acc_bar, 0, err_flag, 3));
         tc_fence_after();
         if (ok) {
@@ -291,8 +327,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int c = 0; c < 32; ++c) v[c] += u[c];
                 }
-                if (!valid) continue;
                 const int cb = n0 + j;
+                if (stats) {
+                    // per-channel sum / sum of squares of this tile for the BatchNorm that follows
+                    // (sync_batchnorm/batchnorm.py:60-62): warp transpose-reduce over the 32 rows, then one
+                    // fp64 atomic per channel and warp.  Rows outside the image contribute nothing.
+                    float sv[32], sq[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float o = valid ? v[c] + ((bias && cb + c < p.Cout) ? __ldg(bias + cb + c) : 0.f) : 0.f;
+                        sv[c] = o; sq[c] = o * o;
+                    }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float s_send = up ? sv[i] : sv[i + off], q_send = up ? sq[i] : sq[i + off];
+                            const float s_recv = __shfl_xor_sync(0xffffffffu, s_send, off);
+                            const float q_recv = __shfl_xor_sync(0xffffffffu, q_send, off);
+                            sv[i] = (up ? sv[i + off] : sv[i]) + s_recv;
+                            sq[i] = (up ? sq[i + off] : sq[i]) + q_recv;
+                        }
+                    }
+                    if (cb + lane < p.Cout) {
+                        atomicAdd(stats + cb + lane, (double)sv[0]);
+                        atomicAdd(stats + p.Cout + cb + lane, (double)sq[0]);
+                    }
+                }
+                if (!valid) continue;
                 if (cb + 31 < p.Cout && (p.ldo & 3) == 0) {
 #pragma unroll
                     for (int c = 0; c < 32; c += 4) {
@@ -383,20 +446,22 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
     if (g->Cin % 32 != 0 || g->ntaps > PXL_MAX_TAPS) return PXL_ERR_UNSUPPORTED;
     const int wtaps = ext && ext->w_ntaps > 0 ? ext->w_ntaps : g->ntaps;    // taps in the weight tensor
     const int nsplit = g->precision == 2 ? 3 : 1;
-    if (nsplit == 3 && (!in_lo || !w_lo)) return PXL_ERR_BAD_ARG;
-    const bool has_out_xform = ext && (ext->out_mul != 1 || ext->out_offy != 0 || ext->out_offx != 0);
+    if (nsplit == 3 && !w_lo) return PXL_ERR_BAD_ARG;
+    const int a_inkernel = (nsplit == 3 && !in_lo) ? 1 : 0;       // in_hi then holds the raw fp32 activations
+    const int omul = (ext && ext->out_mul > 0) ? ext->out_mul : 1;
+    const bool has_out_xform = ext && (omul != 1 || ext->out_offy != 0 || ext->out_offx != 0);
     bool flat = (g->ntaps == 1 && taps[0] == 0 && taps[1] == 0 && g->OH == g->H && g->OW == g->W && g->mul == 1 &&
                  !has_out_xform);
     TcParams p;
     p.Cin = g->Cin; p.Cout = g->Cout; p.ldo = g->ldo; p.ntaps = g->ntaps; p.kchunks = g->Cin / 32;
-    p.nsplit = nsplit;
+    p.nsplit = nsplit; p.a_inkernel = a_inkernel;
     for (int t = 0; t < g->ntaps; ++t) {
         p.dy[t] = (short)taps[2 * t]; p.dx[t] = (short)taps[2 * t + 1];
         p.widx[t] = (short)((ext && ext->widx_host) ? ext->widx_host[t] : t);
         if (p.widx[t] < 0 || p.widx[t] >= wtaps) return PXL_ERR_BAD_ARG;
     }
     p.in_mul = g->mul;
-    p.out_mul = ext ? ext->out_mul : 1; p.out_offy = ext ? ext->out_offy : 0; p.out_offx = ext ? ext->out_offx : 0;
+    p.out_mul = omul; p.out_offy = has_out_xform ? ext->out_offy : 0; p.out_offx = has_out_xform ? ext->out_offx : 0;
     int mapW, mapH, mapN;
     if (flat) {
         const int64_t M = (int64_t)g->N * g->H * g->W;
@@ -412,12 +477,25 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
     pick_tile(p.OH, p.OW, flat, p.BW, p.BH);
     if (g->mul == 2 && (p.BW > 128 || p.BH > 128)) return PXL_ERR_UNSUPPORTED;
     p.tilesW = (p.OW + p.BW - 1) / p.BW; p.tilesH = (p.OH + p.BH - 1) / p.BH;
+    // tuning knobs (environment, read once): shared-memory budget per CTA in KB (<= ~100 lets two CTAs share
+    // an SM so one CTA's epilogue overlaps the other's main loop), N-tile cap, accumulator count
+    static int cfg_budget_kb = -1, cfg_bn_max1 = 256, cfg_bn_max3 = 128, cfg_nacc3 = 4;
+    if (cfg_budget_kb < 0) {
+        const char* e = getenv("PXL_TC_SMEM_KB"); cfg_budget_kb = e ? atoi(e) : 200;
+        if ((e = getenv("PXL_TC_BN_MAX_TF32"))) cfg_bn_max1 = atoi(e);
+        if ((e = getenv("PXL_TC_BN_MAX_TF32X3"))) cfg_bn_max3 = atoi(e);
+        if ((e = getenv("PXL_TC_NACC_TF32X3"))) cfg_nacc3 = atoi(e);
+    }
     p.BN = g->Cout > 128 ? 256 : (g->Cout > 64 ? 128 : (g->Cout > 32 ? 64 : 32));
-    if (nsplit == 3 && p.BN > 128) p.BN = 128;                 // leave TMEM room for 4 accumulators
-    p.nacc = nsplit == 3 ? 4 : 1;
+    const int bn_cap = nsplit == 3 ? cfg_bn_max3 : cfg_bn_max1;
+    if (p.BN > bn_cap) p.BN = bn_cap;
+    p.nacc = nsplit == 3 ? cfg_nacc3 : 1;
+    while (p.nacc > 1 && (p.BN < 32 ? 32 : p.BN) * p.nacc > 512) p.nacc >>= 1;
     const int per_op = TC_A_BYTES + p.BN * 128;
     const int stage_bytes = per_op * (nsplit == 3 ? 2 : 1);
-    const int budget = 200 * 1024;
+    // measured (tools/sweep_tc.sh, MT step): single-pass TF32 is 6.5 % faster with two co-resident CTAs per SM
+    // (<= 100 KB each: one CTA's epilogue overlaps the other's main loop); 3xTF32 needs the deeper ring
+    const int budget = (getenv("PXL_TC_SMEM_KB") ? cfg_budget_kb : (nsplit == 3 ? 200 : 100)) * 1024;
     p.stages = budget / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return PXL_ERR_UNSUPPORTED;
@@ -429,8 +507,11 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
     rc = make_w_map(&mB, w_hi, (int64_t)wtaps * g->Cin, g->Cout, p.BN);
     if (rc) return rc;
     if (nsplit == 3) {
-        rc = make_act_map(&mAlo, in_lo, g->Cin, mapW, mapH, mapN, p.BW, p.BH, g->mul);
-        if (rc) return rc;
+        if (a_inkernel) mAlo = mA;
+        else {
+            rc = make_act_map(&mAlo, in_lo, g->Cin, mapW, mapH, mapN, p.BW, p.BH, g->mul);
+            if (rc) return rc;
+        }
         rc = make_w_map(&mBlo, w_lo, (int64_t)wtaps * g->Cin, g->Cout, p.BN);
         if (rc) return rc;
     } else {
@@ -450,7 +531,7 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
         attr = true;
     }
     dim3 grid((unsigned)((int64_t)p.N * p.tilesH * p.tilesW), (unsigned)((g->Cout + p.BN - 1) / p.BN));
-    conv_tc_kernel<<<grid, 192, smem, st>>>(mA, mAlo, mB, mBlo, p, bias, out, g_err_flag);
+    conv_tc_kernel<<<grid, 192, smem, st>>>(mA, mAlo, mB, mBlo, p, bias, out, ext ? ext->bn_stats : nullptr, g_err_flag);
     PXL_CHECK_LAUNCH();
     return 0;
 }
@@ -487,6 +568,7 @@ struct WgParams {
     int N, OH, OW, mul;
     int BW, BH, tilesW, tilesH, rows, rows_alloc;
     int BN, stages, nsplit, nacc;
+    int inkernel;      // 3xTF32: dY / X arrive raw and are split hi/lo in shared memory by the epilogue warps
     int tiles_ci, ktiles_per_cta, ktiles_total;
     short dy[PXL_MAX_TAPS], dx[PXL_MAX_TAPS];
 };
@@ -511,7 +593,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
                      const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapXLo,
                      const WgParams p, float* __restrict__ dw, int* __restrict__ err_flag) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[8], empty_bar[8], acc_bar;
+    __shared__ uint64_t full_bar[8], empty_bar[8], ready_bar[8], acc_bar;
     __shared__ uint32_t tmem_base_slot;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 
@@ -541,7 +623,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128); }
         mbar_init(&acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -555,7 +637,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
         if (warp == 0) {
             if (lane == 0) {
                 const uint32_t box_bytes = (uint32_t)(p.rows * 128);
-                const uint32_t tx = box_bytes * (uint32_t)(nsA + nsB) * (p.nsplit == 3 ? 2u : 1u);
+                const uint32_t tx = box_bytes * (uint32_t)(nsA + nsB) * ((p.nsplit == 3 && !p.inkernel) ? 2u : 1u);
                 const int tdy = p.dy[tap], tdx = p.dx[tap];
                 bool ok = true;
                 for (int it = 0; it < iters && ok; ++it) {
@@ -568,7 +650,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
                     const int w0 = tw * p.BW, h0 = th * p.BH;
                     uint8_t* sa = smem + (size_t)s * stage_bytes;
                     mbar_expect_tx(&full_bar[s], tx);
-                    for (int part = 0; part < (p.nsplit == 3 ? 2 : 1); ++part) {
+                    for (int part = 0; part < ((p.nsplit == 3 && !p.inkernel) ? 2 : 1); ++part) {
                         uint8_t* base = sa + (size_t)part * per_op;
                         const CUtensorMap* mdy = part ? &mapDyLo : &mapDy;
                         const CUtensorMap* mx = part ? &mapXLo : &mapX;
@@ -589,7 +671,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
                 for (int it = 0; it < iters && ok; ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                    ok = mbar_wait(&full_bar[s], ph, err_flag, 12);
+                    ok = mbar_wait(p.inkernel ? &ready_bar[s] : &full_bar[s], ph, err_flag, 12);
                     if (!ok) break;
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
@@ -611,6 +693,37 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
         } else {
             const int q = warp & 3;
             const int co = co0 + q * 32 + lane;
+            if (p.inkernel) {
+                // raw fp32 slabs -> hi (in place) / lo (second half of the stage); elementwise, layout-agnostic
+                const int t = threadIdx.x - 64;
+                const int chunks = per_op / 16;
+                bool okt = true;
+                for (int it = 0; it < iters && okt; ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    okt = mbar_wait(&full_bar[s], ph, err_flag, 14);
+                    if (!okt) break;
+                    float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+                    float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + per_op);
+                    for (int c = t; c < chunks; c += 128) {
+                        const float4 v = hi[c];
+                        float4 h, l;
+                        const float* vp = &v.x; float* hp = &h.x; float* lp = &l.x;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            uint32_t u;
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vp[e]));
+                            u &= 0xFFFFE000u;
+                            hp[e] = __uint_as_float(u);
+                            lp[e] = vp[e] - hp[e];
+                        }
+                        hi[c] = h;
+                        lo[c] = l;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
+                }
+            }
             const bool ok = __all_sync(0xffffffffu, mbar_wait(&acc_bar, 0, err_flag, 13));
             tc_fence_after();
             if (ok) {
@@ -675,10 +788,11 @@ extern "C" int pxl_conv_wgrad_tc_launch(const pxl_conv_geom* g, const int* taps,
     if (g->div != 1 || (g->mul != 1 && g->mul != 2)) return PXL_ERR_UNSUPPORTED;   // stride 2 via TMA traversal stride
     if (g->Cin % 32 != 0 || g->ldo % 32 != 0 || g->ntaps > PXL_MAX_TAPS) return PXL_ERR_UNSUPPORTED;
     const int nsplit = g->precision == 2 ? 3 : 1;
-    if (nsplit == 3 && (!in_lo || !dy_lo)) return PXL_ERR_BAD_ARG;
+    if (nsplit == 3 && ((in_lo == nullptr) != (dy_lo == nullptr))) return PXL_ERR_BAD_ARG;
+    const int inkernel = (nsplit == 3 && !in_lo) ? 1 : 0;         // in_hi / dy_hi then hold the raw fp32 tensors
     const bool flat = (g->ntaps == 1 && taps[0] == 0 && taps[1] == 0 && g->OH == g->H && g->OW == g->W && g->mul == 1);
     WgParams p;
-    p.Cin = g->Cin; p.Cout = g->Cout; p.ldo = g->ldo; p.ntaps = g->ntaps; p.mul = g->mul; p.nsplit = nsplit;
+    p.Cin = g->Cin; p.Cout = g->Cout; p.ldo = g->ldo; p.ntaps = g->ntaps; p.mul = g->mul; p.nsplit = nsplit; p.inkernel = inkernel;
     for (int t = 0; t < g->ntaps; ++t) { p.dy[t] = (short)taps[2 * t]; p.dx[t] = (short)taps[2 * t + 1]; }
     int mapW, mapH, mapN, inW, inH;
     if (flat) {
@@ -719,7 +833,7 @@ extern "C" int pxl_conv_wgrad_tc_launch(const pxl_conv_geom* g, const int* taps,
     if (rc) return rc;
     rc = make_act_map_strided(&mX, in_hi, g->Cin, inW, inH, mapN, p.BW, p.BH, g->mul);
     if (rc) return rc;
-    if (nsplit == 3) {
+    if (nsplit == 3 && !inkernel) {
         rc = make_act_map_strided(&mDyLo, dy_lo, g->ldo, mapW, mapH, mapN, p.BW, p.BH, 1);
         if (rc) return rc;
         rc = make_act_map_strided(&mXLo, in_lo, g->Cin, inW, inH, mapN, p.BW, p.BH, g->mul);

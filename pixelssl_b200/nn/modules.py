@@ -18,6 +18,7 @@ class Conv2d(nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, bias=True, out_lanes=0):
         super().__init__()
         self.out_lanes = out_lanes        # > out_channels: zero-padded output lanes (e.g. 21 -> 32)
+        self.feeds_bn = False             # set by the owner when a BatchNorm2d consumes the output directly
         self.in_channels, self.out_channels = in_channels, out_channels
         self.kernel_size = (kernel_size, kernel_size)
         self.stride, self.padding, self.dilation = stride, padding, dilation
@@ -36,7 +37,8 @@ class Conv2d(nn.Module):
             # input lanes were zero-padded (e.g. 21 -> 32 so the tcgen05 kernel applies): pad the weight
             # with matching zero channels; tiny tensor, plain autograd ops
             w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, x.shape[1] - self.in_channels)).contiguous(memory_format=CL)
-        return ops.conv2d(ops.as_cl(x), w, self.bias, self.stride, self.padding, self.dilation, self.out_lanes)
+        return ops.conv2d(ops.as_cl(x), w, self.bias, self.stride, self.padding, self.dilation, self.out_lanes,
+                          want_bn_stats=self.feeds_bn and self.training)
 
     def extra_repr(self):
         return '{in_channels}, {out_channels}, kernel_size={kernel_size}, stride={stride}, padding={padding}, ' \

@@ -362,7 +362,7 @@ def _tc_launch(geom, taps, ext, x_parts, w_parts, bias, out):
          _p(x_parts[0]), _p(x_parts[1]), _p(w_parts[0]), _p(w_parts[1]), _p(bias), _p(out), _stream())
 
 
-def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, out=None, precision=None):
+def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, out=None, precision=None, bn_stats=None):
     """Launch the NHWC tap-table convolution on raw buffers.  w_packed: [Cout][ntaps][Cin] contiguous.
     precision 0: FFMA kernel; 1: tcgen05 single-pass TF32; 2: tcgen05 3xTF32 (operands split on the
     fly).  Shapes the tensor-core kernel does not cover (Cin % 32 != 0, other strides) use the FFMA kernel."""
@@ -375,13 +375,19 @@ def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div,
             out.zero_()
     if prec != 0 and tc_supported(Cin, mul, div):
         if prec == 2:
-            x_parts = x if isinstance(x, tuple) else split_cached(x)
+            # activations go in raw: the kernel splits them hi/lo in shared memory; the (small, per-step
+            # cached) weights are split here
+            x_parts = x if isinstance(x, tuple) else (x, None)
             w_parts = w_packed if isinstance(w_packed, tuple) else split_cached(w_packed)
         else:
             x_parts, w_parts = (x, None), (w_packed, None)
         if div == 1:
             geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, 1, ntaps, prec)
-            _tc_launch(geom, taps, None, x_parts, w_parts, bias, out)
+            ext = None
+            if bn_stats is not None:      # the epilogue also accumulates sum(y), sum(y^2) per channel
+                ext = ConvTcExt(0, None, 0, 0, 0, 0, 0, ctypes.c_void_p(bn_stats.data_ptr()))
+                bn_stats._pxl_filled = True
+            _tc_launch(geom, taps, ext, x_parts, w_parts, bias, out)
             return out
         # dgrad of a stride-2 convolution: output pixel (iy, ix) only receives the taps with
         # (iy + dy) and (ix + dx) even; per output parity class that is a stride-1 problem over dY
@@ -402,7 +408,7 @@ def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div,
             if not widx or ohs <= 0 or ows <= 0:
                 continue
             geom = ConvGeom(N, H, W, Cin, ohs, ows, Cout, ldo, 1, 1, len(widx), prec)
-            ext = ConvTcExt(ntaps, (ctypes.c_int * len(widx))(*widx), 2, py, px, OH, OW)
+            ext = ConvTcExt(ntaps, (ctypes.c_int * len(widx))(*widx), 2, py, px, OH, OW, None)
             _tc_launch(geom, sub, ext, x_parts, w_parts, bias, out)
         return out
     if isinstance(x, tuple):
@@ -426,8 +432,11 @@ def conv_wgrad_raw(x, dy, dw, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, p
     if prec != 0 and div == 1 and mul in _WGRAD_TC_STRIDES and Cin % 32 == 0 and ldo % 32 == 0:
         geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
         if prec == 2:
-            x_hi, x_lo = x if isinstance(x, tuple) else split_cached(x)
-            d_hi, d_lo = dy if isinstance(dy, tuple) else split_cached(dy)
+            if isinstance(x, tuple) != isinstance(dy, tuple):        # mixed: split the raw one too
+                x = x if isinstance(x, tuple) else split_tf32(x)
+                dy = dy if isinstance(dy, tuple) else split_tf32(dy)
+            x_hi, x_lo = x if isinstance(x, tuple) else (x, None)     # raw operands: split inside the kernel
+            d_hi, d_lo = dy if isinstance(dy, tuple) else (dy, None)
             call('pxl_conv_wgrad_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x_hi), _p(x_lo), _p(d_hi), _p(d_lo),
                  _p(dw), _stream())
         else:
@@ -453,7 +462,7 @@ class _Conv2d(torch.autograd.Function):
     """nn.Conv2d on NHWC (resnet.py:18-25 etc.).  weight logical [Cout,Cin,kh,kw] channels_last."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, dilation, out_lanes=0):
+    def forward(ctx, x, weight, bias, stride, padding, dilation, out_lanes=0, bn_stats=None):
         _chk(x, 'x', cl=True); _chk(weight, 'weight', cl=True)
         N, Cin, H, W = x.shape
         Cout, Cin2, kh, kw = weight.shape
@@ -465,15 +474,9 @@ class _Conv2d(torch.autograd.Function):
         OH = (H + 2 * padding - dilation * (kh - 1) - 1) // stride + 1
         OW = (W + 2 * padding - dilation * (kw - 1) - 1) // stride + 1
         taps = _taps(kh, kw, dilation, padding)
-        split = _conv_precision == 2 and tc_supported(Cin, stride, 1)
-        xin = split_cached(x) if split else x
-        win = split_cached(weight) if split else weight
-        out = conv_raw(xin, win, bias, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1)
-        if split:     # keep the split operand for wgrad instead of x (x = hi + lo exactly)
-            ctx.save_for_backward(xin[0], xin[1], weight)
-        else:
-            ctx.save_for_backward(x, weight)
-        ctx.split = split
+        out = conv_raw(x, weight, bias, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1, bn_stats=bn_stats)
+        ctx.save_for_backward(x, weight)
+        ctx.split = False
         ctx.meta = (taps, N, H, W, Cin, OH, OW, Cout, stride, kh * kw, bias is not None)
         return out
 
@@ -511,7 +514,7 @@ class _Conv2d(torch.autograd.Function):
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(Cout, dtype=torch.float32, device=dy.device)
             call('pxl_bias_grad', _p(dy), N * OH * OW, Cout, ldo, _p(db), 0, _stream())
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
     @staticmethod
     def backward(ctx, dy):
@@ -526,10 +529,8 @@ class _Conv2d(torch.autograd.Function):
         dy = as_cl(dy)
         dx = dw = db = None
         dyin = dy
-        if _conv_precision == 2 and Cout % 32 == 0:
-            dyin = split_cached(dy)       # shared by dgrad and wgrad
         if ctx.needs_input_grad[0]:
-            if isinstance(dyin, tuple) and tc_supported(Cout, 1, stride):
+            if _conv_precision == 2 and tc_supported(Cout, 1, stride):
                 w_hi, w_lo = split_cached(weight)
                 wt = (transpose_weights(w_hi, Cout, T, Cin), transpose_weights(w_lo, Cout, T, Cin))
             else:
@@ -544,12 +545,21 @@ class _Conv2d(torch.autograd.Function):
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(Cout, dtype=torch.float32, device=dy.device)
             call('pxl_bias_grad', _p(dy), N * OH * OW, Cout, Cout, _p(db), 0, _stream())
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, out_lanes=0):
-    """out_lanes > Cout: the output tensor gets that many channel lanes (the extra ones zero)."""
-    return _Conv2d.apply(x, weight, bias, int(stride), int(padding), int(dilation), int(out_lanes))
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, out_lanes=0, want_bn_stats=False):
+    """out_lanes > Cout: the output tensor gets that many channel lanes (the extra ones zero).
+    want_bn_stats: when the tensor-core kernel runs, its epilogue also accumulates the per-channel
+    sum / sum of squares of the output; they are attached to the result as ``._pxl_bn_sums`` (fp64 [2*Cout])
+    and picked up by bn_act, which then skips its own statistics pass."""
+    sums = None
+    if want_bn_stats and _conv_precision != 0 and not out_lanes:
+        sums = torch.zeros(2 * weight.shape[0], dtype=torch.float64, device=x.device)
+    out = _Conv2d.apply(x, weight, bias, int(stride), int(padding), int(dilation), int(out_lanes), sums)
+    if sums is not None and getattr(sums, '_pxl_filled', False):
+        out._pxl_bn_sums = sums
+    return out
 
 
 class _Aspp(torch.autograd.Function):
@@ -643,7 +653,7 @@ class _BnAct(torch.autograd.Function):
     ranks share batch statistics (the reference's cross-replica SyncBN); None = local."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps, relu, group, clamp_var):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps, relu, group, clamp_var, sums=None):
         _chk(x, 'x', cl=True)
         N, C, H, W = x.shape
         rows = N * H * W
@@ -653,8 +663,9 @@ class _BnAct(torch.autograd.Function):
         count = float(rows)
         clamp = 1 if clamp_var else 0
         if training:
-            sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
-            call('pxl_bn_stats', _p(x), rows, C, _p(sums), _stream())
+            if sums is None:
+                sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+                call('pxl_bn_stats', _p(x), rows, C, _p(sums), _stream())
             if group is not None:
                 import torch.distributed as dist
                 dist.all_reduce(sums, group=group)
@@ -693,15 +704,16 @@ class _BnAct(torch.autograd.Function):
         dres = torch.empty_like(x) if has_res else None
         call('pxl_bn_bwd_dx', _p(x), _p(y), _p(dy), _p(coeff[0]), _p(coeff[1]), _p(gamma), _p(dsums), count, int(relu),
              _p(dx), _p(dres), rows, C, _stream())
-        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None, None
 
 
 def bn_act(x, gamma, beta, running_mean, running_var, training=True, momentum=0.1, eps=1e-5, relu=False,
            residual=None, group=None, clamp_var=False):
     """clamp_var: use the reference's multi-replica formula inv_std = clamp(var, eps)^-1/2
     (batchnorm.py:125) instead of (var + eps)^-1/2; implied when ``group`` spans several ranks."""
+    sums = getattr(x, '_pxl_bn_sums', None) if training else None      # produced by the conv epilogue
     return _BnAct.apply(x, gamma, beta, running_mean, running_var, residual, bool(training), float(momentum),
-                        float(eps), bool(relu), group, bool(clamp_var))
+                        float(eps), bool(relu), group, bool(clamp_var), sums)
 
 
 class _MaxPool(torch.autograd.Function):

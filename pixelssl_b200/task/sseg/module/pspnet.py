@@ -15,6 +15,7 @@ class _Stage(nn.Sequential):
     def __init__(self, in_channels, out_channels, bin_sz):
         super().__init__(nn.Identity(), Conv2d(in_channels, out_channels, 1, bias=False), BatchNorm2d(out_channels), nn.Identity())
         self.bin_sz = bin_sz
+        self[1].feeds_bn = True
 
     def forward(self, x):
         return self[2](self[1](ops.adaptive_avg_pool(x, self.bin_sz)), relu=True)
@@ -23,6 +24,7 @@ class _Stage(nn.Sequential):
 class _Bottleneck(nn.Sequential):
     def __init__(self, in_channels, out_channels):
         super().__init__(Conv2d(in_channels, out_channels, 3, padding=1, bias=False), BatchNorm2d(out_channels), nn.Identity())
+        self[0].feeds_bn = True
 
     def forward(self, x):
         return self[1](self[0](x), relu=True)

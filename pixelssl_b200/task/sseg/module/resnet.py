@@ -25,6 +25,8 @@ class Bottleneck(nn.Module):
         self.bn3 = BatchNorm2d(planes * 4)
         self.downsample = downsample
         self.stride, self.dilation = stride, dilation
+        for conv in (self.conv1, self.conv2, self.conv3) + ((downsample[0],) if downsample is not None else ()):
+            conv.feeds_bn = True          # the tensor-core epilogue then produces the BN statistics
 
     def forward(self, x):
         out = self.bn1(self.conv1(x), relu=True)

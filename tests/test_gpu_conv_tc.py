@@ -131,3 +131,27 @@ def test_tf32_operand_rounding_probe(ops):
     v = float(y[0, 0, 0, 0])
     print('tf32 probe: 1 + 2^-11 + 2^-12 ->', v, '(truncation gives 1.0, round-to-nearest gives 1 + 2^-10)')
     assert v in (1.0, 1.0 + 2.0 ** -10, 1.0 + 2.0 ** -11 + 2.0 ** -12)
+
+
+@pytest.mark.parametrize('precision', [1, 2])
+@pytest.mark.parametrize('shape', [(2, 64, 33, 33, 256, 1), (2, 128, 17, 19, 64, 3), (1, 64, 129, 129, 64, 3)])
+def test_bn_statistics_fused_in_epilogue(ops, shape, precision):
+    """The conv epilogue's per-channel sum / sum-of-squares equal those of the tensor it stored."""
+    N, Cin, H, W, Cout, k = shape
+    g = torch.Generator().manual_seed(Cout + H)
+    x = torch.randn(N, Cin, H, W, generator=g).cuda().contiguous(memory_format=CL)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda().contiguous(memory_format=CL)
+    ops._conv_precision = precision
+    y = ops.conv2d(x, w, None, 1, k // 2, 1, want_bn_stats=True)
+    ops._conv_precision = 0
+    sums = getattr(y, '_pxl_bn_sums', None)
+    assert sums is not None and ops.conv_tc_status() == 0
+    yd = y.double()
+    ref = torch.cat((yd.sum(dim=(0, 2, 3)), (yd * yd).sum(dim=(0, 2, 3))))
+    assert rel(sums, ref) <= 1e-5
+    # and bn_act consumes them: identical output with and without the fused statistics
+    gm, bt = torch.ones(Cout).cuda(), torch.zeros(Cout).cuda()
+    a = ops.bn_act(y, gm, bt, torch.zeros(Cout).cuda(), torch.ones(Cout).cuda(), training=True, relu=True)
+    y2 = y.clone(memory_format=torch.preserve_format)
+    b = ops.bn_act(y2, gm, bt, torch.zeros(Cout).cuda(), torch.ones(Cout).cuda(), training=True, relu=True)
+    assert rel(a, b) <= 1e-5
