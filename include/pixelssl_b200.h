@@ -285,6 +285,17 @@ int pxl_bilinear_nhwc(const float* in, float* out, int N, int h, int w, int C, i
                       int align_corners, int backward, void* stream);
 int pxl_copy_lanes_nhwc(const float* src, float* dst, int64_t rows, int C, int ld, int coff, int extract, void* stream);
 
+/* Validation confusion matrix: cmat[gt*C + argmax_c pred] += 1 over pixels with 0 <= gt < C (planar pred
+ * [n,C,HW], float labels [n,HW], int64 cmat[C*C] accumulated in place; C <= 64).
+ * SemanticSegmentationFunc.metrics, task/sseg/func.py:36-48 (np.argmax / np.bincount) */
+int pxl_confusion_matrix(const float* pred, const float* gt, int n, int C, int64_t HW, int64_t* cmat,
+                         void* stream);
+/* Mean-Teacher input noise, in place on inp [n,CHW]: per-sample min/max normalise, add noise, clip to
+ * [0,1], de-normalise.  GaussianNoiseLayer.forward, pixelssl/nn/module/gaussian_noise.py:18-41
+ * (the caller draws the N(0, uniform(0,std)) noise tensor). */
+int64_t pxl_gaussian_noise_workspace_bytes(int n);
+int pxl_gaussian_noise(float* inp, const float* noise, int n, int64_t CHW, float* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

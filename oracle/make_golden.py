@@ -401,6 +401,51 @@ def golden_pspnet(pixelssl, size=97, batch=2):
     print('pspnet golden: logits', tuple(logits.shape), float(logits.abs().max()))
 
 
+def golden_val(pixelssl, sseg_proxy):
+    """Validation metrics (task/sseg/func.py:36-80), the MT input-noise layer
+    (pixelssl/nn/module/gaussian_noise.py) and the two-stream sampler (pixelssl/nn/data.py:126-177)."""
+    import func as sseg_func
+    from pixelssl.utils import logger as ref_logger
+    from pixelssl.nn.module import GaussianNoiseLayer
+    from pixelssl.nn import data as ref_data
+    out = {}
+    # ---- metrics over two batches -----------------------------------------------------------
+    args = make_args(pixelssl, sseg_proxy, 'ssl_null', {}, 2, 0)
+    tf = sseg_func.task_func()(args)
+    meters = ref_logger.AvgMeterSet()
+    g = torch.Generator().manual_seed(11)
+    for k, (n, h, w) in enumerate([(3, 40, 37), (2, 33, 65)]):
+        pred = torch.softmax(3.0 * torch.randn(n, args.num_classes, h, w, generator=g), dim=1)
+        pred[0, :, 0, 0] = 0.25                       # an exact tie: argmax must pick the first index
+        gt = torch.randint(0, args.num_classes, (n, 1, h, w), generator=g).float()
+        gt[torch.rand(n, 1, h, w, generator=g) < 0.1] = 255.0
+        gt[0, 0, 1, :3] = -1.0
+        if k == 1:
+            gt[gt == 7.0] = 3.0                       # a class absent from gt -> nanmean path
+        tf.metrics((pred,), (gt,), None, meters, id_str='task')
+        out['metrics_pred%d' % k], out['metrics_gt%d' % k] = pred.numpy(), gt.numpy()
+        out['metrics_cmat_sum%d' % k] = np.array(meters['task_confusion_matrix'].sum)
+        out['metrics_values%d' % k] = np.array([float(meters['task_metric_' + m].val)
+                                                for m in ('acc', 'acc-class', 'mIoU', 'fwIoU')])
+    # ---- gaussian noise layer ----------------------------------------------------------------
+    torch.manual_seed(5)
+    random.seed(5)
+    layer = GaussianNoiseLayer(0.15)
+    inp = torch.randn(3, 3, 29, 31) * torch.tensor([1.0, 5.0, 0.01]).view(3, 1, 1, 1) + 0.3
+    res = layer.forward(inp.clone())
+    out['gn_inp'], out['gn_noise'], out['gn_out'] = inp.numpy(), layer.noise.numpy().copy(), res.numpy()
+    # ---- two-stream sampler: 3 epochs per configuration ---------------------------------------
+    cfgs = np.array([[10, 37, 2, 3], [50, 13, 4, 2], [8, 8, 2, 2], [7, 29, 3, 5], [40, 90, 4, 6]])
+    out['sampler_cfgs'] = cfgs
+    for c, (nl, nu, lb, ub) in enumerate(cfgs):
+        np.random.seed(100 + c)
+        smp = ref_data.TwoStreamBatchSampler(list(range(nl)), list(range(1000, 1000 + nu)), int(lb), int(ub))
+        for e in range(3):
+            out['sampler_%d_epoch%d' % (c, e)] = np.array([list(map(int, b)) for b in smp], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, 'val.npz'), **out)
+    print('val.npz written:', {k: v.shape for k, v in out.items() if not k.startswith('sampler_')})
+
+
 def golden_fp64():
     """Exact-arithmetic (fp64) evaluation of the SAME steps with the oracle, to measure the
     reference's own fp32 rounding noise on these (ill-conditioned, random-init) networks.  The GPU
@@ -457,7 +502,7 @@ if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     pixelssl, sseg_proxy = patch_and_import()
-    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 'gct', 'cct', 'pspnet', 'fp64']
+    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 'gct', 'cct', 'pspnet', 'val', 'fp64']
     if which == ['fp64']:
         golden_fp64()
         sys.exit(0)
@@ -477,5 +522,7 @@ if __name__ == '__main__':
         golden_cct(pixelssl, sseg_proxy)
     if 'pspnet' in which:
         golden_pspnet(pixelssl)
+    if 'val' in which:
+        golden_val(pixelssl, sseg_proxy)
     if 'fp64' in which:
         golden_fp64()

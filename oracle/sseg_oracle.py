@@ -587,3 +587,46 @@ def pspnet_forward(img, state, training=True, output_stride=16, blocks=R50_BLOCK
     for j in (1, 2, 3):
         x = F.pixel_shuffle(F.relu(F.conv2d(x, state['decoder.%d.conv.weight' % j], state['decoder.%d.conv.bias' % j])), 2)
     return F.interpolate(x, size=img.shape[2:], mode='bilinear', align_corners=True), px
+
+
+# ----------------------------------------------------------------------------------------------
+# validation metrics and the MT input-noise layer
+# ----------------------------------------------------------------------------------------------
+def confusion_matrix(pred, gt, num_classes):
+    """SemanticSegmentationFunc.metrics, task/sseg/func.py:39-47: argmax over channels, pixels with
+    0 <= gt < C, bincount of C*gt + pred.  Rows = ground truth."""
+    pred = np.asarray(pred)
+    gt = np.asarray(gt)
+    arg = np.expand_dims(np.argmax(pred, axis=1), axis=1)
+    mask = (gt >= 0) & (gt < num_classes)
+    label = num_classes * gt[mask].astype('int') + arg[mask]
+    return np.bincount(label, minlength=num_classes ** 2).reshape(num_classes, num_classes)
+
+
+def seg_metrics(cmat_sum):
+    """acc, acc-class, mIoU, fwIoU of the accumulated confusion matrix, task/sseg/func.py:64-80."""
+    cmat_sum = np.asarray(cmat_sum)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        acc = np.diag(cmat_sum).sum() / cmat_sum.sum()
+        acc_class = np.nanmean(np.diag(cmat_sum) / cmat_sum.sum(axis=1))
+        iou = np.diag(cmat_sum) / (np.sum(cmat_sum, axis=1) + np.sum(cmat_sum, axis=0) - np.diag(cmat_sum))
+        miou = np.nanmean(iou)
+        freq = np.sum(cmat_sum, axis=1) / np.sum(cmat_sum)
+        fwiou = (freq[freq > 0] * iou[freq > 0]).sum()
+    return np.array([acc, acc_class, miou, fwiou])
+
+
+def gaussian_noise_layer(inp, noise):
+    """GaussianNoiseLayer.forward, pixelssl/nn/module/gaussian_noise.py:18-41, for a given noise tensor
+    (the layer draws it as N(0, uniform(0, std))).  Out of place."""
+    x = inp.clone()
+    imax = x.amax(dim=(1, 2, 3), keepdim=True)
+    imin = x.amin(dim=(1, 2, 3), keepdim=True)
+    rng = imax - imin + 1e-9
+    x = (x - imin) / rng
+    x = x + noise
+    upper = (x > 1.0).float()
+    lower = (x < 0.0).float()
+    x = x * (1 - upper) + upper
+    x = x * (1 - lower)
+    return x * rng + imin

@@ -82,6 +82,9 @@ SIGNATURES = {
     'pxl_adaptive_avgpool_nhwc': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'pxl_bilinear_nhwc': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'pxl_copy_lanes_nhwc': (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P]),
+    'pxl_confusion_matrix': (c_int, [P, P, c_int, c_int, c_int64, P, P]),
+    'pxl_gaussian_noise_workspace_bytes': (c_int64, [c_int]),
+    'pxl_gaussian_noise': (c_int, [P, P, c_int, c_int64, P, P]),
     'pxl_sgd_ema': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, P]),
     'pxl_ema': (c_int, [P, P, c_int64, c_float, P]),
 }

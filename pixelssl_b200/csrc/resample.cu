@@ -83,36 +83,104 @@ __device__ __forceinline__ void y_support(int i, int h, int H, float sh, bool ac
     if (yhi > H - 1) yhi = H - 1;
 }
 
+// v3: no contended atomics, no per-element weight arithmetic.
+//   * per CTA (low-res row i, channel c, image b): the horizontal weights wx(x, j) depend only on the
+//     column pair, so they are tabulated once in shared memory (wtab[j][t], t over the <= SUP high-res
+//     columns under low-res column j);
+//   * the ~2/sh contributing high-res rows are staged G at a time by the whole CTA (coalesced loads,
+//     G*W/128 independent loads per thread), stored at x + x/R so that lanes walking supports that
+//     start R apart hit distinct banks;
+//   * work item = (staged row g, column j): a SUP-long dot product from shared memory, one shared
+//     atomicAdd per item.
 template <bool NHWC>
 __global__ void __launch_bounds__(128)
 bilinear_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int C, int h, int w, int H, int W,
-                    float sh, float sw, bool ac, int ldc) {
-    extern __shared__ float acc[];   // [w]
+                    float sh, float sw, bool ac, int ldc, int R, int rowbuf, int SUP, int G) {
+    extern __shared__ float smem[];
+    const int wpad = (w + 31) & ~31;
+    float* acc = smem;                                   // [wpad]
+    int4* meta = reinterpret_cast<int4*>(smem + wpad);   // [wpad] {xlo, count, padded start, xlo % R}
+    float* wtab = smem + wpad + 4 * wpad;                // [w][SUP]
+    float* rb = wtab + (((size_t)w * SUP + 3) & ~(size_t)3);   // [G][rowbuf]
     const int i = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
-    for (int j = threadIdx.x; j < w; j += blockDim.x) acc[j] = 0.f;
-    __syncthreads();
-    int ylo, yhi;
-    y_support(i, h, H, sh, ac, ylo, yhi);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const float* gp = gout + ((int64_t)b * C + c) * (int64_t)H * W;
-    for (int y = ylo + warp; y <= yhi; y += nwarps) {
-        const float fy = src_index(sh, y, ac);
-        const int y0 = (int)fy;
-        const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
-        const float ly1 = fy - (float)y0;
-        float wy = 0.f;
-        if (y0 == i) wy += 1.f - ly1;
-        if (y1 == i) wy += ly1;
-        if (wy == 0.f && y0 != i && y1 != i) continue;
-        const float* row = gp + (int64_t)y * W;
-        for (int x = lane; x < W; x += 32) {
-            const float g = __ldg(row + x) * wy;
+
+    for (int j = threadIdx.x; j < w; j += blockDim.x) {
+        acc[j] = 0.f;
+        int xlo, xhi;
+        if (sw <= 0.f) { xlo = 0; xhi = W - 1; }
+        else {
+            float lo, hi;
+            if (ac) { lo = ((float)j - 1.f) / sw; hi = ((float)j + 1.f) / sw; }
+            else { lo = ((float)j - 0.5f) / sw - 0.5f; hi = ((float)j + 1.5f) / sw - 0.5f; }
+            xlo = (int)floorf(lo) - 1; xhi = (int)ceilf(hi) + 1;
+            if (j == 0 || xlo < 0) xlo = 0;
+            if (xhi > W - 1) xhi = W - 1;
+        }
+        // trim to the columns that really touch j and tabulate their weights
+        int first = -1, last = -2;
+        for (int x = xlo; x <= xhi; ++x) {
+            const float fx = src_index(sw, x, ac);
+            const int x0 = (int)fx;
+            const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+            if (x0 == j || x1 == j) { if (first < 0) first = x; last = x; }
+        }
+        int cnt = last - first + 1;
+        if (first < 0) { first = 0; cnt = 0; }
+        if (cnt > SUP) cnt = SUP;                         // cannot happen (SUP is a host-side bound)
+        for (int t = 0; t < cnt; ++t) {
+            const int x = first + t;
             const float fx = src_index(sw, x, ac);
             const int x0 = (int)fx;
             const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
             const float lx1 = fx - (float)x0;
-            atomicAdd(acc + x0, g * (1.f - lx1));
-            atomicAdd(acc + x1, g * lx1);
+            float wx = 0.f;
+            if (x0 == j) wx += 1.f - lx1;
+            if (x1 == j) wx += lx1;
+            wtab[j * SUP + t] = wx;
+        }
+        meta[j] = make_int4(first, cnt, first + first / R, first % R);
+    }
+    int ylo, yhi;
+    y_support(i, h, H, sh, ac, ylo, yhi);
+    const float* gp = gout + ((int64_t)b * C + c) * (int64_t)H * W;
+    for (int y0g = ylo; y0g <= yhi; y0g += G) {
+        const int rows = min(G, yhi - y0g + 1);
+        __syncthreads();                                  // previous group consumed / tables ready
+        {   // x / R advanced incrementally (x grows by blockDim.x per trip): no integer division in the loop
+            const int dq = (int)blockDim.x / R, dr = (int)blockDim.x - dq * R;
+            int q = (int)threadIdx.x / R, r = (int)threadIdx.x - q * R;
+            for (int x = threadIdx.x; x < W; x += blockDim.x) {
+                const float* src = gp + (int64_t)y0g * W + x;
+                float* dst = rb + x + q;
+#pragma unroll 4
+                for (int g = 0; g < rows; ++g) dst[g * rowbuf] = __ldg(src + (int64_t)g * W);
+                q += dq; r += dr;
+                if (r >= R) { r -= R; ++q; }
+            }
+        }
+        __syncthreads();
+        for (int item = threadIdx.x; item < rows * w; item += blockDim.x) {
+            const int g = item / w, j = item - g * w;
+            const int y = y0g + g;
+            const float fy = src_index(sh, y, ac);
+            const int yy0 = (int)fy;
+            const int yy1 = yy0 + (yy0 < h - 1 ? 1 : 0);
+            const float ly1 = fy - (float)yy0;
+            float wy = 0.f;
+            if (yy0 == i) wy += 1.f - ly1;
+            if (yy1 == i) wy += ly1;
+            if (wy == 0.f) continue;
+            const int4 m = meta[j];
+            const float* wt = wtab + j * SUP;
+            const float* rp = rb + g * rowbuf;
+            int pidx = m.z, rem = m.w;
+            float sacc = 0.f;
+            for (int t = 0; t < m.y; ++t) {
+                sacc = fmaf(rp[pidx], wt[t], sacc);
+                ++pidx;
+                if (++rem == R) { rem = 0; ++pidx; }
+            }
+            atomicAdd(acc + j, sacc * wy);
         }
     }
     __syncthreads();
@@ -125,13 +193,26 @@ bilinear_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int
 extern "C" int pxl_bilinear_bwd(const float* grad_out, float* grad_in, int n, int C, int h, int w, int H, int W,
                                 int align_corners, int in_nhwc, int ldc, void* stream) {
     if (!grad_out || !grad_in || n <= 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return PXL_ERR_BAD_ARG;
-    if (C > 65535 || n > 65535 || (size_t)w * sizeof(float) > 48 * 1024) return PXL_ERR_UNSUPPORTED;
+    if (C > 65535 || n > 65535) return PXL_ERR_UNSUPPORTED;
     const float sh = resize_scale(h, H, align_corners), sw = resize_scale(w, W, align_corners);
     dim3 grid((unsigned)h, (unsigned)C, (unsigned)n);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)w * sizeof(float);
-    if (in_nhwc) bilinear_bwd_kernel<true><<<grid, 128, smem, st>>>(grad_out, grad_in, C, h, w, H, W, sh, sw, align_corners != 0, ldc);
-    else bilinear_bwd_kernel<false><<<grid, 128, smem, st>>>(grad_out, grad_in, C, h, w, H, W, sh, sw, align_corners != 0, C);
+    int R = sw > 0.f ? (int)(1.f / sw + 0.5f) : W;
+    if (R < 1) R = 1;
+    // high-res columns under one low-res column: < 2/sw + 2; odd so that wtab rows start in distinct banks
+    int SUP = sw > 0.f ? (int)ceilf(2.f / sw) + 3 : W;
+    if (SUP > W) SUP = W;
+    SUP |= 1;
+    const int rowbuf = ((W + W / R + 1) + 31) & ~31;
+    const int wpad = (w + 31) & ~31;
+    const size_t fixed = (size_t)wpad * 5 + (((size_t)w * SUP + 3) & ~(size_t)3);
+    const size_t budget = 48 * 1024 / sizeof(float);
+    if (fixed + (size_t)rowbuf > budget) return PXL_ERR_UNSUPPORTED;
+    int G = (int)((budget - fixed) / rowbuf);
+    if (G > 8) G = 8;
+    const size_t smem = (fixed + (size_t)G * rowbuf) * sizeof(float);
+    if (in_nhwc) bilinear_bwd_kernel<true><<<grid, 128, smem, st>>>(grad_out, grad_in, C, h, w, H, W, sh, sw, align_corners != 0, ldc, R, rowbuf, SUP, G);
+    else bilinear_bwd_kernel<false><<<grid, 128, smem, st>>>(grad_out, grad_in, C, h, w, H, W, sh, sw, align_corners != 0, C, R, rowbuf, SUP, G);
     PXL_CHECK_LAUNCH();
     return 0;
 }

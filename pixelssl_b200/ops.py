@@ -1258,3 +1258,45 @@ class _PyramidConcat(torch.autograd.Function):
 
 def pyramid_concat(features, branches):
     return _PyramidConcat.apply(as_cl(features), *[as_cl(b) for b in branches])
+
+
+def confusion_matrix_(cmat, pred, gt, num_classes=None):
+    """cmat[gt*C + argmax(pred,1)] += 1 over pixels with 0 <= gt < C, accumulated in place into the int64
+    device tensor ``cmat`` [C,C] (task/sseg/func.py:36-48: np.argmax + np.bincount)."""
+    _chk(pred, 'pred')
+    _chk(gt, 'gt')
+    n, c, h, w = pred.shape
+    if num_classes is not None and num_classes != c:
+        raise ValueError('pred has %d channels, num_classes = %d' % (c, num_classes))
+    if gt.numel() != n * h * w:
+        raise ValueError('gt must hold one label per pixel')
+    if cmat.dtype != torch.int64 or not cmat.is_cuda or cmat.numel() != c * c or not cmat.is_contiguous():
+        raise TypeError('cmat must be a contiguous CUDA int64 tensor with C*C entries')
+    call('pxl_confusion_matrix', _p(pred), _p(gt), n, c, h * w, ctypes.c_void_p(cmat.data_ptr()), _stream())
+    return cmat
+
+
+_GN_WS = {}
+
+
+def gaussian_noise_(inp, std, noise=None):
+    """GaussianNoiseLayer.forward (pixelssl/nn/module/gaussian_noise.py:18-41) in place on ``inp``
+    [n,C,H,W]: noise ~ N(0, uniform(0, std)) drawn by torch's device generator unless given."""
+    if std is None:
+        return inp
+    _chk(inp, 'inp')
+    n = inp.shape[0]
+    if noise is None:
+        import random
+        noise = torch.empty_like(inp).normal_(0, std=random.uniform(0, std))
+    else:
+        _chk(noise, 'noise')
+        if noise.shape != inp.shape:
+            raise ValueError('noise shape mismatch')
+    key = (inp.device.index, n)
+    ws = _GN_WS.get(key)
+    if ws is None:
+        nbytes = _lib.load().pxl_gaussian_noise_workspace_bytes(n)
+        ws = _GN_WS[key] = torch.empty(nbytes // 4, dtype=torch.float32, device=inp.device)
+    call('pxl_gaussian_noise', _p(inp), _p(noise), n, inp.numel() // n, _p(ws), _stream())
+    return inp

@@ -35,6 +35,34 @@ class _SSLBase:
     def load_checkpoint(self):
         return self._load_checkpoint()
 
+    def _metrics(self, resulter, gt, inp, id_str):
+        """``self.task_func.metrics(activated_pred, gt, inp, self.meters, id_str=...)`` of every
+        reference ``_validate`` (e.g. ssl_mt.py:264-265, ssl_null.py:169)."""
+        if self.task_func is None or not hasattr(self.task_func, 'metrics'):
+            return
+        activated_pred = resulter.get('activated_pred') if resulter is not None else None
+        if activated_pred is None:
+            self._pred_err()
+        self.task_func.metrics(activated_pred, gt, inp, self.meters, id_str=id_str)
+
+    def _log_validation_metrics(self, id_strs):
+        """The 'Validation metrics' epilogue of every reference ``_validate`` (ssl_mt.py:285-294)."""
+        if self.task_func is None or not hasattr(self.task_func, 'METRIC_STR'):
+            return
+        info = {i: '' for i in id_strs}
+        for key in sorted(list(self.meters.keys())):
+            if self.task_func.METRIC_STR in key:
+                for id_str in info:
+                    if key.startswith(id_str):
+                        info[id_str] += '{0}: {1:.6}\t'.format(key, self.meters[key])
+        logger.log_info('Validation metrics:\n' + ''.join(
+            '  {0}-metrics\t=>\t{1}\n'.format(i, info[i].replace('_', '-')) for i in id_strs))
+
+    def _pred_err(self):
+        logger.log_err('In SSL_{0}, the \'resulter\' dict returned by the task model should contain the following keys:\n'
+                       '   (1) \'pred\'\t=>\tunactivated task predictions\n'
+                       '   (2) \'activated_pred\'\t=>\tactivated task predictions\n'.format(self.NAME.upper()))
+
     def _build(self, model_funcs, optimizer_funcs, lrer_funcs, criterion_funcs, task_func):
         raise NotImplementedError
 

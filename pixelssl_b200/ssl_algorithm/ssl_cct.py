@@ -334,6 +334,8 @@ class SSLCCT(ssl_base._SSLBase):
             inp, gt = ssl_base.to_device(inp), ssl_base.to_device(gt)
             resulter, _ = self.model.forward(inp, gt, False)
             self.meters.update('task_loss', tool.dict_value(resulter, 'task_loss', err=True).mean().data)
+            self._metrics(resulter, gt, inp, 'task')
+        self._log_validation_metrics(('task',))
 
     def _save_checkpoint(self, epoch):
         state = {'algorithm': self.NAME, 'epoch': epoch, 'model': self.model.state_dict(),

@@ -181,10 +181,12 @@ class SSLCUTMIX(ssl_base._SSLBase):
         self.t_model.eval()
         for idx, (inp, gt) in enumerate(data_loader):
             inp, gt = ssl_base.to_device(inp), ssl_base.to_device(gt)
-            for key, model in (('s', self.s_model), ('t', self.t_model)):
+            for key, model, id_str in (('s', self.s_model, 'student'), ('t', self.t_model, 'teacher')):
                 resulter, _ = model.forward(inp)
                 pred = tool.dict_value(resulter, 'pred')
                 self.meters.update(key + '_task_loss', torch.mean(self.s_criterion.forward(pred, gt, inp)).data)
+                self._metrics(resulter, gt, inp, id_str)
+        self._log_validation_metrics(('student', 'teacher'))
 
     def _save_checkpoint(self, epoch):
         state = {'algorithm': self.NAME, 'epoch': epoch,

@@ -263,8 +263,11 @@ class SSLGCT(ssl_base._SSLBase):
         for idx, (inp, gt) in enumerate(data_loader):
             inp, gt = ssl_base.to_device(inp), ssl_base.to_device(gt)
             for mid, model, crit in (('l', self.l_model, self.l_criterion), ('r', self.r_model, self.r_criterion)):
-                pred = tool.dict_value(model.forward(inp)[0], 'pred')
+                resulter = model.forward(inp)[0]
+                pred = tool.dict_value(resulter, 'pred')
                 self.meters.update('{0}_task_loss'.format(mid), torch.mean(crit.forward(pred, gt, inp)).data)
+                self._metrics(resulter, gt, inp, mid)
+        self._log_validation_metrics(('l', 'r'))
 
     def _save_checkpoint(self, epoch):
         state = {'algorithm': self.NAME, 'epoch': epoch,

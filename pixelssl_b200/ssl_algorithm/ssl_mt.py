@@ -53,9 +53,6 @@ class SSLMT(ssl_base._SSLBase):
             if self.args.cons_rampup_epochs < 0:
                 logger.log_err('The argument - cons_rampup_epochs - is not set (or invalid)\n'
                                'Please set - cons_rampup_epochs >= 0 - for training\n')
-        if getattr(self.args, 'gaussian_noise_std', None) is not None:
-            logger.log_err('gaussian_noise_std: the input-noise kernel (gaussian_noise.py:17-40) is not part '
-                           'of this build yet; the shipped sseg scripts leave it disabled\n')
 
     def _build(self, model_funcs, optimizer_funcs, lrer_funcs, criterion_funcs, task_func):
         self.task_func = task_func
@@ -76,8 +73,7 @@ class SSLMT(ssl_base._SSLBase):
         """One iteration of the loop body of ssl_mt.py:131-220 on host tensors ``inp``/``gt``
         (tuples).  Returns nothing; results land in ``self.meters`` as device tensors."""
         lbs = self.args.labeled_batch_size
-        s_inp = t_inp = ssl_base.to_device(inp)
-        gt = ssl_base.to_device(gt)
+        s_inp, t_inp, gt = self._batch_prehandle(inp, gt, True)
         cons_rampup_scale = func.sigmoid_rampup(cur_step, total_rampup_steps)
         s_arena, t_arena = self.s_model.arena, self.t_model.arena
         s_arena.zero_grad()
@@ -142,13 +138,26 @@ class SSLMT(ssl_base._SSLBase):
         if self.args.is_epoch_lrer:
             self.s_lrer.step()
 
+    def _batch_prehandle(self, inp, gt, is_train):
+        """ssl_mt.py:337-357: host -> HBM; while training the first input element gets independent
+        Gaussian noise for the student and the teacher (``pxl_gaussian_noise`` in place on each device
+        copy).  With the noise disabled both models read the same device tensor."""
+        std = getattr(self.args, 'gaussian_noise_std', None)
+        s_inp = ssl_base.to_device(inp)
+        if is_train and std is not None:
+            t_first = s_inp[0].clone()
+            s_inp = (ops.gaussian_noise_(s_inp[0], std),) + tuple(s_inp[1:])
+            t_inp = (ops.gaussian_noise_(t_first, std),) + tuple(s_inp[1:])
+        else:
+            t_inp = s_inp
+        return s_inp, t_inp, ssl_base.to_device(gt)
+
     def _validate(self, data_loader, epoch):
         self.meters.reset()
         self.s_model.eval()
         self.t_model.eval()
         for idx, (inp, gt) in enumerate(data_loader):
-            s_inp = t_inp = ssl_base.to_device(inp)
-            gt = ssl_base.to_device(gt)
+            s_inp, t_inp, gt = self._batch_prehandle(inp, gt, False)
             s_resulter, _ = self.s_model.forward(s_inp)
             s_pred = tool.dict_value(s_resulter, 'pred')
             self.meters.update('s_task_loss', torch.mean(self.s_criterion.forward(s_pred, gt, s_inp)).data)
@@ -157,9 +166,9 @@ class SSLMT(ssl_base._SSLBase):
             self.meters.update('t_task_loss', torch.mean(self.s_criterion.forward(t_pred, gt, t_inp)).data)
             cons_loss = ops.mse_consistency(s_pred[0], t_pred[0].detach(), self.args.cons_scale)
             self.meters.update('cons_loss', cons_loss.data)
-            if self.task_func is not None and hasattr(self.task_func, 'metrics'):
-                self.task_func.metrics(tool.dict_value(s_resulter, 'activated_pred'), gt, s_inp, self.meters, id_str='student')
-                self.task_func.metrics(tool.dict_value(t_resulter, 'activated_pred'), gt, t_inp, self.meters, id_str='teacher')
+            self._metrics(s_resulter, gt, s_inp, 'student')
+            self._metrics(t_resulter, gt, t_inp, 'teacher')
+        self._log_validation_metrics(('student', 'teacher'))
 
     def _save_checkpoint(self, epoch):
         state = {'algorithm': self.NAME, 'epoch': epoch,

@@ -84,6 +84,8 @@ class SSLNULL(ssl_base._SSLBase):
             resulter, _ = self.model.forward(inp)
             pred = tool.dict_value(resulter, 'pred')
             self.meters.update('task_loss', torch.mean(self.criterion.forward(pred, gt, inp)).data)
+            self._metrics(resulter, gt, inp, 'task')
+        self._log_validation_metrics(('task',))
 
     def _save_checkpoint(self, epoch):
         state = {'algorithm': self.NAME, 'epoch': epoch, 'model': self.model.state_dict(),

@@ -1,5 +1,10 @@
-"""TaskFunc hooks used inside the training step (task/sseg/func.py:134-253).  Validation-time
-``metrics`` / ``visualize`` are out of scope for this round."""
+"""TaskFunc hooks used inside the training step (task/sseg/func.py:134-253) and the validation
+``metrics`` (task/sseg/func.py:36-80).  ``visualize`` (PIL colourisation to disk) stays with the
+reference."""
+import numpy as np
+import torch
+
+from ... import ops
 
 
 def task_func():
@@ -11,6 +16,26 @@ class SemanticSegmentationFunc:
 
     def __init__(self, args):
         self.args = args
+
+    def metrics(self, pred, gt, inp, meters, id_str=''):
+        """Confusion matrix of this batch on the device (``pxl_confusion_matrix``; the reference moves
+        the whole probability map to the host and uses np.argmax/np.bincount, func.py:39-47); only the
+        C x C int64 matrix crosses PCIe.  acc / acc-class / mIoU / fwIoU are the reference's formulas
+        on the meter's running sum (func.py:64-80)."""
+        assert len(pred) == len(gt) == 1
+        nc = self.args.num_classes
+        cmat = torch.zeros((nc, nc), dtype=torch.int64, device=pred[0].device)
+        ops.confusion_matrix_(cmat, pred[0].detach().contiguous(), gt[0].detach().contiguous(), nc)
+        confusion_matrix = cmat.cpu().numpy()
+        meters.update('{0}_confusion_matrix'.format(id_str), confusion_matrix)
+
+        names = {k: '{0}_{1}_{2}'.format(id_str, self.METRIC_STR, k) for k in ('acc', 'acc-class', 'mIoU', 'fwIoU')}
+        for name in names.values():
+            if meters.has_key(name):
+                meters.reset(name)
+        values = summarize_confusion_matrix(meters['{0}_confusion_matrix'.format(id_str)].sum)
+        for k, name in names.items():
+            meters.update(name, values[k])
 
     def sslcct_ad_in_channels(self):
         return 2048
@@ -26,3 +51,18 @@ class SemanticSegmentationFunc:
 
     def ssladv_fcd_in_channels(self):
         return self.args.num_classes
+
+
+def summarize_confusion_matrix(cmat_sum):
+    """acc, acc-class, mIoU, fwIoU of an accumulated confusion matrix (rows = gt), func.py:64-80;
+    0/0 classes are skipped through nanmean exactly like the reference."""
+    cmat_sum = np.asarray(cmat_sum)
+    diag = np.diag(cmat_sum)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        acc = diag.sum() / cmat_sum.sum()
+        acc_class = np.nanmean(diag / cmat_sum.sum(axis=1))
+        iou = diag / (np.sum(cmat_sum, axis=1) + np.sum(cmat_sum, axis=0) - diag)
+        miou = np.nanmean(iou)
+        freq = np.sum(cmat_sum, axis=1) / np.sum(cmat_sum)
+        fwiou = (freq[freq > 0] * iou[freq > 0]).sum()
+    return {'acc': acc, 'acc-class': acc_class, 'mIoU': miou, 'fwIoU': fwiou}

@@ -165,7 +165,9 @@ def test_cutmix_bit_exact(ops):
 
 @pytest.mark.parametrize('h,w,H,W,ac', [(33, 33, 513, 513, True), (9, 9, 129, 129, True), (5, 7, 97, 65, True),
                                         (33, 33, 65, 65, False), (20, 20, 39, 39, False), (1, 1, 8, 8, True),
-                                        (6, 6, 45, 45, False), (45, 45, 90, 90, True)])
+                                        (6, 6, 45, 45, False), (45, 45, 90, 90, True),
+                                        (65, 65, 33, 33, True), (40, 40, 17, 23, False), (3, 300, 7, 601, True),
+                                        (17, 17, 17, 17, False), (2, 2, 64, 64, False)])
 def test_bilinear_planar(ops, h, w, H, W, ac):
     gs = gen(h * 100 + H)
     x = torch.randn(2, 5, h, w, generator=gs)

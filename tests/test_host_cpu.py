@@ -122,3 +122,54 @@ def test_register_into_unmodified_pixelssl():
     parser = runner.create_parser('ssl_mt')
     ns = parser.parse_args(['--cons-scale', '1.0', '--ema-decay', '0.99'])
     assert ns.cons_scale == 1.0 and ns.ema_decay == 0.99
+
+
+def test_two_stream_sampler_matches_reference_streams():
+    """World size 1: the index stream equals the reference sampler's (golden, 3 epochs, seeded np.random).
+    World size 2: the two ranks partition every reference GLOBAL batch, labeled-first per rank."""
+    from pixelssl_b200.nn.data import TwoStreamBatchSampler
+    g = np.load(os.path.join(G, 'val.npz'))
+    for c, (nl, nu, lb, ub) in enumerate(g['sampler_cfgs']):
+        lab, unl = list(range(nl)), list(range(1000, 1000 + nu))
+        np.random.seed(100 + c)
+        smp = TwoStreamBatchSampler(lab, unl, int(lb), int(ub), rank=0, world_size=1)
+        for e in range(3):
+            want = g['sampler_%d_epoch%d' % (c, e)]
+            got = np.array([list(map(int, b)) for b in smp], dtype=np.int64).reshape(want.shape)
+            assert len(smp) == len(want)
+            assert np.array_equal(got, want), (c, e)
+        if lb % 2 or ub % 2:
+            continue
+        hl, hu = int(lb) // 2, int(ub) // 2
+        per_rank = []
+        for r in range(2):
+            np.random.seed(100 + c)
+            s2 = TwoStreamBatchSampler(lab, unl, hl, hu, rank=r, world_size=2)
+            per_rank.append([[list(map(int, b)) for b in s2] for _ in range(3)])
+        for e in range(3):
+            want = g['sampler_%d_epoch%d' % (c, e)]
+            for k, gb in enumerate(want):
+                L, U = list(gb[:lb]), list(gb[lb:])
+                for r in range(2):
+                    assert per_rank[r][e][k] == L[r * hl:(r + 1) * hl] + U[r * hu:(r + 1) * hu]
+
+
+def test_two_stream_sampler_private_seed_and_errors():
+    from pixelssl_b200.nn.data import TwoStreamBatchSampler
+    a = TwoStreamBatchSampler(list(range(20)), list(range(100, 160)), 2, 3, rank=1, world_size=2, seed=9)
+    b = TwoStreamBatchSampler(list(range(20)), list(range(100, 160)), 2, 3, rank=1, world_size=2, seed=9)
+    assert [list(x) for x in a] == [list(x) for x in b]
+    assert all(len(x) == 5 and all(i < 100 for i in x[:2]) and all(i >= 100 for i in x[2:]) for x in a)
+    with pytest.raises(ValueError):
+        TwoStreamBatchSampler([0, 1], [2, 3], 1, 1, rank=2, world_size=2)
+    with pytest.raises(AssertionError):
+        TwoStreamBatchSampler([0, 1], [2, 3, 4, 5], 2, 1, rank=0, world_size=2)
+
+
+def test_summarize_confusion_matrix_matches_golden():
+    from pixelssl_b200.task.sseg.func import summarize_confusion_matrix
+    g = np.load(os.path.join(G, 'val.npz'))
+    for k in range(2):
+        v = summarize_confusion_matrix(g['metrics_cmat_sum%d' % k])
+        got = np.array([v['acc'], v['acc-class'], v['mIoU'], v['fwIoU']])
+        np.testing.assert_allclose(got, g['metrics_values%d' % k], rtol=1e-12)

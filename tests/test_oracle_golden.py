@@ -286,3 +286,18 @@ def test_pspnet_forward_matches_reference():
     assert np.abs(logits.numpy() - g['logits']).max() / np.abs(g['logits']).max() < 1e-5
     cs = np.array([float(px.double().sum()), float((px.double() ** 2).sum())])
     np.testing.assert_allclose(cs, g['latent_checksum'][0], rtol=1e-5)
+
+
+def test_validation_metrics_match_reference():
+    g = load('val.npz')
+    total = np.zeros((21, 21), dtype=np.int64)
+    for k in range(2):
+        total += O.confusion_matrix(g['metrics_pred%d' % k], g['metrics_gt%d' % k], 21)
+        assert np.array_equal(total, g['metrics_cmat_sum%d' % k])
+        np.testing.assert_allclose(O.seg_metrics(total), g['metrics_values%d' % k], rtol=1e-12)
+
+
+def test_gaussian_noise_layer_matches_reference():
+    g = load('val.npz')
+    out = O.gaussian_noise_layer(torch.from_numpy(g['gn_inp']), torch.from_numpy(g['gn_noise']))
+    assert np.array_equal(out.numpy(), g['gn_out'])
