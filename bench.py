@@ -251,9 +251,51 @@ def cpu_reference(steps, warmup, lbs, ubs):
             'seconds': dt}
 
 
+def stock_torch_gpu_reference(steps, warmup, lbs, ubs):
+    """Informational only (``--impl reference --ref-device cuda``): the SAME oracle port of the reference
+    step run with stock PyTorch/cuDNN ops on cuda:0 (NCHW fp32 storage, cuDNN TF32 convolutions = torch's
+    default, no cudnn.benchmark - the reference sets none), full batch.  This is the "reference's 1-GPU
+    PyTorch images/sec" that BASELINE.json's >=5x target is phrased against; none of this repo's kernels
+    run here."""
+    import torch
+    from oracle import sseg_oracle as O
+    dev = torch.device('cuda:0')
+    s = {k: v.to(dev) for k, v in O.init_deeplabv2(0).items()}
+    t = {k: v.to(dev) for k, v in O.init_deeplabv2(1).items()}
+    mt = O.MTOracle(s, t, lr=0.00025, momentum=0.9, weight_decay=0.0005, max_iters=20 * 662, cons_scale=1.0,
+                    rampup_steps=3 * 662, ema_decay=0.99, cons_for_labeled=False)
+    batches = [O.synthetic_batch(1234 + i, lbs + ubs, lbs, H, W) for i in range(2)]
+    batches = [(a.pin_memory(), b.pin_memory()) for a, b in batches]
+
+    def one(i):
+        img, lab = batches[i % 2]
+        out = mt.step(img.to(dev, non_blocking=True), lab.to(dev, non_blocking=True), lbs)
+        return float(out['s_task_loss'])
+
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {'value': (lbs + ubs) * steps / dt, 'unit': 'images/s', 'seconds': dt,
+            'sample': '%d MT steps of DeepLab-v2-R101 at batch %d+%d, 513x513, stock PyTorch ops on cuda:0 '
+                      '(oracle port, cuDNN TF32 default)' % (steps, lbs, ubs)}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
+        return
+    if args.ref_device == 'cuda':
+        r = stock_torch_gpu_reference(args.steps, args.warmup, 8, 8)
+        print(json.dumps({'impl': 'reference', 'ref_device': 'cuda', 'metric': 'images/sec DeepLab-v2-R101 MT 513x513 bs16',
+                          'value': r['value'], 'unit': 'images/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
+                          'ms_per_step': r['seconds'] / args.steps * 1e3, 'higher_is_better': True, 'dtype': 'tf32 (cuDNN default)',
+                          'data': 'synthetic', 'config': {'workload': r['sample'], 'global_batch': 16}, 'gpu_launches': 0,
+                          'note': 'informational: stock PyTorch on the GPU, not the CPU reference arm'}))
         return
     cb = cpu_reference(steps=args.steps, warmup=min(args.warmup, 1) if args.steps > 3 else args.warmup, lbs=1, ubs=1)
     out = {'impl': 'reference', 'metric': 'images/sec DeepLab-v2-R101 MT 513x513 bs16', 'value': cb['value'],
@@ -278,6 +320,8 @@ def main():
     ap.add_argument('--precision', type=str, default=os.environ.get('PXL_CONV_PRECISION', 'tf32x3'),
                     choices=['fp32', 'tf32', 'tf32x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-device', type=str, default='cpu', choices=['cpu', 'cuda'],
+                    help='--impl reference only: cuda = the oracle port with stock PyTorch ops on cuda:0 (informational)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'engine':
         args.warmup = 3

@@ -57,6 +57,22 @@ static int make_act_map(CUtensorMap* m, const float* base, int C, int W, int H, 
     return r == CUDA_SUCCESS ? 0 : PXL_ERR_BAD_ARG;
 }
 
+// NHWC fp32 output viewed as (Cout, W, H, N) with pixel stride ldo: box {32, bw, bh, 1}, 128-byte swizzle.
+// Used by the epilogue's TMA store: channels >= Cout and pixels outside the image are clipped by the TMA unit.
+static int make_out_map(CUtensorMap* m, const float* base, int Cout, int ldo, int W, int H, int N, int bw, int bh) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return PXL_ERR_UNSUPPORTED;
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ldo * 4, (cuuint64_t)W * ldo * 4, (cuuint64_t)H * W * ldo * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (box[1] > 256 || box[2] > 256) return PXL_ERR_UNSUPPORTED;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : PXL_ERR_BAD_ARG;
+}
+
 // weights [rows][K] fp32, box {32, bn}
 static int make_w_map(CUtensorMap* m, const float* base, int64_t K, int rows, int bn) {
     EncodeTiledFn enc = get_encode();
@@ -113,6 +129,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* src, const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -179,6 +205,8 @@ struct TcParams {
     int a_inkernel; // 3xTF32 only: A arrives as raw fp32 and is split hi/lo in shared memory by the epilogue warps
     int in_mul;     // input pixel = output pixel * in_mul + tap (stride-2 forward uses the TMA traversal stride)
     int out_mul, out_offy, out_offx, outH, outW;   // output pixel (oy,ox) is stored at (oy*out_mul+offy, ox*out_mul+offx)
+    int ntilesN, total_tiles;   // persistent kernel: N tiles per pixel tile, tiles in total
+    int tma_store;  // epilogue stages 32-channel slabs in the (drained) operand ring and writes them with TMA
     short dy[PXL_MAX_TAPS], dx[PXL_MAX_TAPS], widx[PXL_MAX_TAPS];
 };
 
@@ -187,6 +215,7 @@ struct TcParams {
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
+               const __grid_constant__ CUtensorMap mapOut,
                const TcParams p, const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats,
                int* __restrict__ err_flag) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -355,6 +384,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         atomicAdd(stats + p.Cout + cb + lane, (double)sq[0]);
                     }
                 }
+                if (p.tma_store) {
+                    // stage this warp's 32 rows of the slab in the drained operand ring (canonical 128B-swizzled
+                    // rows: conflict-free float4 writes), TMA-store the whole 128-row slab once all four warps
+                    // are done.  The ring holds `fit` slabs; a round = up to `fit` consecutive slabs.
+                    const int fit = (p.stages * stage_bytes) / TC_A_BYTES;
+                    const int slab = (j >> 5) % fit;
+                    float4* dst = reinterpret_cast<float4*>(smem + (size_t)slab * TC_A_BYTES + (size_t)r * 128);
+                    if (cb < p.Cout) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                            if (bias) {
+                                const int cc = cb + 4 * c;
+                                if (cc < p.Cout) o.x += __ldg(bias + cc);
+                                if (cc + 1 < p.Cout) o.y += __ldg(bias + cc + 1);
+                                if (cc + 2 < p.Cout) o.z += __ldg(bias + cc + 2);
+                                if (cc + 3 < p.Cout) o.w += __ldg(bias + cc + 3);
+                            }
+                            dst[c ^ (r & 7)] = o;
+                        }
+                    }
+                    const bool round_end = (slab == fit - 1) || (j + 32 >= p.BN);
+                    if (round_end) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (threadIdx.x == 64) {
+                            const int first = j - slab * 32;          // first column of this round
+                            for (int jj = 0; jj <= slab; ++jj) {
+                                const int cs = n0 + first + jj * 32;
+                                if (cs < p.Cout)
+                                    tma_store_4d(smem + (size_t)jj * TC_A_BYTES, &mapOut, cs, w0, h0, n);
+                            }
+                            tma_store_commit_and_wait_read();
+                        }
+                        if (j + 32 < p.BN) asm volatile("bar.sync 1, 128;" ::: "memory");   // ring reusable
+                    }
+                    continue;
+                }
                 if (!valid) continue;
                 if (cb + 31 < p.Cout && (p.ldo & 3) == 0) {
 #pragma unroll
@@ -367,6 +434,251 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int c = 0; c < 32; ++c)
                         if (cb + c < p.Cout) orow[cb + c] = v[c] + (bias ? __ldg(bias + cb + c) : 0.f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks over output tiles (static stride).  The operand ring keeps
+// streaming across tile boundaries, the accumulator is double-buffered in TMEM (set = tile & 1) and the
+// epilogue of tile t (TMEM -> registers -> swizzled staging slab -> TMA store) overlaps the main loop of
+// tile t+1.  Warp roles: 0 TMA producer, 1 MMA issuer (+TMEM allocator), 2..5 epilogue, 6..9 operand
+// transform (3xTF32 with raw activations only: hi/lo split of the A tile in shared memory).
+// ------------------------------------------------------------------------------------------
+#define TC_STG_SLABS 2
+
+__device__ __forceinline__ void tc_tile_coords(const TcParams& p, int tile, int& n0, int& w0, int& h0, int& n) {
+    const int nt = tile % p.ntilesN, pix = tile / p.ntilesN;
+    const int tw = pix % p.tilesW, th = (pix / p.tilesW) % p.tilesH;
+    n = pix / (p.tilesW * p.tilesH);
+    w0 = tw * p.BW; h0 = th * p.BH; n0 = nt * p.BN;
+}
+
+__global__ void __launch_bounds__(320, 1)
+conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+                       const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
+                       const __grid_constant__ CUtensorMap mapOut,
+                       const TcParams p, const float* __restrict__ bias, float* __restrict__ out,
+                       double* __restrict__ stats, int* __restrict__ err_flag) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[8], empty_bar[8], ready_bar[8], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = p.BN * 128;
+    const int per_op = TC_A_BYTES + b_bytes;
+    const int stage_bytes = per_op * (p.nsplit == 3 ? 2 : 1);
+    uint8_t* staging = smem + (size_t)p.stages * stage_bytes;        // TC_STG_SLABS x 16 KB, 1024-aligned
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int iters = p.ntaps * p.kchunks;
+    const uint32_t acc_cols = p.BN < 32 ? 32 : p.BN;
+    const uint32_t set_cols = acc_cols * p.nacc;
+    const uint32_t tmem_cols = 512;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t tx = (uint32_t)((p.BW * p.BH * 128 + b_bytes) * (p.nsplit == 3 ? 2 : 1));
+            if (p.a_inkernel) tx -= (uint32_t)(p.BW * p.BH * 128);
+            uint32_t gs = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+                int n0, w0, h0, n;
+                tc_tile_coords(p, tile, n0, w0, h0, n);
+                for (int it = 0; it < iters; ++it, ++gs) {
+                    const int s = gs % p.stages;
+                    const uint32_t ph = (gs / p.stages) & 1u;
+                    ok = mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 1);
+                    if (!ok) break;
+                    const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * 32;
+                    uint8_t* sa = smem + (size_t)s * stage_bytes;
+                    mbar_expect_tx(&full_bar[s], tx);
+                    const int ax = w0 * p.in_mul + p.dx[tap], ay = h0 * p.in_mul + p.dy[tap];
+                    const int bk = p.widx[tap] * p.Cin + c0;
+                    tma_load_4d(sa, &mapA, &full_bar[s], c0, ax, ay, n);
+                    tma_load_2d(sa + TC_A_BYTES, &mapB, &full_bar[s], bk, n0);
+                    if (p.nsplit == 3) {
+                        if (!p.a_inkernel) tma_load_4d(sa + per_op, &mapAlo, &full_bar[s], c0, ax, ay, n);
+                        tma_load_2d(sa + per_op + TC_A_BYTES, &mapBlo, &full_bar[s], bk, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = tf32_idesc(p.BN);
+            uint32_t gs = 0, tcount = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++tcount) {
+                const uint32_t set = tcount & 1u, aph = (tcount >> 1) & 1u;
+                ok = mbar_wait(&acc_empty[set], aph ^ 1u, err_flag, 5);       // epilogue drained this set
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t set_base = tmem_d + set * set_cols;
+                for (int it = 0; it < iters; ++it, ++gs) {
+                    const int s = gs % p.stages;
+                    const uint32_t ph = (gs / p.stages) & 1u;
+                    ok = mbar_wait(p.a_inkernel ? &ready_bar[s] : &full_bar[s], ph, err_flag, 2);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t da = kmajor_sw128_desc(sa), db = kmajor_sw128_desc(sa + TC_A_BYTES);
+                    const uint32_t acc = set_base + (uint32_t)(it % p.nacc) * acc_cols;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_tf32(acc, da + 2 * k, db + 2 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
+                    if (p.nsplit == 3) {
+                        const uint64_t dal = kmajor_sw128_desc(sa + per_op), dbl = kmajor_sw128_desc(sa + per_op + TC_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_tf32(acc, dal + 2 * k, db + 2 * k, idesc, 1);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_tf32(acc, da + 2 * k, dbl + 2 * k, idesc, 1);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                if (ok) umma_commit(&acc_full[set]);
+            }
+        }
+    } else if (warp < 6) {
+        // ================= epilogue =================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int et = threadIdx.x - 64;                 // 0..127
+        uint32_t tcount = 0, sc = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++tcount) {
+            const uint32_t set = tcount & 1u, aph = (tcount >> 1) & 1u;
+            ok = __all_sync(0xffffffffu, mbar_wait(&acc_full[set], aph, err_flag, 3));
+            if (!ok) break;
+            tc_fence_after();
+            int n0, w0, h0, n;
+            tc_tile_coords(p, tile, n0, w0, h0, n);
+            const int hy = r / p.BW, wx = r - hy * p.BW;
+            const int oy = h0 + hy, ox = w0 + wx;
+            const bool valid = hy < p.BH && oy < p.OH && ox < p.OW;
+            float* orow = out + ((int64_t)(n * p.outH + oy * p.out_mul + p.out_offy) * p.outW + ox * p.out_mul + p.out_offx) * p.ldo;
+            const int used = iters < p.nacc ? iters : p.nacc;
+            const uint32_t tbase = tmem_d + set * set_cols + ((uint32_t)(q * 32) << 16);
+            for (int j = 0; j < p.BN; j += 32) {
+                const int cb = n0 + j;
+                if (cb >= p.Cout) break;                  // uniform: nothing left to store for this tile
+                float v[32];
+                tmem_ld32(tbase + (uint32_t)j, v);
+                for (int a = 1; a < used; ++a) {
+                    float u[32];
+                    tmem_ld32(tbase + (uint32_t)a * acc_cols + (uint32_t)j, u);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] += u[c];
+                }
+                if (bias) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) if (cb + c < p.Cout) v[c] += __ldg(bias + cb + c);
+                }
+                if (stats) {
+                    float sv[32], sq[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) { const float o = valid ? v[c] : 0.f; sv[c] = o; sq[c] = o * o; }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float s_send = up ? sv[i] : sv[i + off], q_send = up ? sq[i] : sq[i + off];
+                            const float s_recv = __shfl_xor_sync(0xffffffffu, s_send, off);
+                            const float q_recv = __shfl_xor_sync(0xffffffffu, q_send, off);
+                            sv[i] = (up ? sv[i + off] : sv[i]) + s_recv;
+                            sq[i] = (up ? sq[i + off] : sq[i]) + q_recv;
+                        }
+                    }
+                    if (cb + lane < p.Cout) {
+                        atomicAdd(stats + cb + lane, (double)sv[0]);
+                        atomicAdd(stats + p.Cout + cb + lane, (double)sq[0]);
+                    }
+                }
+                if (p.tma_store) {
+                    const uint32_t b = sc & 1u;
+                    // slab b was last stored two slabs ago: its TMA read must be over before it is rewritten
+                    if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    float4* dst = reinterpret_cast<float4*>(staging + (size_t)b * TC_A_BYTES + (size_t)r * 128);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        dst[c ^ (r & 7)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et == 0) {
+                        tma_store_4d(staging + (size_t)b * TC_A_BYTES, &mapOut, cb, w0, h0, n);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++sc;
+                } else if (valid) {
+                    if (cb + 31 < p.Cout && (p.ldo & 3) == 0) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4)
+                            *reinterpret_cast<float4*>(orow + cb + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (cb + c < p.Cout) orow[cb + c] = v[c];
+                    }
+                }
+            }
+            // this accumulator set may be overwritten by the MMA warp now
+            tc_fence_before();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[set])) : "memory");
+        }
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    } else {
+        // ================= operand transform (3xTF32, raw activations) =================
+        if (p.a_inkernel) {
+            const int t = threadIdx.x - 192;
+            uint32_t gs = 0;
+            bool okt = true;
+            for (int tile = blockIdx.x; tile < p.total_tiles && okt; tile += gridDim.x) {
+                for (int it = 0; it < iters; ++it, ++gs) {
+                    const int s = gs % p.stages;
+                    const uint32_t ph = (gs / p.stages) & 1u;
+                    okt = mbar_wait(&full_bar[s], ph, err_flag, 4);
+                    if (!okt) break;
+                    float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+                    float4* a_lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + per_op);
+#pragma unroll
+                    for (int c = 0; c < TC_A_BYTES / 16 / 128; ++c) {
+                        const float4 v = a_hi[t + c * 128];
+                        float4 h, l;
+                        const float* vp = &v.x; float* hp = &h.x; float* lp = &l.x;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            uint32_t u;
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vp[e]));
+                            u &= 0xFFFFE000u;
+                            hp[e] = __uint_as_float(u);
+                            lp[e] = vp[e] - hp[e];
+                        }
+                        a_hi[t + c * 128] = h;
+                        a_lo[t + c * 128] = l;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
                 }
             }
         }
@@ -476,7 +788,6 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
     }
     pick_tile(p.OH, p.OW, flat, p.BW, p.BH);
     if (g->mul == 2 && (p.BW > 128 || p.BH > 128)) return PXL_ERR_UNSUPPORTED;
-    p.tilesW = (p.OW + p.BW - 1) / p.BW; p.tilesH = (p.OH + p.BH - 1) / p.BH;
     // tuning knobs (environment, read once): shared-memory budget per CTA in KB (<= ~100 lets two CTAs share
     // an SM so one CTA's epilogue overlaps the other's main loop), N-tile cap, accumulator count
     static int cfg_budget_kb = -1, cfg_bn_max1 = 256, cfg_bn_max3 = 128, cfg_nacc3 = 4;
@@ -489,17 +800,38 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
     p.BN = g->Cout > 128 ? 256 : (g->Cout > 64 ? 128 : (g->Cout > 32 ? 64 : 32));
     const int bn_cap = nsplit == 3 ? cfg_bn_max3 : cfg_bn_max1;
     if (p.BN > bn_cap) p.BN = bn_cap;
+    static int cfg_persist = -1;
+    if (cfg_persist < 0) { const char* e = getenv("PXL_TC_PERSIST"); cfg_persist = e ? atoi(e) : 1; }
+    // measured per layer shape (tools/bench_conv.py): the persistent kernel wins everywhere for 3xTF32 and for
+    // single-pass TF32 except multi-tap convolutions with more than one wave of tiles, where two co-resident
+    // non-persistent CTAs per SM pull more L2 bandwidth (those layers are operand-traffic bound)
+    int use_persist = cfg_persist;
+    if (cfg_persist == 1 && nsplit == 1 && g->ntaps > 1) {
+        int bw, bh;
+        pick_tile(p.OH, p.OW, flat, bw, bh);
+        const int64_t tiles = (int64_t)p.N * ((p.OW + bw - 1) / bw) * ((p.OH + bh - 1) / bh) * ((g->Cout + p.BN - 1) / p.BN);
+        if (tiles > PXL_NUM_SMS) use_persist = 0;
+    }
     p.nacc = nsplit == 3 ? cfg_nacc3 : 1;
-    while (p.nacc > 1 && (p.BN < 32 ? 32 : p.BN) * p.nacc > 512) p.nacc >>= 1;
+    // TMEM: 512 columns per SM; the persistent kernel keeps two accumulator sets (epilogue / main loop overlap)
+    while (p.nacc > 1 && (p.BN < 32 ? 32 : p.BN) * p.nacc * (use_persist ? 2 : 1) > 512) p.nacc >>= 1;
     const int per_op = TC_A_BYTES + p.BN * 128;
     const int stage_bytes = per_op * (nsplit == 3 ? 2 : 1);
     // measured (tools/sweep_tc.sh, MT step): single-pass TF32 is 6.5 % faster with two co-resident CTAs per SM
     // (<= 100 KB each: one CTA's epilogue overlaps the other's main loop); 3xTF32 needs the deeper ring
-    const int budget = (getenv("PXL_TC_SMEM_KB") ? cfg_budget_kb : (nsplit == 3 ? 200 : 100)) * 1024;
-    p.stages = budget / stage_bytes;
+    pick_tile(p.OH, p.OW, flat, p.BW, p.BH);
+    p.tilesW = (p.OW + p.BW - 1) / p.BW; p.tilesH = (p.OH + p.BH - 1) / p.BH;
+    const int64_t n_ctas = (int64_t)p.N * p.tilesH * p.tilesW * ((g->Cout + p.BN - 1) / p.BN);
+    // a grid that fits one wave at one CTA per SM gets the deep ring instead of a co-resident CTA
+    const int budget = (getenv("PXL_TC_SMEM_KB") ? cfg_budget_kb : ((nsplit == 3 || n_ctas <= PXL_NUM_SMS) ? 200 : 100)) * 1024;
+    p.ntilesN = (g->Cout + p.BN - 1) / p.BN;
+    p.total_tiles = (int)n_ctas;
+    const size_t persist_fixed = 1024 + (size_t)TC_STG_SLABS * TC_A_BYTES;     // alignment slack + staging slabs
+    if (use_persist) p.stages = (int)((227 * 1024 - 2048 - persist_fixed) / stage_bytes);
+    else p.stages = budget / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return PXL_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    const size_t smem = use_persist ? (size_t)p.stages * stage_bytes + persist_fixed : (size_t)p.stages * stage_bytes + 1024;
 
     CUtensorMap mA, mAlo, mB, mBlo;
     int rc = make_act_map(&mA, in_hi, g->Cin, mapW, mapH, mapN, p.BW, p.BH, g->mul);
@@ -517,6 +849,15 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
     } else {
         mAlo = mA; mBlo = mB;
     }
+    // TMA-store epilogue: needs 16-byte pixel strides and the plain output mapping
+    static int cfg_tma_store = -1;
+    if (cfg_tma_store < 0) { const char* e = getenv("PXL_TC_TMA_STORE"); cfg_tma_store = e ? atoi(e) : 1; }
+    p.tma_store = (cfg_tma_store && !has_out_xform && (g->ldo % 4) == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
+    CUtensorMap mO = mA;
+    if (p.tma_store) {
+        rc = make_out_map(&mO, out, g->Cout, g->ldo, p.outW, p.outH, p.N, p.BW, p.BH);
+        if (rc) p.tma_store = 0;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (!g_err_flag) {
         cudaError_t e = cudaMalloc(&g_err_flag, sizeof(int));
@@ -530,8 +871,20 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
+    if (use_persist) {
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+            if (e != cudaSuccess) return (int)e;
+            attr2 = true;
+        }
+        const unsigned nblk = (unsigned)(p.total_tiles < PXL_NUM_SMS ? p.total_tiles : PXL_NUM_SMS);
+        conv_tc_persist_kernel<<<nblk, 320, smem, st>>>(mA, mAlo, mB, mBlo, mO, p, bias, out, ext ? ext->bn_stats : nullptr, g_err_flag);
+        PXL_CHECK_LAUNCH();
+        return 0;
+    }
     dim3 grid((unsigned)((int64_t)p.N * p.tilesH * p.tilesW), (unsigned)((g->Cout + p.BN - 1) / p.BN));
-    conv_tc_kernel<<<grid, 192, smem, st>>>(mA, mAlo, mB, mBlo, p, bias, out, ext ? ext->bn_stats : nullptr, g_err_flag);
+    conv_tc_kernel<<<grid, 192, smem, st>>>(mA, mAlo, mB, mBlo, mO, p, bias, out, ext ? ext->bn_stats : nullptr, g_err_flag);
     PXL_CHECK_LAUNCH();
     return 0;
 }
