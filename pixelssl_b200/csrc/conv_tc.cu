@@ -109,6 +109,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* flag, int code) {
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        if (mbar_try_wait_cluster(bar, parity)) return true;
+        if ((spin & 1023u) == 1023u && *(volatile int*)flag != 0) return false;
+    }
+    atomicCAS(flag, 0, code);
+    return false;
+}
 // bounded wait: returns false (and raises *flag) if the barrier never completes
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* flag, int code) {
     for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
@@ -688,6 +707,315 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2, cluster of two CTAs on one TPC): the pair computes a
+// 256-pixel x BN tile per step.  Each CTA stages ITS 128 pixels of A and HALF of the B tile (BN/2 weight
+// rows); one tcgen05.mma.cta_group::2 issued by the leader CTA reads A and B from both CTAs' shared memory
+// and writes rows 0..127 into the leader's TMEM and rows 128..255 into the peer's.  Operand traffic per
+// FLOP drops by a third compared with two independent 128 x BN tiles, and the shared-memory stage shrinks
+// so the ring gets deeper.  Same persistent structure as conv_tc_persist_kernel.
+//
+// Barriers (identical shared-memory offsets in both CTAs):
+//   full[s]   single-pass TF32: leader's only, count 1 + tx bytes of BOTH CTAs (2-SM TMA form signals the
+//             leader's barrier).  3xTF32 in-kernel split: per CTA, local loads.
+//   ready[s]  3xTF32: leader's only, count 256 = transform threads of both CTAs (peer arrives remotely)
+//   empty[s]  per CTA, count 1, arrival = multicast tcgen05.commit of the leader's MMA thread
+//   acc_full[2]  per CTA, count 1, multicast commit;   acc_empty[2]  leader's only, count 256
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+__device__ __forceinline__ void tc_pair_coords(const TcParams& p, int work, uint32_t rank, int& n0, int& w0, int& h0, int& n) {
+    const int nt = work % p.ntilesN, pix = 2 * (work / p.ntilesN) + (int)rank;
+    const int tw = pix % p.tilesW, th = (pix / p.tilesW) % p.tilesH;
+    n = pix / (p.tilesW * p.tilesH);                     // == p.N for the padding tile of an odd tile count
+    w0 = tw * p.BW; h0 = th * p.BH; n0 = nt * p.BN;
+}
+
+__global__ void __launch_bounds__(320, 1)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
+                    const __grid_constant__ CUtensorMap mapOut,
+                    const TcParams p, const float* __restrict__ bias, float* __restrict__ out,
+                    double* __restrict__ stats, int* __restrict__ err_flag) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[8], empty_bar[8], ready_bar[8], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int bh_rows = p.BN / 2;                         // weight rows staged by this CTA
+    const int b_bytes = bh_rows * 128;
+    const int per_op = TC_A_BYTES + b_bytes;
+    const int stage_bytes = per_op * (p.nsplit == 3 ? 2 : 1);
+    uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int iters = p.ntaps * p.kchunks;
+    const uint32_t acc_cols = p.BN;
+    const uint32_t set_cols = acc_cols * p.nacc;
+    const uint32_t tmem_cols = 512;
+    const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 256); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc2(&tmem_base_slot, tmem_cols);
+    tc_fence_before();
+    cluster_sync_all();                                   // peer barriers initialised, TMEM allocated in both CTAs
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            const uint32_t my_bytes = (uint32_t)((p.BW * p.BH * 128 + b_bytes) * (p.nsplit == 3 ? 2 : 1)) -
+                                      (p.a_inkernel ? (uint32_t)(p.BW * p.BH * 128) : 0u);
+            uint32_t gs = 0;
+            bool ok = true;
+            for (int work = cid; work < p.total_tiles && ok; work += nclusters) {
+                int n0, w0, h0, n;
+                tc_pair_coords(p, work, rank, n0, w0, h0, n);
+                const int brow = n0 + (int)rank * bh_rows;
+                for (int it = 0; it < iters; ++it, ++gs) {
+                    const int s = gs % p.stages;
+                    const uint32_t ph = (gs / p.stages) & 1u;
+                    ok = mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 1);
+                    if (!ok) break;
+                    const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * 32;
+                    uint8_t* sa = smem + (size_t)s * stage_bytes;
+                    const int ax = w0 * p.in_mul + p.dx[tap], ay = h0 * p.in_mul + p.dy[tap];
+                    const int bk = p.widx[tap] * p.Cin + c0;
+                    if (p.a_inkernel) {
+                        // local barrier: this CTA's transform warps wait for this CTA's bytes
+                        mbar_expect_tx(&full_bar[s], my_bytes);
+                        tma_load_4d(sa, &mapA, &full_bar[s], c0, ax, ay, n);
+                        tma_load_2d(sa + TC_A_BYTES, &mapB, &full_bar[s], bk, brow);
+                        tma_load_2d(sa + per_op + TC_A_BYTES, &mapBlo, &full_bar[s], bk, brow);
+                    } else {
+                        // the leader's barrier collects the bytes of both CTAs
+                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+                        if (leader) mbar_expect_tx(&full_bar[s], 2u * my_bytes);
+                        tma2_load_4d(sa, &mapA, fb, c0, ax, ay, n);
+                        tma2_load_2d(sa + TC_A_BYTES, &mapB, fb, bk, brow);
+                        if (p.nsplit == 3) {
+                            tma2_load_4d(sa + per_op, &mapAlo, fb, c0, ax, ay, n);
+                            tma2_load_2d(sa + per_op + TC_A_BYTES, &mapBlo, fb, bk, brow);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA, one thread) =================
+        if (leader && lane == 0) {
+            // M = 256 (bits 24..28 = M >> 4), N = BN
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            uint32_t gs = 0, tcount = 0;
+            bool ok = true;
+            for (int work = cid; work < p.total_tiles && ok; work += nclusters, ++tcount) {
+                const uint32_t set = tcount & 1u, aph = (tcount >> 1) & 1u;
+                ok = mbar_wait_cluster(&acc_empty[set], aph ^ 1u, err_flag, 5);
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t set_base = tmem_d + set * set_cols;
+                for (int it = 0; it < iters; ++it, ++gs) {
+                    const int s = gs % p.stages;
+                    const uint32_t ph = (gs / p.stages) & 1u;
+                    ok = mbar_wait_cluster(p.a_inkernel ? &ready_bar[s] : &full_bar[s], ph, err_flag, 2);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t da = kmajor_sw128_desc(sa), db = kmajor_sw128_desc(sa + TC_A_BYTES);
+                    const uint32_t acc = set_base + (uint32_t)(it % p.nacc) * acc_cols;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma2_tf32(acc, da + 2 * k, db + 2 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
+                    if (p.nsplit == 3) {
+                        const uint64_t dal = kmajor_sw128_desc(sa + per_op), dbl = kmajor_sw128_desc(sa + per_op + TC_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma2_tf32(acc, dal + 2 * k, db + 2 * k, idesc, 1);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma2_tf32(acc, da + 2 * k, dbl + 2 * k, idesc, 1);
+                    }
+                    umma2_commit_mc(&empty_bar[s]);          // frees the slot in both CTAs
+                }
+                if (ok) umma2_commit_mc(&acc_full[set]);
+            }
+        }
+    } else if (warp < 6) {
+        // ================= epilogue (both CTAs, own 128 rows) =================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int et = threadIdx.x - 64;
+        uint32_t tcount = 0, sc = 0;
+        bool ok = true;
+        for (int work = cid; work < p.total_tiles && ok; work += nclusters, ++tcount) {
+            const uint32_t set = tcount & 1u, aph = (tcount >> 1) & 1u;
+            ok = __all_sync(0xffffffffu, mbar_wait(&acc_full[set], aph, err_flag, 3));
+            if (!ok) break;
+            tc_fence_after();
+            int n0, w0, h0, n;
+            tc_pair_coords(p, work, rank, n0, w0, h0, n);
+            const int hy = r / p.BW, wx = r - hy * p.BW;
+            const int oy = h0 + hy, ox = w0 + wx;
+            const bool valid = n < p.N && hy < p.BH && oy < p.OH && ox < p.OW;
+            float* orow = out + ((int64_t)(n * p.outH + oy * p.out_mul + p.out_offy) * p.outW + ox * p.out_mul + p.out_offx) * p.ldo;
+            const int used = iters < p.nacc ? iters : p.nacc;
+            const uint32_t tbase = tmem_d + set * set_cols + ((uint32_t)(q * 32) << 16);
+            for (int j = 0; j < p.BN; j += 32) {
+                const int cb = n0 + j;
+                if (cb >= p.Cout || n >= p.N) break;
+                float v[32];
+                tmem_ld32(tbase + (uint32_t)j, v);
+                for (int a = 1; a < used; ++a) {
+                    float u[32];
+                    tmem_ld32(tbase + (uint32_t)a * acc_cols + (uint32_t)j, u);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] += u[c];
+                }
+                if (bias) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) if (cb + c < p.Cout) v[c] += __ldg(bias + cb + c);
+                }
+                if (stats) {
+                    float sv[32], sq[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) { const float o = valid ? v[c] : 0.f; sv[c] = o; sq[c] = o * o; }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float s_send = up ? sv[i] : sv[i + off], q_send = up ? sq[i] : sq[i + off];
+                            const float s_recv = __shfl_xor_sync(0xffffffffu, s_send, off);
+                            const float q_recv = __shfl_xor_sync(0xffffffffu, q_send, off);
+                            sv[i] = (up ? sv[i + off] : sv[i]) + s_recv;
+                            sq[i] = (up ? sq[i + off] : sq[i]) + q_recv;
+                        }
+                    }
+                    if (cb + lane < p.Cout) {
+                        atomicAdd(stats + cb + lane, (double)sv[0]);
+                        atomicAdd(stats + p.Cout + cb + lane, (double)sq[0]);
+                    }
+                }
+                if (p.tma_store) {
+                    const uint32_t b = sc & 1u;
+                    if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    float4* dst = reinterpret_cast<float4*>(staging + (size_t)b * TC_A_BYTES + (size_t)r * 128);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        dst[c ^ (r & 7)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et == 0) {
+                        tma_store_4d(staging + (size_t)b * TC_A_BYTES, &mapOut, cb, w0, h0, n);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++sc;
+                } else if (valid) {
+                    if (cb + 31 < p.Cout && (p.ldo & 3) == 0) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4)
+                            *reinterpret_cast<float4*>(orow + cb + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (cb + c < p.Cout) orow[cb + c] = v[c];
+                    }
+                }
+            }
+            // release this accumulator set to the leader's MMA thread (256 arrivals: both CTAs)
+            tc_fence_before();
+            mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[set]), 0));
+        }
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    } else {
+        // ================= operand transform (3xTF32 with raw activations; both CTAs) =================
+        if (p.a_inkernel) {
+            const int t = threadIdx.x - 192;
+            uint32_t gs = 0;
+            bool okt = true;
+            for (int work = cid; work < p.total_tiles && okt; work += nclusters) {
+                for (int it = 0; it < iters; ++it, ++gs) {
+                    const int s = gs % p.stages;
+                    const uint32_t ph = (gs / p.stages) & 1u;
+                    okt = mbar_wait(&full_bar[s], ph, err_flag, 4);
+                    if (!okt) break;
+                    float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+                    float4* a_lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + per_op);
+#pragma unroll
+                    for (int c = 0; c < TC_A_BYTES / 16 / 128; ++c) {
+                        const float4 v = a_hi[t + c * 128];
+                        float4 h, l;
+                        const float* vp = &v.x; float* hp = &h.x; float* lp = &l.x;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            uint32_t u;
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vp[e]));
+                            u &= 0xFFFFE000u;
+                            hp[e] = __uint_as_float(u);
+                            lp[e] = vp[e] - hp[e];
+                        }
+                        a_hi[t + c * 128] = h;
+                        a_lo[t + c * 128] = l;
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");      // generic writes -> async proxy (both SMs' tensor cores)
+                    mbar_arrive_cluster(mapa_u32(smem_u32(&ready_bar[s]), 0));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                                   // nobody leaves while the peer may still touch its smem/TMEM
+    if (warp == 1) tmem_dealloc2(tmem_d, tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------
 // tf32 split: hi = x with the low 13 mantissa bits cleared after round-to-nearest, lo = x - hi
 // ------------------------------------------------------------------------------------------
@@ -812,10 +1140,21 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
         const int64_t tiles = (int64_t)p.N * ((p.OW + bw - 1) / bw) * ((p.OH + bh - 1) / bh) * ((g->Cout + p.BN - 1) / p.BN);
         if (tiles > PXL_NUM_SMS) use_persist = 0;
     }
+    // CTA pairs (cta_group::2): 256 pixels x BN per step, each CTA stages half of the weight tile
+    static int cfg_pair = -1;
+    if (cfg_pair < 0) { const char* e = getenv("PXL_TC_PAIR"); cfg_pair = e ? atoi(e) : 0; }
+    int use_pair = 0;
+    if (cfg_pair && cfg_persist && p.BN >= 128) {
+        int bw, bh;
+        pick_tile(p.OH, p.OW, flat, bw, bh);
+        const int64_t pix_tiles = (int64_t)p.N * ((p.OW + bw - 1) / bw) * ((p.OH + bh - 1) / bh);
+        if (pix_tiles >= 2) use_pair = 1;
+    }
+    if (use_pair) use_persist = 1;
     p.nacc = nsplit == 3 ? cfg_nacc3 : 1;
     // TMEM: 512 columns per SM; the persistent kernel keeps two accumulator sets (epilogue / main loop overlap)
     while (p.nacc > 1 && (p.BN < 32 ? 32 : p.BN) * p.nacc * (use_persist ? 2 : 1) > 512) p.nacc >>= 1;
-    const int per_op = TC_A_BYTES + p.BN * 128;
+    const int per_op = TC_A_BYTES + (use_pair ? p.BN / 2 : p.BN) * 128;
     const int stage_bytes = per_op * (nsplit == 3 ? 2 : 1);
     // measured (tools/sweep_tc.sh, MT step): single-pass TF32 is 6.5 % faster with two co-resident CTAs per SM
     // (<= 100 KB each: one CTA's epilogue overlaps the other's main loop); 3xTF32 needs the deeper ring
@@ -836,7 +1175,8 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
     CUtensorMap mA, mAlo, mB, mBlo;
     int rc = make_act_map(&mA, in_hi, g->Cin, mapW, mapH, mapN, p.BW, p.BH, g->mul);
     if (rc) return rc;
-    rc = make_w_map(&mB, w_hi, (int64_t)wtaps * g->Cin, g->Cout, p.BN);
+    const int b_box_rows = use_pair ? p.BN / 2 : p.BN;
+    rc = make_w_map(&mB, w_hi, (int64_t)wtaps * g->Cin, g->Cout, b_box_rows);
     if (rc) return rc;
     if (nsplit == 3) {
         if (a_inkernel) mAlo = mA;
@@ -844,7 +1184,7 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
             rc = make_act_map(&mAlo, in_lo, g->Cin, mapW, mapH, mapN, p.BW, p.BH, g->mul);
             if (rc) return rc;
         }
-        rc = make_w_map(&mBlo, w_lo, (int64_t)wtaps * g->Cin, g->Cout, p.BN);
+        rc = make_w_map(&mBlo, w_lo, (int64_t)wtaps * g->Cin, g->Cout, b_box_rows);
         if (rc) return rc;
     } else {
         mAlo = mA; mBlo = mB;
@@ -870,6 +1210,31 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
         if (e != cudaSuccess) return (int)e;
         attr = true;
+    }
+    if (use_pair) {
+        static bool attr3 = false;
+        if (!attr3) {
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+            if (e != cudaSuccess) return (int)e;
+            attr3 = true;
+        }
+        const int64_t pix_tiles = (int64_t)p.N * p.tilesH * p.tilesW;
+        p.total_tiles = (int)(((pix_tiles + 1) / 2) * p.ntilesN);          // work items of a pair
+        int nclusters = p.total_tiles < PXL_NUM_SMS / 2 ? p.total_tiles : PXL_NUM_SMS / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * nclusters), 1, 1);
+        cfg.blockDim = dim3(320, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        double* st_ptr = ext ? (double*)ext->bn_stats : nullptr;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, mA, mAlo, mB, mBlo, mO, p, bias, out, st_ptr, g_err_flag);
+        if (e != cudaSuccess) return (int)e;
+        pxl_count_launch_(1);
+        return 0;
     }
     if (use_persist) {
         static bool attr2 = false;
@@ -941,7 +1306,7 @@ __device__ __forceinline__ uint64_t mnmajor_sw128_desc(uint32_t smem_addr, uint3
     return d;
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapDyLo,
                      const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapXLo,
                      const WgParams p, float* __restrict__ dw, int* __restrict__ err_flag) {
@@ -976,7 +1341,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], blockDim.x - 64); }
         mbar_init(&acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1047,8 +1412,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
             const int q = warp & 3;
             const int co = co0 + q * 32 + lane;
             if (p.inkernel) {
-                // raw fp32 slabs -> hi (in place) / lo (second half of the stage); elementwise, layout-agnostic
+                // raw fp32 slabs -> hi (in place) / lo (second half of the stage); elementwise, layout-agnostic.
+                // All warps from 2 up take part (8 of them in the 3xTF32 launch: the split of BOTH operands is
+                // as much work per stage as its 12 MMAs, four warps could not keep up)
                 const int t = threadIdx.x - 64;
+                const int tstride = blockDim.x - 64;
                 const int chunks = per_op / 16;
                 bool okt = true;
                 for (int it = 0; it < iters && okt; ++it) {
@@ -1058,7 +1426,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
                     if (!okt) break;
                     float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
                     float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + per_op);
-                    for (int c = t; c < chunks; c += 128) {
+                    for (int c = t; c < chunks; c += tstride) {
                         const float4 v = hi[c];
                         float4 h, l;
                         const float* vp = &v.x; float* hp = &h.x; float* lp = &l.x;
@@ -1077,7 +1445,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
                 }
             }
-            const bool ok = __all_sync(0xffffffffu, mbar_wait(&acc_bar, 0, err_flag, 13));
+            const bool ok = warp < 6 && __all_sync(0xffffffffu, mbar_wait(&acc_bar, 0, err_flag, 13));
             tc_fence_after();
             if (ok) {
                 const int used = iters < p.nacc ? iters : p.nacc;
@@ -1155,12 +1523,15 @@ extern "C" int pxl_conv_wgrad_tc_launch(const pxl_conv_geom* g, const int* taps,
     } else {
         p.N = g->N; p.OH = g->OH; p.OW = g->OW; mapW = g->OW; mapH = g->OH; mapN = g->N; inW = g->W; inH = g->H;
     }
-    const int maxrows = nsplit == 3 ? 32 : 64;
+    static int cfg_wg_bn_max = -1;
+    if (cfg_wg_bn_max < 0) { const char* e = getenv("PXL_WG_BN_MAX"); cfg_wg_bn_max = e ? atoi(e) : 128; }
+    const bool wide = nsplit == 1 && cfg_wg_bn_max >= 256 && g->Cin >= 256;     // 128 x 256 tile, 32-row stages
+    const int maxrows = nsplit == 3 ? 32 : (wide ? 32 : 64);
     pick_ktile(p.OH, p.OW, flat, maxrows, p.BW, p.BH);
     p.rows = p.BW * p.BH;
     p.rows_alloc = (p.rows + 7) / 8 * 8;
     p.tilesW = (p.OW + p.BW - 1) / p.BW; p.tilesH = (p.OH + p.BH - 1) / p.BH;
-    p.BN = g->Cin > 64 ? 128 : (g->Cin > 32 ? 64 : 32);
+    p.BN = wide ? 256 : (g->Cin > 64 ? 128 : (g->Cin > 32 ? 64 : 32));
     p.nacc = 512 / (p.BN < 32 ? 32 : p.BN); if (p.nacc > 4) p.nacc = 4;
     p.tiles_ci = (g->Cin + p.BN - 1) / p.BN;
     const int tiles_co = (g->Cout + 127) / 128;
@@ -1172,9 +1543,21 @@ extern "C" int pxl_conv_wgrad_tc_launch(const pxl_conv_geom* g, const int* taps,
     // split the pixel range: enough CTAs to fill the GPU, and at most ~4096 pixel rows per CTA so the
     // truncating TMEM accumulation stays at fp32 level (the cross-CTA RED adds round to nearest)
     const int64_t base_ctas = (int64_t)tiles_co * p.tiles_ci * g->ntaps;
-    int64_t split = pxl_cdiv((int64_t)PXL_NUM_SMS * 2, base_ctas);
-    const int64_t by_rows = pxl_cdiv((int64_t)p.ktiles_total * p.rows_alloc, 4096);
-    if (by_rows > split) split = by_rows;
+    int64_t by_rows = pxl_cdiv((int64_t)p.ktiles_total * p.rows_alloc, 4096);
+    if (by_rows < 1) by_rows = 1;
+    // one CTA per SM (the ring takes ~200 KB): pick the pixel split that minimises
+    //   rounds x (main-loop iterations per CTA + a fixed prologue/epilogue cost)
+    // so that the grid fills whole waves instead of leaving a mostly idle last one
+    int64_t split = by_rows, best_cost = -1;
+    int64_t hi = pxl_cdiv((int64_t)PXL_NUM_SMS * 4, base_ctas) + 1;
+    if (hi < by_rows) hi = by_rows;
+    if (hi > p.ktiles_total) hi = p.ktiles_total;
+    for (int64_t sp = by_rows; sp <= hi; ++sp) {
+        const int64_t per = pxl_cdiv(p.ktiles_total, sp);
+        const int64_t ctas = base_ctas * pxl_cdiv(p.ktiles_total, per);
+        const int64_t cost = pxl_cdiv(ctas, PXL_NUM_SMS) * (per + 6);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; split = sp; }
+    }
     if (split > p.ktiles_total) split = p.ktiles_total;
     if (split < 1) split = 1;
     if (split > 65535) split = 65535;
@@ -1206,7 +1589,7 @@ extern "C" int pxl_conv_wgrad_tc_launch(const pxl_conv_geom* g, const int* taps,
     }
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     dim3 grid((unsigned)(tiles_co * p.tiles_ci), (unsigned)g->ntaps, (unsigned)split);
-    conv_wgrad_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mDy, mDyLo, mX, mXLo, p, dw, g_err_flag);
+    conv_wgrad_tc_kernel<<<grid, inkernel ? 320 : 192, smem, (cudaStream_t)stream>>>(mDy, mDyLo, mX, mXLo, p, dw, g_err_flag);
     PXL_CHECK_LAUNCH();
     return 0;
 }

@@ -64,8 +64,8 @@ class BatchNorm2d(nn.Module):
         self.multi_replica_formula = False     # clamp(var, eps) instead of var + eps (batchnorm.py:125)
 
     def forward(self, x, relu=False, residual=None):
-        if self.training:
-            self.num_batches_tracked += 1
+        # num_batches_tracked stays 0 like the reference's: _SynchronizedBatchNorm.forward calls F.batch_norm
+        # directly (batchnorm.py:50-53) and never touches the counter, so its checkpoints always hold 0
         return ops.bn_act(ops.as_cl(x), self.weight, self.bias, self.running_mean, self.running_var,
                           training=self.training, momentum=self.momentum, eps=self.eps, relu=relu,
                           residual=residual, group=self.sync_group if self.training else None,

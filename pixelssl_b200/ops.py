@@ -325,9 +325,37 @@ ACCUM_WGRAD_INPLACE = True      # wgrad kernels add straight into weight.grad (t
 
 def new_step():
     """Called once per training step: invalidates the cached tf32 splits of the weights (the fused
-    SGD kernel updates parameters through raw pointers, invisible to torch's version counters)."""
+    SGD kernel updates parameters through raw pointers, invisible to torch's version counters) and
+    recycles the statistics pool."""
     global _epoch
     _epoch += 1
+    _stat_pool_reset()
+
+
+# Per-channel fp64 accumulators (BN sums, their gradients) are tiny and short-lived (consumed by the next
+# launch on the same stream); carving them out of one pool that is cleared with ONE memset per step
+# replaces ~300 two-kilobyte memsets per MT step.
+_STAT_POOL_DOUBLES = 1 << 20
+_stat_pool = {}
+
+
+def _stat_zeros(n, device):
+    ent = _stat_pool.get(device)
+    if ent is None:
+        ent = _stat_pool[device] = [torch.zeros(_STAT_POOL_DOUBLES, dtype=torch.float64, device=device), 0]
+    buf, cur = ent
+    n_al = (n + 1) & ~1                              # keep 16-byte alignment
+    if cur + n_al > buf.numel():
+        return torch.zeros(n, dtype=torch.float64, device=device)
+    ent[1] = cur + n_al
+    return buf[cur:cur + n]
+
+
+def _stat_pool_reset():
+    for ent in _stat_pool.values():
+        if ent[1]:
+            ent[0][:ent[1]].zero_()
+            ent[1] = 0
 
 
 def split_tf32(x):
@@ -555,7 +583,7 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, out_lanes=0, w
     and picked up by bn_act, which then skips its own statistics pass."""
     sums = None
     if want_bn_stats and _conv_precision != 0 and not out_lanes:
-        sums = torch.zeros(2 * weight.shape[0], dtype=torch.float64, device=x.device)
+        sums = _stat_zeros(2 * weight.shape[0], x.device)
     out = _Conv2d.apply(x, weight, bias, int(stride), int(padding), int(dilation), int(out_lanes), sums)
     if sums is not None and getattr(sums, '_pxl_filled', False):
         out._pxl_bn_sums = sums
@@ -664,7 +692,7 @@ class _BnAct(torch.autograd.Function):
         clamp = 1 if clamp_var else 0
         if training:
             if sums is None:
-                sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+                sums = _stat_zeros(2 * C, dev)
                 call('pxl_bn_stats', _p(x), rows, C, _p(sums), _stream())
             if group is not None:
                 import torch.distributed as dist
@@ -691,7 +719,7 @@ class _BnAct(torch.autograd.Function):
         dev = dy.device
         if not training:
             raise NotImplementedError('backward through eval-mode BN is not on the training path')
-        dsums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+        dsums = _stat_zeros(2 * C, dev)
         call('pxl_bn_bwd_reduce', _p(x), _p(y), _p(dy), _p(coeff[0]), _p(coeff[1]), int(relu), rows, C, _p(dsums), _stream())
         dgamma = torch.empty(C, dtype=torch.float32, device=dev)
         dbeta = torch.empty(C, dtype=torch.float32, device=dev)

@@ -4,6 +4,8 @@ precision 2 (3xTF32: hi/lo operand split, fp32 TMEM accumulation) must agree wit
 relative (measured 5e-7 at K=64 .. 2e-5 at K=2304: the tensor core's fp32 accumulator is not an
 IEEE round-to-nearest adder, so the error grows ~sqrt(K)); precision 1 (single TF32 pass, what cuDNN does by default for the reference on GPU) to
 2e-3.  The mbarrier watchdog must stay silent."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -155,3 +157,17 @@ def test_bn_statistics_fused_in_epilogue(ops, shape, precision):
     y2 = y.clone(memory_format=torch.preserve_format)
     b = ops.bn_act(y2, gm, bt, torch.zeros(Cout).cuda(), torch.ones(Cout).cuda(), training=True, relu=True)
     assert rel(a, b) <= 1e-5
+
+
+def test_cta_pair_kernel_opt_in_subprocess():
+    """The cta_group::2 (CTA-pair) variant is opt-in (PXL_TC_PAIR=1, read once per process): run a few of the
+    parity cases of this file in a child process with it enabled so the path stays verified."""
+    import subprocess
+    import sys
+    env = dict(os.environ, PXL_TC_PAIR='1')
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, '-m', 'pytest', here, '-q', '-x', '-m', 'gpu', '-k',
+                        'not subprocess and (forward_and_dgrad or fused or aspp)'],
+                       env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(here)))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
