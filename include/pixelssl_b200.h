@@ -212,6 +212,9 @@ int pxl_stem_conv7x7s2(const float* img_planar, const float* w, float* out, int 
                        int OH, int OW, void* stream);
 int pxl_stem_conv7x7s2_wgrad(const float* img_planar, const float* dy, float* dw, int N, int H, int W,
                              int OH, int OW, void* stream);
+/* im2col of the stem for the tensor-core path: cols [N*OH*OW][160], k = (r*7+s)*3+c (the weight's physical
+ * order), lanes 147..159 zero; the stem then is a flat 1x1 convolution with 160 input lanes */
+int pxl_stem_im2col(const float* img_planar, float* cols, int N, int H, int W, int OH, int OW, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Optimiser + EMA on flat parameter arenas:

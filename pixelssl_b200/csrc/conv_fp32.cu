@@ -546,3 +546,42 @@ extern "C" int pxl_stem_conv7x7s2_wgrad(const float* img, const float* dy, float
     PXL_CHECK_LAUNCH();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// stem im2col for the tensor-core path: cols[pixel][k], k = (r*7 + s)*3 + c for k < 147 (the physical
+// order of the channels_last [64,3,7,7] weight), zero for 147 <= k < 160.  The 7x7/2 stem then runs as a
+// flat 1x1 convolution with 160 input lanes on tcgen05 (forward and wgrad share the matrix).
+// ------------------------------------------------------------------------------------------
+#define ST_KP 160
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ img, float* __restrict__ cols, int N, int H, int W, int OH, int OW) {
+    const int64_t total4 = (int64_t)N * OH * OW * (ST_KP / 4);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k4 = (int)(i % (ST_KP / 4));
+        const int64_t pix = i / (ST_KP / 4);
+        const int ox = (int)(pix % OW), oy = (int)((pix / OW) % OH), n = (int)(pix / ((int64_t)OW * OH));
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k4 * 4 + e;
+            float x = 0.f;
+            if (k < ST_K) {
+                const int c = k % 3, rs = k / 3, r = rs / 7, sx = rs - r * 7;
+                const int iy = oy * 2 - 3 + r, ix = ox * 2 - 3 + sx;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) x = __ldg(img + ((int64_t)(n * 3 + c) * H + iy) * W + ix);
+            }
+            v[e] = x;
+        }
+        reinterpret_cast<float4*>(cols)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+extern "C" int pxl_stem_im2col(const float* img, float* cols, int N, int H, int W, int OH, int OW, void* stream) {
+    if (!img || !cols || N <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0) return PXL_ERR_BAD_ARG;
+    const int64_t total4 = (int64_t)N * OH * OW * (ST_KP / 4);
+    int64_t blocks = pxl_cdiv(total4, 256 * 4);
+    if (blocks > PXL_NUM_SMS * 16) blocks = PXL_NUM_SMS * 16;
+    stem_im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(img, cols, N, H, W, OH, OW);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}

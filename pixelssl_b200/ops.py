@@ -642,33 +642,56 @@ def aspp(x, weights, biases, dilations=(6, 12, 18, 24)):
 
 
 class _Stem(torch.autograd.Function):
-    """conv 7x7/2 pad 3 on the planar image -> NHWC (resnet.py:69,121); no input gradient."""
+    """conv 7x7/2 pad 3 on the planar image -> NHWC (resnet.py:69,121); no input gradient.
+
+    fp32 mode: the dedicated FFMA kernels.  Tensor-core modes: the image is unfolded once into a
+    [pixels, 160] matrix (147 taps*channels + 13 zero lanes) and the stem runs as a flat 1x1 convolution on
+    tcgen05, forward and wgrad sharing the matrix (19.9 GFLOP each on the 513x513 x16 batch)."""
 
     @staticmethod
-    def forward(ctx, img, weight):
+    def forward(ctx, img, weight, sums):
         _chk(img, 'img'); _chk(weight, 'weight', cl=True)
         N, C, H, W = img.shape
         if C != 3 or tuple(weight.shape) != (64, 3, 7, 7):
             raise ValueError('stem expects a 3-channel image and a [64,3,7,7] weight')
         OH, OW = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         out = torch.empty((N, 64, OH, OW), dtype=torch.float32, device=img.device, memory_format=CL)
-        call('pxl_stem_conv7x7s2', _p(img), _p(weight), _p(out), N, H, W, OH, OW, _stream())
-        ctx.save_for_backward(img)
-        ctx.meta = (N, H, W, OH, OW)
+        prec = _conv_precision
+        ctx.meta = (N, H, W, OH, OW, prec)
+        if prec == 0:
+            call('pxl_stem_conv7x7s2', _p(img), _p(weight), _p(out), N, H, W, OH, OW, _stream())
+            ctx.save_for_backward(img)
+            return out
+        cols = torch.empty((N, 160, OH, OW), dtype=torch.float32, device=img.device, memory_format=CL)
+        call('pxl_stem_im2col', _p(img), _p(cols), N, H, W, OH, OW, _stream())
+        wp = torch.zeros((64, 160), dtype=torch.float32, device=img.device)
+        wp[:, :147] = weight.detach().permute(0, 2, 3, 1).reshape(64, 147)      # physical order of the CL weight
+        conv_raw(cols, wp, None, [0, 0], N, OH, OW, 160, OH, OW, 64, 64, 1, 1, out=out, precision=prec, bn_stats=sums)
+        ctx.save_for_backward(cols if ctx.needs_input_grad[1] else None)
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        (img,) = ctx.saved_tensors
-        N, H, W, OH, OW = ctx.meta
+        (saved,) = ctx.saved_tensors
+        N, H, W, OH, OW, prec = ctx.meta
         dy = as_cl(dy)
-        dw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=dy.device, memory_format=CL).zero_()
-        call('pxl_stem_conv7x7s2_wgrad', _p(img), _p(dy), _p(dw), N, H, W, OH, OW, _stream())
-        return None, dw
+        if prec == 0:
+            dw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=dy.device, memory_format=CL).zero_()
+            call('pxl_stem_conv7x7s2_wgrad', _p(saved), _p(dy), _p(dw), N, H, W, OH, OW, _stream())
+            return None, dw, None
+        dwp = torch.zeros((64, 160), dtype=torch.float32, device=dy.device)
+        conv_wgrad_raw(saved, dy, dwp, [0, 0], N, OH, OW, 160, OH, OW, 64, 64, 1, 1, precision=prec)
+        dw = dwp[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2)              # logical [64,3,7,7], CL strides
+        return None, dw, None
 
 
-def stem_conv(img, weight):
-    return _Stem.apply(img.contiguous(), weight)
+def stem_conv(img, weight, want_bn_stats=False):
+    """want_bn_stats: like conv2d - on the tensor-core path the epilogue accumulates the BN sums."""
+    sums = _stat_zeros(128, img.device) if (want_bn_stats and _conv_precision != 0) else None
+    out = _Stem.apply(img.contiguous(), weight, sums)
+    if sums is not None and getattr(sums, '_pxl_filled', False):
+        out._pxl_bn_sums = sums
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

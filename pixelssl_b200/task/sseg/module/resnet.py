@@ -69,7 +69,7 @@ class ResNet(nn.Module):
         return nn.Sequential(*blocks)
 
     def forward(self, img):
-        x = ops.stem_conv(img, self.conv1.weight)          # planar image -> NHWC
+        x = ops.stem_conv(img, self.conv1.weight, want_bn_stats=self.training)          # planar image -> NHWC
         x = self.bn1(x, relu=True)
         x = ops.maxpool3x3s2(x)
         x = self.layer1(x)

@@ -171,3 +171,30 @@ def test_cta_pair_kernel_opt_in_subprocess():
                        env=env, capture_output=True, text=True, timeout=600,
                        cwd=os.path.dirname(os.path.dirname(here)))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize('precision,tol_y,tol_w', [('tf32x3', 2e-5, 5e-5), ('tf32', 3e-3, 3e-3)])
+@pytest.mark.parametrize('N,H,W', [(2, 65, 65), (1, 97, 129), (2, 40, 36)])
+def test_stem_tensor_core_path(ops, N, H, W, precision, tol_y, tol_w):
+    """7x7/2 stem as im2col (pxl_stem_im2col) + flat 1x1 tcgen05 convolution, forward, weight gradient and the
+    fused BatchNorm sums, against torch CPU fp32 (resnet.py:69,121)."""
+    gs = torch.Generator().manual_seed(H * 7 + W)
+    img = torch.randn(N, 3, H, W, generator=gs)
+    w = torch.randn(64, 3, 7, 7, generator=gs) * 0.1
+    wc = w.clone().requires_grad_(True)
+    yc = F.conv2d(img, wc, stride=2, padding=3)
+    wt = torch.randn(yc.shape, generator=gs)
+    (yc * wt).sum().backward()
+    ops.set_conv_precision(precision)
+    try:
+        wg = w.cuda().contiguous(memory_format=CL).requires_grad_(True)
+        yg = ops.stem_conv(img.cuda(), wg, want_bn_stats=True)
+        (yg * wt.cuda()).sum().backward()
+        sums = yg._pxl_bn_sums.cpu()
+    finally:
+        ops.set_conv_precision('fp32')
+    assert rel(yg.cpu(), yc) <= tol_y
+    assert rel(wg.grad.cpu(), wc.grad) <= tol_w
+    ref = torch.cat((yc.double().sum(dim=(0, 2, 3)), (yc.double() ** 2).sum(dim=(0, 2, 3))))
+    assert rel(sums, ref) <= max(tol_y * 10, 1e-4)
+    assert ops.conv_tc_status() == 0
