@@ -26,7 +26,13 @@ def register_into_pixelssl(pixelssl_module=None, task_sseg_modules=None):
         setattr(pixelssl_module.ssl_algorithm, name, mod)
     if task_sseg_modules is not None:
         from .task.sseg import model as b200_model, criterion as b200_criterion
-        task_model, task_criterion = task_sseg_modules
+        task_model, task_criterion = task_sseg_modules[0], task_sseg_modules[1]
         task_model.deeplabv2 = b200_model.deeplabv2
+        task_model.pspnet = b200_model.pspnet
         task_criterion.sseg_criterion = b200_criterion.sseg_criterion
+        if len(task_sseg_modules) > 2:
+            # optional third module = the task's func.py: validation metrics on the GPU (confusion matrix kernel);
+            # the reference's own TaskFunc keeps working too (it moves the probability map to the host)
+            from .task.sseg import func as b200_func
+            task_sseg_modules[2].task_func = b200_func.task_func
     return pixelssl_module

@@ -194,6 +194,9 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, c
         const float4* xp = reinterpret_cast<const float4*>(x) + c4;
         const float4* yp = reinterpret_cast<const float4*>(y) + c4;
         const float4* dp = reinterpret_cast<const float4*>(dy) + c4;
+        // 4 rows per trip: 12 independent 16-byte loads in flight per thread (these launches are short, the
+        // loop is latency-bound otherwise)
+#pragma unroll 4
         for (int64_t r = r0 + ty; r < r1; r += TY) {
             float4 d = __ldg(dp + r * c4max);
             if (RELU) {
