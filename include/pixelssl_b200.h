@@ -299,6 +299,27 @@ int pxl_confusion_matrix(const float* pred, const float* gt, int n, int C, int64
 int64_t pxl_gaussian_noise_workspace_bytes(int n);
 int pxl_gaussian_noise(float* inp, const float* noise, int n, int64_t CHW, float* workspace, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Cross-GPU BatchNorm statistics over NVLink peer memory (one process per GPU).  Replaces the reference's
+ * per-layer replica synchronisation (sync_batchnorm/batchnorm.py:55-78,90-125; comm.py) and, for the forward,
+ * also _compute_mean_std: one single-CTA kernel pushes this rank's 2C fp64 sums into every rank's mailbox
+ * (CUDA-IPC mapped), waits for all lanes, adds them in rank order and (count > 0) finalizes the layer.
+ *   pxl_peer_alloc/export/open: mailbox of pxl_peer_mailbox_bytes() bytes, 64-byte IPC handle, peer mapping.
+ *   pxl_peer_allreduce_bn: sums [n = 2C] in place; mailboxes = host array of `world` device pointers (own one at
+ *   index rank); seq = 1, 2, 3, ... identical on all ranks; count <= 0: plain all-reduce (backward dsums).
+ * --------------------------------------------------------------------------------------------- */
+int64_t pxl_peer_mailbox_bytes(void);
+int pxl_peer_alloc(void** ptr);
+int pxl_peer_free(void* ptr);
+int pxl_peer_export(void* ptr, unsigned char* handle64);
+int pxl_peer_open(const unsigned char* handle64, void** ptr);
+int pxl_peer_close(void* ptr);
+int pxl_peer_allreduce_bn(double* sums, int n, void* const* mailboxes, int rank, int world, int64_t seq,
+                          double count, int C, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, float momentum, float eps, int clamp_mode, float* mean,
+                          float* invstd, float* scale, float* shift, void* stream);
+int pxl_peer_status(void);
+
 #ifdef __cplusplus
 }
 #endif

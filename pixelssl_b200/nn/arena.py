@@ -166,6 +166,31 @@ class EngineParallel(nn.Module):
             for m in self.module.modules():
                 if isinstance(m, BatchNorm2d) or hasattr(m, 'num_BN'):       # BatchNorm2d and IBNorm
                     m.sync_group = dist.group.WORLD
+            _ensure_peer_exchange(dist.group.WORLD)
 
     def forward(self, *inputs, **kwargs):
         return self.module(*inputs, **kwargs)
+
+
+
+_peer_exchange_state = {}
+
+
+def _ensure_peer_exchange(group):
+    """BN statistics travel over NVLink peer memory (nn/peer.py) when every rank drives a CUDA device of this node
+    and PXL_PEER_BN != 0; otherwise the per-layer NCCL all-reduce stays.  Set up once per process group."""
+    import os
+    import torch.distributed as dist
+    from .. import ops
+    if id(group) in _peer_exchange_state:
+        return _peer_exchange_state[id(group)]
+    px = None
+    want = os.environ.get('PXL_PEER_BN', '1') != '0' and torch.cuda.is_available() and dist.get_backend(group) == 'nccl'
+    flags = [None] * dist.get_world_size(group)
+    dist.all_gather_object(flags, bool(want), group=group)
+    if all(flags) and dist.get_world_size(group) <= 8:
+        from .peer import PeerExchange
+        px = PeerExchange(group)
+        ops.register_peer_exchange(group, px)
+    _peer_exchange_state[id(group)] = px
+    return px

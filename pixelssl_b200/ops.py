@@ -698,6 +698,17 @@ def stem_conv(img, weight, want_bn_stats=False):
 # batch norm (+ReLU, +residual), max-pool
 # ------------------------------------------------------------------------------------------------
 
+# process group (by id) -> nn.peer.PeerExchange; registered by EngineParallel when CUDA IPC is available
+_peer_exchanges = {}
+
+
+def register_peer_exchange(group, exchange):
+    if exchange is None:
+        _peer_exchanges.pop(id(group), None)
+    else:
+        _peer_exchanges[id(group)] = exchange
+
+
 class _BnAct(torch.autograd.Function):
     """_SynchronizedBatchNorm.forward (batchnorm.py:48-78) fused with the ReLU / residual add that
     follow it in Bottleneck.forward (resnet.py:33-48).  ``group``: torch.distributed group whose
@@ -717,13 +728,22 @@ class _BnAct(torch.autograd.Function):
             if sums is None:
                 sums = _stat_zeros(2 * C, dev)
                 call('pxl_bn_stats', _p(x), rows, C, _p(sums), _stream())
+            fused = False
             if group is not None:
                 import torch.distributed as dist
-                dist.all_reduce(sums, group=group)
                 count = float(rows) * dist.get_world_size(group)
                 clamp = 1     # batchnorm.py:125: the multi-replica path clamps var instead of adding eps
-            call('pxl_bn_finalize', _p(sums), count, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
-                 float(momentum), float(eps), clamp, _p(coeff[0]), _p(coeff[1]), _p(coeff[2]), _p(coeff[3]), _stream())
+                px = _peer_exchanges.get(id(group))
+                if px is not None and 2 * C <= 4096:
+                    # NVLink peer-memory exchange fused with the finalize (csrc/peer_exchange.cu)
+                    px.allreduce_bn(sums, (count, C, gamma, beta, running_mean, running_var, momentum, eps, clamp,
+                                           coeff[0], coeff[1], coeff[2], coeff[3]))
+                    fused = True
+                else:
+                    dist.all_reduce(sums, group=group)
+            if not fused:
+                call('pxl_bn_finalize', _p(sums), count, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                     float(momentum), float(eps), clamp, _p(coeff[0]), _p(coeff[1]), _p(coeff[2]), _p(coeff[3]), _stream())
         else:
             call('pxl_bn_eval_coeffs', C, _p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps),
                  _p(coeff[2]), _p(coeff[3]), _stream())
@@ -749,8 +769,12 @@ class _BnAct(torch.autograd.Function):
         # parameter gradients use the LOCAL sums (DDP averages them with the other grads)
         call('pxl_bn_bwd_params', _p(dsums), C, _p(dgamma), _p(dbeta), 0, _stream())
         if group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(dsums, group=group)
+            px = _peer_exchanges.get(id(group))
+            if px is not None and 2 * C <= 4096:
+                px.allreduce_bn(dsums)
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(dsums, group=group)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
         call('pxl_bn_bwd_dx', _p(x), _p(y), _p(dy), _p(coeff[0]), _p(coeff[1]), _p(gamma), _p(dsums), count, int(relu),

@@ -100,3 +100,73 @@ def test_two_gpu_step_equals_single_gpu_big_batch():
     assert rel(b2, b1) <= 1e-4        # synchronised batch statistics
     assert rel(p2, p1) <= 5e-4        # = lr * gradient noise (10x lr on the classifier), measured 1.9e-4
     assert rel(g2, g1) <= 5e-2        # whole-network gradient: fp32-noise floor of this net (see test_gpu_model)
+
+
+def _peer_worker(rank, world, port, q):
+    import ctypes
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from pixelssl_b200.nn.peer import PeerExchange
+        from pixelssl_b200._lib import call
+        px = PeerExchange(dist.group.WORLD)
+        ok = True
+        worst = 0.0
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for it, C in enumerate([4, 64, 256, 2048, 64, 1024, 8, 2048, 512, 64]):     # > NSLOT exchanges: slots recycle
+            g = torch.Generator().manual_seed(100 * it + rank)
+            rows = 1000.0
+            x = torch.randn(int(rows), C, generator=g, dtype=torch.float64) * (1 + rank) + 0.3 * rank
+            local = torch.cat((x.sum(0), (x * x).sum(0))).cuda()
+            want = local.clone()
+            dist.all_reduce(want)                                   # NCCL result as the yardstick
+            # plain exchange (backward dsums)
+            got = px.allreduce_bn(local.clone())
+            worst = max(worst, float((got - want).abs().max() / want.abs().max()))
+            # fused with finalize
+            gamma = torch.rand(C, generator=g).cuda() + 0.5
+            beta = torch.randn(C, generator=g).cuda()
+            rm_a, rv_a = torch.zeros(C).cuda(), torch.ones(C).cuda()
+            rm_b, rv_b = rm_a.clone(), rv_a.clone()
+            ca = torch.empty(4, C).cuda()
+            cb = torch.empty(4, C).cuda()
+            s2 = px.allreduce_bn(local.clone(), (rows * world, C, gamma, beta, rm_a, rv_a, 0.1, 1e-5, 1, ca[0], ca[1], ca[2], ca[3]))
+            call('pxl_bn_finalize', P(s2), rows * world, C, P(gamma), P(beta), P(rm_b), P(rv_b), 0.1, 1e-5, 1,
+                 P(cb[0]), P(cb[1]), P(cb[2]), P(cb[3]), st)
+            torch.cuda.synchronize()
+            ok = ok and torch.equal(ca, cb) and torch.equal(rm_a, rm_b) and torch.equal(rv_a, rv_b)
+            # every rank must hold bit-identical totals
+            both = [torch.empty_like(s2) for _ in range(world)]
+            dist.all_gather(both, s2)
+            ok = ok and all(torch.equal(both[0], b) for b in both)
+        status = px.status()
+        dist.barrier()
+        px.close()
+        if rank == 0:
+            q.put((ok, worst, status))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_memory_bn_exchange_two_gpus():
+    """csrc/peer_exchange.cu: the NVLink mailbox all-reduce equals NCCL's (fp64, 1e-15), its fused finalize equals
+    pxl_bn_finalize bit for bit, all ranks get identical totals, slots recycle, watchdog silent."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, worst, status = q.get(timeout=200)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert status == 0
+    assert worst <= 1e-14, worst
+    assert ok
