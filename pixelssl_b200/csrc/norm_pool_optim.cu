@@ -16,7 +16,13 @@ static RedLayout red_layout(int64_t rows, int C) {
     L.TX = c4 >= 32 ? 32 : (c4 >= 16 ? 16 : (c4 >= 8 ? 8 : (c4 >= 4 ? 4 : (c4 >= 2 ? 2 : 1))));
     L.TY = 256 / L.TX;
     L.colBlocks = (int)pxl_cdiv(c4, L.TX);
+    // 8 CTAs per SM in total, but every CTA ends with 2 fp64 atomics per channel: cap the row blocks (= atomics per
+    // address) at one per 256 KB of tensor, at least one per SM - on a 17 MB layer ~550 contended atomics per
+    // address cost more than streaming the layer (tools/bench_bn.py: 45 us vs 20 us)
     int64_t target = (int64_t)PXL_NUM_SMS * 8 / L.colBlocks;
+    int64_t cap = rows * C / 65536;
+    if (cap < PXL_NUM_SMS) cap = PXL_NUM_SMS;
+    if (target > cap) target = cap;
     if (target < 1) target = 1;
     int64_t rpb = pxl_cdiv(rows, target);
     if (rpb < L.TY * 4) rpb = L.TY * 4;
@@ -66,6 +72,7 @@ bn_stats_kernel(const float* __restrict__ x, int64_t rows, int C, int TX, int TY
     float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
     if (c4 < c4max) {
         const float4* xp = reinterpret_cast<const float4*>(x) + c4;
+#pragma unroll 8
         for (int64_t r = r0 + ty; r < r1; r += TY) {
             float4 v = __ldg(xp + r * c4max);
             s = f4add(s, v);
@@ -225,35 +232,48 @@ extern "C" int pxl_bn_bwd_reduce(const float* x, const float* y, const float* dy
     return 0;
 }
 
+// dx = A*dz + B*x + K per channel with A = gamma*invstd, B = -A*invstd*mean(dz*xhat), K = -A*mean(dz) - B*mean:
+// a thread owns 4 fixed channels (coefficients in registers, computed once from the fp64 sums) and walks down
+// the rows, 4 rows per trip.
 template <bool RELU, bool DRES>
 __global__ void __launch_bounds__(256)
 bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, const float4* __restrict__ dy,
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                  const double* __restrict__ dsums, double inv_count, float4* __restrict__ dx, float4* __restrict__ dres,
-                 int64_t n4, int C) {
-    const int c4max = C >> 2;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const int c = 4 * (int)(i % c4max);
+                 int64_t rows, int C, int TX, int TY, int64_t rowsPerBlock) {
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
+    if (c4 >= c4max) return;
+    float A[4], B[4], K[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = 4 * c4 + k;
+        const float m = __ldg(mean + c), is = __ldg(invstd + c), g = __ldg(gamma + c);
+        const float mdz = (float)(__ldg(dsums + c) * inv_count);
+        const float mdzx = (float)(__ldg(dsums + C + c) * inv_count);
+        A[k] = g * is;
+        B[k] = -A[k] * is * mdzx;
+        K[k] = -A[k] * mdz - B[k] * m;
+    }
+    const int64_t r0 = (int64_t)blockIdx.x * rowsPerBlock;
+    const int64_t r1 = min(rows, r0 + rowsPerBlock);
+#pragma unroll 4
+    for (int64_t r = r0 + ty; r < r1; r += TY) {
+        const int64_t i = r * c4max + c4;
         float4 d = __ldcs(dy + i);
         if (RELU) {
-            float4 o = __ldcs(y + i);
+            const float4 o = __ldcs(y + i);
             d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
             d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
         }
         if (DRES) dres[i] = d;
         const float4 v = __ldcs(x + i);
-        float4 r;
-        float* rp = &r.x; const float* dp = &d.x; const float* vp = &v.x;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float m = __ldg(mean + c + k), is = __ldg(invstd + c + k), g = __ldg(gamma + c + k);
-            const float mdz = (float)(__ldg(dsums + c + k) * inv_count);
-            const float mdzx = (float)(__ldg(dsums + C + c + k) * inv_count);
-            const float xh = (vp[k] - m) * is;
-            rp[k] = g * is * (dp[k] - mdz - xh * mdzx);
-        }
-        dx[i] = r;
+        float4 o4;
+        o4.x = fmaf(A[0], d.x, fmaf(B[0], v.x, K[0]));
+        o4.y = fmaf(A[1], d.y, fmaf(B[1], v.y, K[1]));
+        o4.z = fmaf(A[2], d.z, fmaf(B[2], v.z, K[2]));
+        o4.w = fmaf(A[3], d.w, fmaf(B[3], v.w, K[3]));
+        dx[i] = o4;
     }
 }
 
@@ -261,16 +281,27 @@ extern "C" int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, co
                              const float* invstd, const float* gamma, const double* dsums, double count,
                              int relu, float* dx, float* dres, int64_t rows, int C, void* stream) {
     if (!x || !dy || !mean || !invstd || !gamma || !dsums || !dx || rows <= 0 || C <= 0 || (C & 3) || (relu && !y)) return PXL_ERR_BAD_ARG;
-    const int64_t n4 = rows * (C / 4);
-    int blocks = (int)(pxl_cdiv(n4, 256 * 2) < PXL_NUM_SMS * 8 ? pxl_cdiv(n4, 256 * 2) : PXL_NUM_SMS * 8);
+    // same column/row decomposition as the reductions, without their atomics: 8 CTAs per SM
+    RedLayout L;
+    const int c4 = C / 4;
+    L.TX = c4 >= 32 ? 32 : (c4 >= 16 ? 16 : (c4 >= 8 ? 8 : (c4 >= 4 ? 4 : (c4 >= 2 ? 2 : 1))));
+    L.TY = 256 / L.TX;
+    L.colBlocks = (int)pxl_cdiv(c4, L.TX);
+    int64_t target = (int64_t)PXL_NUM_SMS * 8 / L.colBlocks;
+    if (target < 1) target = 1;
+    int64_t rpb = pxl_cdiv(rows, target);
+    if (rpb < L.TY * 4) rpb = L.TY * 4;
+    L.rowsPerBlock = rpb;
+    L.rowBlocks = (int)pxl_cdiv(rows, rpb);
+    dim3 grid(L.rowBlocks, L.colBlocks);
     cudaStream_t st = (cudaStream_t)stream;
     const float4 *x4 = (const float4*)x, *y4 = (const float4*)y, *d4 = (const float4*)dy;
     float4 *o4 = (float4*)dx, *r4 = (float4*)dres;
     const double ic = 1.0 / count;
-    if (relu && dres) bn_bwd_dx_kernel<true, true><<<blocks, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, n4, C);
-    else if (relu) bn_bwd_dx_kernel<true, false><<<blocks, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, n4, C);
-    else if (dres) bn_bwd_dx_kernel<false, true><<<blocks, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, n4, C);
-    else bn_bwd_dx_kernel<false, false><<<blocks, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, n4, C);
+    if (relu && dres) bn_bwd_dx_kernel<true, true><<<grid, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock);
+    else if (relu) bn_bwd_dx_kernel<true, false><<<grid, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock);
+    else if (dres) bn_bwd_dx_kernel<false, true><<<grid, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock);
+    else bn_bwd_dx_kernel<false, false><<<grid, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock);
     PXL_CHECK_LAUNCH();
     return 0;
 }
