@@ -120,12 +120,16 @@ int pxl_bn_apply(const float* x, const float* scale, const float* shift, const f
  *   reduce: dsums[0:C] = sum dz, dsums[C:2C] = sum dz*xhat with dz = dy * (y>0 if relu) (fp64;
  *   caller zeroes; all-reduced for N>1);  writes nothing else.
  *   dx:  dx = gamma*invstd*(dz - dsums0/count - xhat*dsums1/count); dres (nullable) = dz.
- *   dgamma += dsums1, dbeta += dsums0 are produced by pxl_bn_bwd_params. */
+ *   dgamma += dsums1, dbeta += dsums0 are produced by pxl_bn_bwd_params.
+ *   relu with y == NULL: the mask is recomputed as fmaf(x, scale, shift) > 0 (exactly what pxl_bn_apply
+ *   evaluated; only valid without a residual) - saves reading y. */
 int pxl_bn_bwd_reduce(const float* x, const float* y, const float* dy, const float* mean,
-                      const float* invstd, int relu, int64_t rows, int C, double* dsums, void* stream);
+                      const float* invstd, int relu, int64_t rows, int C, double* dsums,
+                      const float* scale, const float* shift, void* stream);
 int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, const float* mean,
                   const float* invstd, const float* gamma, const double* dsums, double count,
-                  int relu, float* dx, float* dres, int64_t rows, int C, void* stream);
+                  int relu, float* dx, float* dres, int64_t rows, int C,
+                  const float* scale, const float* shift, void* stream);
 int pxl_bn_bwd_params(const double* dsums, int C, float* dgamma, float* dbeta, int accumulate,
                       void* stream);
 

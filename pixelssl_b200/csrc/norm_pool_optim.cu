@@ -185,11 +185,13 @@ extern "C" int pxl_bn_apply(const float* x, const float* scale, const float* shi
 //   reduce: dsums[0:C] += sum dz ; dsums[C:2C] += sum dz * xhat
 //   dx = gamma*invstd * (dz - dsums0/count - xhat*dsums1/count)
 // ------------------------------------------------------------------------------------------
-template <bool RELU>
+// RELU: 0 none, 1 mask from y, 2 mask recomputed from x (fmaf(x, scale, shift) > 0, no residual)
+template <int RELU>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
                      const float* __restrict__ mean, const float* __restrict__ invstd, int64_t rows, int C,
-                     int TX, int TY, int64_t rowsPerBlock, double* __restrict__ dsums) {
+                     int TX, int TY, int64_t rowsPerBlock, double* __restrict__ dsums,
+                     const float* __restrict__ scale, const float* __restrict__ shift) {
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
     const int64_t r0 = (int64_t)blockIdx.x * rowsPerBlock;
@@ -201,17 +203,22 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, c
         const float4* xp = reinterpret_cast<const float4*>(x) + c4;
         const float4* yp = reinterpret_cast<const float4*>(y) + c4;
         const float4* dp = reinterpret_cast<const float4*>(dy) + c4;
+        float4 sc = make_float4(0, 0, 0, 0), sh = sc;
+        if (RELU == 2) { sc = __ldg(reinterpret_cast<const float4*>(scale) + c4); sh = __ldg(reinterpret_cast<const float4*>(shift) + c4); }
         // 4 rows per trip: 12 independent 16-byte loads in flight per thread (these launches are short, the
         // loop is latency-bound otherwise)
 #pragma unroll 4
         for (int64_t r = r0 + ty; r < r1; r += TY) {
             float4 d = __ldg(dp + r * c4max);
-            if (RELU) {
+            float4 v = __ldg(xp + r * c4max);
+            if (RELU == 1) {
                 float4 o = __ldg(yp + r * c4max);
                 d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
                 d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
+            } else if (RELU == 2) {
+                d.x = fmaf(v.x, sc.x, sh.x) > 0.f ? d.x : 0.f; d.y = fmaf(v.y, sc.y, sh.y) > 0.f ? d.y : 0.f;
+                d.z = fmaf(v.z, sc.z, sh.z) > 0.f ? d.z : 0.f; d.w = fmaf(v.w, sc.w, sh.w) > 0.f ? d.w : 0.f;
             }
-            float4 v = __ldg(xp + r * c4max);
             float4 xh = make_float4((v.x - m.x) * is.x, (v.y - m.y) * is.y, (v.z - m.z) * is.z, (v.w - m.w) * is.w);
             s = f4add(s, d);
             q = f4add(q, f4mul(d, xh));
@@ -221,13 +228,15 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, c
 }
 
 extern "C" int pxl_bn_bwd_reduce(const float* x, const float* y, const float* dy, const float* mean,
-                                 const float* invstd, int relu, int64_t rows, int C, double* dsums, void* stream) {
-    if (!x || !dy || !mean || !invstd || !dsums || rows <= 0 || C <= 0 || (C & 3) || (relu && !y)) return PXL_ERR_BAD_ARG;
+                                 const float* invstd, int relu, int64_t rows, int C, double* dsums,
+                                 const float* scale, const float* shift, void* stream) {
+    if (!x || !dy || !mean || !invstd || !dsums || rows <= 0 || C <= 0 || (C & 3) || (relu && !y && !(scale && shift))) return PXL_ERR_BAD_ARG;
     RedLayout L = red_layout(rows, C);
     dim3 grid(L.rowBlocks, L.colBlocks);
     cudaStream_t st = (cudaStream_t)stream;
-    if (relu) bn_bwd_reduce_kernel<true><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums);
-    else bn_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums);
+    if (relu && y) bn_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift);
+    else if (relu) bn_bwd_reduce_kernel<2><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift);
+    else bn_bwd_reduce_kernel<0><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift);
     PXL_CHECK_LAUNCH();
     return 0;
 }
@@ -235,12 +244,13 @@ extern "C" int pxl_bn_bwd_reduce(const float* x, const float* y, const float* dy
 // dx = A*dz + B*x + K per channel with A = gamma*invstd, B = -A*invstd*mean(dz*xhat), K = -A*mean(dz) - B*mean:
 // a thread owns 4 fixed channels (coefficients in registers, computed once from the fp64 sums) and walks down
 // the rows, 4 rows per trip.
-template <bool RELU, bool DRES>
+template <int RELU, bool DRES>
 __global__ void __launch_bounds__(256)
 bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, const float4* __restrict__ dy,
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                  const double* __restrict__ dsums, double inv_count, float4* __restrict__ dx, float4* __restrict__ dres,
-                 int64_t rows, int C, int TX, int TY, int64_t rowsPerBlock) {
+                 int64_t rows, int C, int TX, int TY, int64_t rowsPerBlock,
+                 const float* __restrict__ scale, const float* __restrict__ shift) {
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
     if (c4 >= c4max) return;
@@ -255,19 +265,24 @@ bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, con
         B[k] = -A[k] * is * mdzx;
         K[k] = -A[k] * mdz - B[k] * m;
     }
+    float4 sc = make_float4(0, 0, 0, 0), sh = sc;
+    if (RELU == 2) { sc = __ldg(reinterpret_cast<const float4*>(scale) + c4); sh = __ldg(reinterpret_cast<const float4*>(shift) + c4); }
     const int64_t r0 = (int64_t)blockIdx.x * rowsPerBlock;
     const int64_t r1 = min(rows, r0 + rowsPerBlock);
 #pragma unroll 4
     for (int64_t r = r0 + ty; r < r1; r += TY) {
         const int64_t i = r * c4max + c4;
         float4 d = __ldcs(dy + i);
-        if (RELU) {
+        const float4 v = __ldcs(x + i);
+        if (RELU == 1) {
             const float4 o = __ldcs(y + i);
             d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
             d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
+        } else if (RELU == 2) {
+            d.x = fmaf(v.x, sc.x, sh.x) > 0.f ? d.x : 0.f; d.y = fmaf(v.y, sc.y, sh.y) > 0.f ? d.y : 0.f;
+            d.z = fmaf(v.z, sc.z, sh.z) > 0.f ? d.z : 0.f; d.w = fmaf(v.w, sc.w, sh.w) > 0.f ? d.w : 0.f;
         }
         if (DRES) dres[i] = d;
-        const float4 v = __ldcs(x + i);
         float4 o4;
         o4.x = fmaf(A[0], d.x, fmaf(B[0], v.x, K[0]));
         o4.y = fmaf(A[1], d.y, fmaf(B[1], v.y, K[1]));
@@ -279,8 +294,9 @@ bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, con
 
 extern "C" int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, const float* mean,
                              const float* invstd, const float* gamma, const double* dsums, double count,
-                             int relu, float* dx, float* dres, int64_t rows, int C, void* stream) {
-    if (!x || !dy || !mean || !invstd || !gamma || !dsums || !dx || rows <= 0 || C <= 0 || (C & 3) || (relu && !y)) return PXL_ERR_BAD_ARG;
+                             int relu, float* dx, float* dres, int64_t rows, int C,
+                             const float* scale, const float* shift, void* stream) {
+    if (!x || !dy || !mean || !invstd || !gamma || !dsums || !dx || rows <= 0 || C <= 0 || (C & 3) || (relu && !y && !(scale && shift))) return PXL_ERR_BAD_ARG;
     // same column/row decomposition as the reductions, without their atomics: 8 CTAs per SM
     RedLayout L;
     const int c4 = C / 4;
@@ -298,10 +314,15 @@ extern "C" int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, co
     const float4 *x4 = (const float4*)x, *y4 = (const float4*)y, *d4 = (const float4*)dy;
     float4 *o4 = (float4*)dx, *r4 = (float4*)dres;
     const double ic = 1.0 / count;
-    if (relu && dres) bn_bwd_dx_kernel<true, true><<<grid, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock);
-    else if (relu) bn_bwd_dx_kernel<true, false><<<grid, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock);
-    else if (dres) bn_bwd_dx_kernel<false, true><<<grid, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock);
-    else bn_bwd_dx_kernel<false, false><<<grid, 256, 0, st>>>(x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock);
+#define PXL_DX_ARGS x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock, scale, shift
+    const int mode = relu ? (y ? 1 : 2) : 0;
+    if (mode == 1 && dres) bn_bwd_dx_kernel<1, true><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
+    else if (mode == 1) bn_bwd_dx_kernel<1, false><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
+    else if (mode == 2 && dres) bn_bwd_dx_kernel<2, true><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
+    else if (mode == 2) bn_bwd_dx_kernel<2, false><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
+    else if (dres) bn_bwd_dx_kernel<0, true><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
+    else bn_bwd_dx_kernel<0, false><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
+#undef PXL_DX_ARGS
     PXL_CHECK_LAUNCH();
     return 0;
 }

@@ -750,7 +750,7 @@ class _BnAct(torch.autograd.Function):
         if residual is not None:
             _chk(residual, 'residual', cl=True)
         call('pxl_bn_apply', _p(x), _p(coeff[2]), _p(coeff[3]), _p(residual), int(relu), _p(y), rows, C, _stream())
-        ctx.save_for_backward(x, y if relu else None, gamma, coeff, running_var)
+        ctx.save_for_backward(x, y if (relu and residual is not None) else None, gamma, coeff, running_var)
         ctx.meta = (rows, C, count, bool(relu), residual is not None, bool(training), float(eps), group)
         return y
 
@@ -763,7 +763,10 @@ class _BnAct(torch.autograd.Function):
         if not training:
             raise NotImplementedError('backward through eval-mode BN is not on the training path')
         dsums = _stat_zeros(2 * C, dev)
-        call('pxl_bn_bwd_reduce', _p(x), _p(y), _p(dy), _p(coeff[0]), _p(coeff[1]), int(relu), rows, C, _p(dsums), _stream())
+        # ReLU without residual: the mask is recomputed from x (same fmaf as the forward) instead of reading y
+        ymask = y if (relu and has_res) else None
+        call('pxl_bn_bwd_reduce', _p(x), _p(ymask), _p(dy), _p(coeff[0]), _p(coeff[1]), int(relu), rows, C, _p(dsums),
+             _p(coeff[2]), _p(coeff[3]), _stream())
         dgamma = torch.empty(C, dtype=torch.float32, device=dev)
         dbeta = torch.empty(C, dtype=torch.float32, device=dev)
         # parameter gradients use the LOCAL sums (DDP averages them with the other grads)
@@ -777,8 +780,8 @@ class _BnAct(torch.autograd.Function):
                 dist.all_reduce(dsums, group=group)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
-        call('pxl_bn_bwd_dx', _p(x), _p(y), _p(dy), _p(coeff[0]), _p(coeff[1]), _p(gamma), _p(dsums), count, int(relu),
-             _p(dx), _p(dres), rows, C, _stream())
+        call('pxl_bn_bwd_dx', _p(x), _p(ymask), _p(dy), _p(coeff[0]), _p(coeff[1]), _p(gamma), _p(dsums), count, int(relu),
+             _p(dx), _p(dres), rows, C, _p(coeff[2]), _p(coeff[3]), _stream())
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None, None
 
 
@@ -1127,7 +1130,7 @@ class _IBNorm(torch.autograd.Function):
         dsums = torch.zeros((b, 2 * C), dtype=torch.float64, device=dev)
         for i in range(b):
             call('pxl_bn_bwd_reduce', _p(x[i]), _p(None), _p(dy[i]), _p(coeff[i, 0]), _p(coeff[i, 1]), 0, hw, C,
-                 _p(dsums[i]), _stream())
+                 _p(dsums[i]), _p(None), _p(None), _stream())
         tot = dsums.sum(0)
         dgamma = tot[C:C + nb].to(torch.float32)
         dbeta = tot[:nb].to(torch.float32)
@@ -1141,7 +1144,7 @@ class _IBNorm(torch.autograd.Function):
         dx = torch.empty_like(x)
         for i in range(b):
             call('pxl_bn_bwd_dx', _p(x[i]), _p(None), _p(dy[i]), _p(coeff[i, 0]), _p(coeff[i, 1]), _p(gamma), _p(mix[i]),
-                 float(hw), 0, _p(dx[i]), _p(None), hw, C, _stream())
+                 float(hw), 0, _p(dx[i]), _p(None), hw, C, _p(None), _p(None), _stream())
         return dx, dgamma, dbeta, None, None, None, None, None, None
 
 
