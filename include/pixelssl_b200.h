@@ -116,6 +116,11 @@ int pxl_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float
                        const float* running_var, float eps, float* scale, float* shift, void* stream);
 int pxl_bn_apply(const float* x, const float* scale, const float* shift, const float* residual,
                  int relu, float* y, int64_t rows, int C, void* stream);
+/* training forward in one launch: pxl_bn_finalize + pxl_bn_apply (sums already hold the batch totals). */
+int pxl_bn_finalize_apply(const float* x, const double* sums, double count, const float* gamma,
+                          const float* beta, float* running_mean, float* running_var, float momentum,
+                          float eps, int clamp_mode, float* mean, float* invstd, float* scale, float* shift,
+                          const float* residual, int relu, float* y, int64_t rows, int C, void* stream);
 /* backward of y = relu?(bn(x) + residual?):
  *   reduce: dsums[0:C] = sum dz, dsums[C:2C] = sum dz*xhat with dz = dy * (y>0 if relu) (fp64;
  *   caller zeroes; all-reduced for N>1);  writes nothing else.
@@ -129,7 +134,9 @@ int pxl_bn_bwd_reduce(const float* x, const float* y, const float* dy, const flo
 int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, const float* mean,
                   const float* invstd, const float* gamma, const double* dsums, double count,
                   int relu, float* dx, float* dres, int64_t rows, int C,
-                  const float* scale, const float* shift, void* stream);
+                  const float* scale, const float* shift, float* dgamma_acc, float* dbeta_acc, void* stream);
+/* dgamma_acc / dbeta_acc (both or neither): dgamma_acc[c] += dsums[C+c], dbeta_acc[c] += dsums[c] by the same launch
+ * (single-GPU path: dsums are the local sums; replaces pxl_bn_bwd_params + the optimizer-side accumulation). */
 int pxl_bn_bwd_params(const double* dsums, int C, float* dgamma, float* dbeta, int accumulate,
                       void* stream);
 

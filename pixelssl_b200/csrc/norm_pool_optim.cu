@@ -181,6 +181,93 @@ extern "C" int pxl_bn_apply(const float* x, const float* scale, const float* shi
 }
 
 // ------------------------------------------------------------------------------------------
+// training forward in one launch: finalize (the arithmetic of bn_finalize_kernel, per thread for its 4 channels,
+// from the fp64 sums) + apply.  The CTAs of row block 0 also store mean / inv_std / scale / shift for the backward
+// and update the running statistics.  Same 2-D decomposition as bn_bwd_dx_kernel.
+// ------------------------------------------------------------------------------------------
+template <bool RES, bool RELU>
+__global__ void __launch_bounds__(256)
+bn_finalize_apply_kernel(const float4* __restrict__ x, const double* __restrict__ sums, double count,
+                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                         float* running_mean, float* running_var, float momentum, float eps, int clamp_mode,
+                         float* mean, float* invstd, float* scale, float* shift,
+                         const float4* __restrict__ res, float4* __restrict__ y,
+                         int64_t rows, int C, int TX, int TY, int64_t rowsPerBlock) {
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
+    if (c4 >= c4max) return;
+    float sc[4], sh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = 4 * c4 + k;
+        const double m = __ldg(sums + c) / count;
+        double var = __ldg(sums + C + c) / count - m * m;     // biased
+        if (var < 0.0) var = 0.0;
+        const float mf = (float)m;
+        float is;
+        if (clamp_mode) is = 1.0f / sqrtf(fmaxf((float)var, eps));
+        else is = 1.0f / sqrtf((float)var + eps);
+        sc[k] = __ldg(gamma + c) * is;
+        sh[k] = __ldg(beta + c) - mf * sc[k];
+        if (blockIdx.x == 0 && ty == 0) {
+            if (running_mean) {
+                const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mf;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+            }
+            mean[c] = mf; invstd[c] = is; scale[c] = sc[k]; shift[c] = sh[k];
+        }
+    }
+    const int64_t r0 = (int64_t)blockIdx.x * rowsPerBlock;
+    const int64_t r1 = min(rows, r0 + rowsPerBlock);
+#pragma unroll 4
+    for (int64_t r = r0 + ty; r < r1; r += TY) {
+        const int64_t i = r * c4max + c4;
+        float4 v = __ldcs(x + i);
+        v.x = fmaf(v.x, sc[0], sh[0]); v.y = fmaf(v.y, sc[1], sh[1]);
+        v.z = fmaf(v.z, sc[2], sh[2]); v.w = fmaf(v.w, sc[3], sh[3]);
+        if (RES) { const float4 q = __ldcs(res + i); v = f4add(v, q); }
+        if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        y[i] = v;
+    }
+}
+
+static RedLayout stream_layout(int64_t rows, int C) {
+    RedLayout L;
+    const int c4 = C / 4;
+    L.TX = c4 >= 32 ? 32 : (c4 >= 16 ? 16 : (c4 >= 8 ? 8 : (c4 >= 4 ? 4 : (c4 >= 2 ? 2 : 1))));
+    L.TY = 256 / L.TX;
+    L.colBlocks = (int)pxl_cdiv(c4, L.TX);
+    int64_t target = (int64_t)PXL_NUM_SMS * 8 / L.colBlocks;
+    if (target < 1) target = 1;
+    int64_t rpb = pxl_cdiv(rows, target);
+    if (rpb < L.TY * 4) rpb = L.TY * 4;
+    L.rowsPerBlock = rpb;
+    L.rowBlocks = (int)pxl_cdiv(rows, rpb);
+    return L;
+}
+
+extern "C" int pxl_bn_finalize_apply(const float* x, const double* sums, double count, const float* gamma,
+                                     const float* beta, float* running_mean, float* running_var, float momentum,
+                                     float eps, int clamp_mode, float* mean, float* invstd, float* scale, float* shift,
+                                     const float* residual, int relu, float* y, int64_t rows, int C, void* stream) {
+    if (!x || !sums || !gamma || !beta || !mean || !invstd || !scale || !shift || !y || rows <= 0 || C <= 0 || (C & 3) || count <= 0)
+        return PXL_ERR_BAD_ARG;
+    const RedLayout L = stream_layout(rows, C);
+    dim3 grid(L.rowBlocks, L.colBlocks);
+    cudaStream_t st = (cudaStream_t)stream;
+#define PXL_FA_ARGS (const float4*)x, sums, count, gamma, beta, running_mean, running_var, momentum, eps, clamp_mode, mean, invstd, \
+                    scale, shift, (const float4*)residual, (float4*)y, rows, C, L.TX, L.TY, L.rowsPerBlock
+    if (residual && relu) bn_finalize_apply_kernel<true, true><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
+    else if (residual) bn_finalize_apply_kernel<true, false><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
+    else if (relu) bn_finalize_apply_kernel<false, true><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
+    else bn_finalize_apply_kernel<false, false><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
+#undef PXL_FA_ARGS
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // backward.  dz = dy * (y > 0) when the ReLU was fused.
 //   reduce: dsums[0:C] += sum dz ; dsums[C:2C] += sum dz * xhat
 //   dx = gamma*invstd * (dz - dsums0/count - xhat*dsums1/count)
@@ -250,10 +337,20 @@ bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, con
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                  const double* __restrict__ dsums, double inv_count, float4* __restrict__ dx, float4* __restrict__ dres,
                  int64_t rows, int C, int TX, int TY, int64_t rowsPerBlock,
-                 const float* __restrict__ scale, const float* __restrict__ shift) {
+                 const float* __restrict__ scale, const float* __restrict__ shift,
+                 float* dgamma_acc, float* dbeta_acc) {
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
     if (c4 >= c4max) return;
+    if (dgamma_acc && blockIdx.x == 0 && ty == 0) {
+        // parameter gradients (what bn_bwd_params_kernel does), accumulated straight into gamma.grad / beta.grad
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = 4 * c4 + k;
+            dbeta_acc[c] += (float)__ldg(dsums + c);
+            dgamma_acc[c] += (float)__ldg(dsums + C + c);
+        }
+    }
     float A[4], B[4], K[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -295,26 +392,16 @@ bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, con
 extern "C" int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, const float* mean,
                              const float* invstd, const float* gamma, const double* dsums, double count,
                              int relu, float* dx, float* dres, int64_t rows, int C,
-                             const float* scale, const float* shift, void* stream) {
+                             const float* scale, const float* shift, float* dgamma_acc, float* dbeta_acc, void* stream) {
     if (!x || !dy || !mean || !invstd || !gamma || !dsums || !dx || rows <= 0 || C <= 0 || (C & 3) || (relu && !y && !(scale && shift))) return PXL_ERR_BAD_ARG;
-    // same column/row decomposition as the reductions, without their atomics: 8 CTAs per SM
-    RedLayout L;
-    const int c4 = C / 4;
-    L.TX = c4 >= 32 ? 32 : (c4 >= 16 ? 16 : (c4 >= 8 ? 8 : (c4 >= 4 ? 4 : (c4 >= 2 ? 2 : 1))));
-    L.TY = 256 / L.TX;
-    L.colBlocks = (int)pxl_cdiv(c4, L.TX);
-    int64_t target = (int64_t)PXL_NUM_SMS * 8 / L.colBlocks;
-    if (target < 1) target = 1;
-    int64_t rpb = pxl_cdiv(rows, target);
-    if (rpb < L.TY * 4) rpb = L.TY * 4;
-    L.rowsPerBlock = rpb;
-    L.rowBlocks = (int)pxl_cdiv(rows, rpb);
+    const RedLayout L = stream_layout(rows, C);     // the reductions' decomposition without their atomics
     dim3 grid(L.rowBlocks, L.colBlocks);
     cudaStream_t st = (cudaStream_t)stream;
     const float4 *x4 = (const float4*)x, *y4 = (const float4*)y, *d4 = (const float4*)dy;
     float4 *o4 = (float4*)dx, *r4 = (float4*)dres;
     const double ic = 1.0 / count;
-#define PXL_DX_ARGS x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock, scale, shift
+#define PXL_DX_ARGS x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock, scale, shift, \
+                    (dgamma_acc && dbeta_acc) ? dgamma_acc : nullptr, dbeta_acc
     const int mode = relu ? (y ? 1 : 2) : 0;
     if (mode == 1 && dres) bn_bwd_dx_kernel<1, true><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
     else if (mode == 1) bn_bwd_dx_kernel<1, false><<<grid, 256, 0, st>>>(PXL_DX_ARGS);

@@ -724,6 +724,7 @@ class _BnAct(torch.autograd.Function):
         coeff = torch.empty((4, C), dtype=torch.float32, device=dev)     # mean, invstd, scale, shift
         count = float(rows)
         clamp = 1 if clamp_var else 0
+        applied = False
         if training:
             if sums is None:
                 sums = _stat_zeros(2 * C, dev)
@@ -741,22 +742,31 @@ class _BnAct(torch.autograd.Function):
                     fused = True
                 else:
                     dist.all_reduce(sums, group=group)
-            if not fused:
+            if residual is not None:
+                _chk(residual, 'residual', cl=True)
+            if group is None:
+                # local statistics: finalize + apply in one launch
+                call('pxl_bn_finalize_apply', _p(x), _p(sums), count, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                     float(momentum), float(eps), clamp, _p(coeff[0]), _p(coeff[1]), _p(coeff[2]), _p(coeff[3]),
+                     _p(residual), int(relu), _p(y), rows, C, _stream())
+                applied = True
+            elif not fused:
                 call('pxl_bn_finalize', _p(sums), count, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
                      float(momentum), float(eps), clamp, _p(coeff[0]), _p(coeff[1]), _p(coeff[2]), _p(coeff[3]), _stream())
         else:
             call('pxl_bn_eval_coeffs', C, _p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps),
                  _p(coeff[2]), _p(coeff[3]), _stream())
-        if residual is not None:
-            _chk(residual, 'residual', cl=True)
-        call('pxl_bn_apply', _p(x), _p(coeff[2]), _p(coeff[3]), _p(residual), int(relu), _p(y), rows, C, _stream())
-        ctx.save_for_backward(x, y if (relu and residual is not None) else None, gamma, coeff, running_var)
+        if not applied:
+            if residual is not None:
+                _chk(residual, 'residual', cl=True)
+            call('pxl_bn_apply', _p(x), _p(coeff[2]), _p(coeff[3]), _p(residual), int(relu), _p(y), rows, C, _stream())
+        ctx.save_for_backward(x, y if (relu and residual is not None) else None, gamma, coeff, running_var, beta)
         ctx.meta = (rows, C, count, bool(relu), residual is not None, bool(training), float(eps), group)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, gamma, coeff, running_var = ctx.saved_tensors
+        x, y, gamma, coeff, running_var, beta = ctx.saved_tensors
         rows, C, count, relu, has_res, training, eps, group = ctx.meta
         dy = as_cl(dy)
         dev = dy.device
@@ -767,10 +777,15 @@ class _BnAct(torch.autograd.Function):
         ymask = y if (relu and has_res) else None
         call('pxl_bn_bwd_reduce', _p(x), _p(ymask), _p(dy), _p(coeff[0]), _p(coeff[1]), int(relu), rows, C, _p(dsums),
              _p(coeff[2]), _p(coeff[3]), _stream())
-        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
-        # parameter gradients use the LOCAL sums (DDP averages them with the other grads)
-        call('pxl_bn_bwd_params', _p(dsums), C, _p(dgamma), _p(dbeta), 0, _stream())
+        # single GPU with arena gradients in place: the dx launch adds d(gamma), d(beta) straight into .grad
+        acc_inplace = (group is None and ACCUM_WGRAD_INPLACE and gamma.grad is not None and beta.grad is not None
+                       and gamma.grad.is_contiguous() and beta.grad.is_contiguous())
+        dgamma = dbeta = None
+        if not acc_inplace:
+            dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+            # parameter gradients use the LOCAL sums (DDP averages them with the other grads)
+            call('pxl_bn_bwd_params', _p(dsums), C, _p(dgamma), _p(dbeta), 0, _stream())
         if group is not None:
             px = _peer_exchanges.get(id(group))
             if px is not None and 2 * C <= 4096:
@@ -781,7 +796,8 @@ class _BnAct(torch.autograd.Function):
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
         call('pxl_bn_bwd_dx', _p(x), _p(ymask), _p(dy), _p(coeff[0]), _p(coeff[1]), _p(gamma), _p(dsums), count, int(relu),
-             _p(dx), _p(dres), rows, C, _p(coeff[2]), _p(coeff[3]), _stream())
+             _p(dx), _p(dres), rows, C, _p(coeff[2]), _p(coeff[3]),
+             _p(gamma.grad if acc_inplace else None), _p(beta.grad if acc_inplace else None), _stream())
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None, None
 
 
@@ -1144,7 +1160,7 @@ class _IBNorm(torch.autograd.Function):
         dx = torch.empty_like(x)
         for i in range(b):
             call('pxl_bn_bwd_dx', _p(x[i]), _p(None), _p(dy[i]), _p(coeff[i, 0]), _p(coeff[i, 1]), _p(gamma), _p(mix[i]),
-                 float(hw), 0, _p(dx[i]), _p(None), hw, C, _p(None), _p(None), _stream())
+                 float(hw), 0, _p(dx[i]), _p(None), hw, C, _p(None), _p(None), _p(None), _p(None), _stream())
         return dx, dgamma, dbeta, None, None, None, None, None, None
 
 
