@@ -321,6 +321,8 @@ def _ctaps(t):
 
 _epoch = 0
 ACCUM_WGRAD_INPLACE = True      # wgrad kernels add straight into weight.grad (the flat gradient arena)
+import os as _os
+FUSE_BN_FINALIZE = _os.environ.get('PXL_BN_FUSED_FINALIZE', '1') != '0'     # finalize inside the apply launch
 
 
 def new_step():
@@ -744,7 +746,7 @@ class _BnAct(torch.autograd.Function):
                     dist.all_reduce(sums, group=group)
             if residual is not None:
                 _chk(residual, 'residual', cl=True)
-            if group is None:
+            if group is None and FUSE_BN_FINALIZE:
                 # local statistics: finalize + apply in one launch
                 call('pxl_bn_finalize_apply', _p(x), _p(sums), count, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
                      float(momentum), float(eps), clamp, _p(coeff[0]), _p(coeff[1]), _p(coeff[2]), _p(coeff[3]),
