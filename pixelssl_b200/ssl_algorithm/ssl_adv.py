@@ -163,7 +163,7 @@ class SSLADV(ssl_base._SSLBase):
         self.meters.reset()
         self.model.train()
         self.d_model.train()
-        for idx, (inp, gt) in enumerate(data_loader):
+        for idx, (inp, gt) in enumerate(ssl_base.device_prefetch(data_loader)):
             timer = time.time()
             self.train_step(inp, gt)
             self.meters.update('batch_time', time.time() - timer)

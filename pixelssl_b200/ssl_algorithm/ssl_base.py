@@ -79,6 +79,45 @@ class _SSLBase:
         raise NotImplementedError
 
 
+def device_prefetch(data_loader):
+    """Iterate ``data_loader`` one batch ahead: the host->HBM copy of batch k+1 (``Variable(i).cuda()`` of the
+    reference's ``_batch_prehandle``, e.g. ssl_mt.py:337-357) is enqueued on a side stream before step k's kernels
+    are, so it overlaps the compute instead of sitting in front of it.  Yields ``(inp, gt)`` tuples of DEVICE
+    tensors (``to_device`` then passes them through); falls back to plain iteration without CUDA."""
+    import torch
+    if not torch.cuda.is_available():
+        for batch in data_loader:
+            yield batch
+        return
+    copy_stream = torch.cuda.Stream()
+
+    def stage(batch):
+        inp, gt = batch
+        with torch.cuda.stream(copy_stream):
+            d_inp = tuple(t.cuda(non_blocking=True) for t in inp)
+            d_gt = tuple(t.cuda(non_blocking=True) for t in gt)
+        ev = torch.cuda.Event()
+        ev.record(copy_stream)
+        return d_inp, d_gt, ev
+
+    it = iter(data_loader)
+    try:
+        nxt = stage(next(it))
+    except StopIteration:
+        return
+    while nxt is not None:
+        cur = nxt
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            nxt = None
+        main = torch.cuda.current_stream()
+        main.wait_event(cur[2])
+        for t in cur[0] + cur[1]:
+            t.record_stream(main)
+        yield cur[0], cur[1]
+
+
 def to_device(tensors, non_blocking=True):
     """``Variable(i).cuda()`` of every ``_batch_prehandle`` (ssl_mt.py:337-357): host -> HBM copy on
     the current stream (asynchronous when the loader pinned the batch)."""

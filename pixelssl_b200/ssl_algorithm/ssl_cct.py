@@ -312,7 +312,7 @@ class SSLCCT(ssl_base._SSLBase):
     def _train(self, data_loader, epoch):
         self.meters.reset()
         self.model.train()
-        for idx, (inp, gt) in enumerate(data_loader):
+        for idx, (inp, gt) in enumerate(ssl_base.device_prefetch(data_loader)):
             timer = time.time()
             cur_step = len(data_loader) * epoch + idx
             total_steps = len(data_loader) * self.args.cons_rampup_epochs

@@ -158,7 +158,7 @@ class SSLCUTMIX(ssl_base._SSLBase):
         self.meters.reset()
         self.s_model.train()
         self.t_model.train()
-        for idx, (inp, gt) in enumerate(data_loader):
+        for idx, (inp, gt) in enumerate(ssl_base.device_prefetch(data_loader)):
             timer = time.time()
             cur_step = len(data_loader) * epoch + idx
             total_steps = len(data_loader) * self.args.cons_rampup_epochs

@@ -235,7 +235,7 @@ class SSLGCT(ssl_base._SSLBase):
     def _train(self, data_loader, epoch):
         self.meters.reset()
         self.l_model.train(); self.r_model.train(); self.fd_model.train()
-        for idx, (inp, gt) in enumerate(data_loader):
+        for idx, (inp, gt) in enumerate(ssl_base.device_prefetch(data_loader)):
             timer = time.time()
             cur_steps = len(data_loader) * epoch + idx
             total_steps = len(data_loader) * self.args.dc_rampup_epochs

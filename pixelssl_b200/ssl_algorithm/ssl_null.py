@@ -49,7 +49,7 @@ class SSLNULL(ssl_base._SSLBase):
         lbs = self.args.labeled_batch_size
         self.model.train()
         arena = self.model.arena
-        for idx, (inp, gt) in enumerate(data_loader):
+        for idx, (inp, gt) in enumerate(ssl_base.device_prefetch(data_loader)):
             timer = time.time()
             inp, gt = ssl_base.to_device(inp), ssl_base.to_device(gt)
             arena.zero_grad()
