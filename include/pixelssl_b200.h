@@ -213,6 +213,10 @@ int pxl_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream
 int pxl_conv_tc_status(void);
 /* w [Cout][T][Cin] -> wt [Cin][T][Cout] */
 int pxl_conv_transpose_weights(const float* w, float* wt, int Cout, int T, int Cin, void* stream);
+/* the same for every conv weight of a parameter arena in one launch: table[n][6] (device, int64) = {src offset,
+ * dst offset, Cout, T, Cin, first tile}; tiles = 32x32 (co,ci) blocks per tap, numbered tensor by tensor */
+int pxl_conv_transpose_weights_batched(const float* src_base, float* dst_base, const int64_t* table, int n,
+                                       int64_t total_tiles, void* stream);
 /* dbias[co] (+)= sum over rows of dy[row, co] (row stride ldo) */
 int pxl_bias_grad(const float* dy, int64_t rows, int Cout, int ldo, float* dbias, int accumulate,
                   void* stream);

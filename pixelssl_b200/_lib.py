@@ -62,6 +62,7 @@ SIGNATURES = {
     'pxl_split_tf32': (c_int, [P, P, P, c_int64, P]),
     'pxl_conv_tc_status': (c_int, []),
     'pxl_conv_transpose_weights': (c_int, [P, P, c_int, c_int, c_int, P]),
+    'pxl_conv_transpose_weights_batched': (c_int, [P, P, P, c_int, c_int64, P]),
     'pxl_bias_grad': (c_int, [P, c_int64, c_int, c_int, P, c_int, P]),
     'pxl_stem_conv7x7s2': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'pxl_stem_conv7x7s2_wgrad': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),

@@ -370,6 +370,52 @@ extern "C" int pxl_conv_transpose_weights(const float* w, float* wt, int Cout, i
     return 0;
 }
 
+// All conv weights of a parameter arena in ONE launch: table[n][6] = {src offset, dst offset, Cout, T, Cin, first tile}
+// (element offsets into src_base / dst_base; tiles = 32x32 (co, ci) blocks per tap, numbered tensor by tensor).
+// Replaces ~100 per-layer launches per step whose cost was launch latency, not bytes.
+__global__ void __launch_bounds__(256)
+transpose_w_batched_kernel(const float* __restrict__ src_base, float* __restrict__ dst_base,
+                           const long long* __restrict__ table, int n) {
+    __shared__ float tile[32][33];
+    __shared__ long long ent[6];
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = n - 1;                    // last tensor whose first tile <= blockIdx.x
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (table[mid * 6 + 5] <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+        }
+        for (int k = 0; k < 6; ++k) ent[k] = table[lo * 6 + k];
+    }
+    __syncthreads();
+    const float* w = src_base + ent[0];
+    float* wt = dst_base + ent[1];
+    const int Cout = (int)ent[2], T = (int)ent[3], Cin = (int)ent[4];
+    const int local = (int)((long long)blockIdx.x - ent[5]);
+    const int tiles_ci = (Cin + 31) / 32, tiles_co = (Cout + 31) / 32;
+    const int t = local / (tiles_ci * tiles_co);
+    const int rem = local - t * tiles_ci * tiles_co;
+    const int ci0 = (rem % tiles_ci) * 32, co0 = (rem / tiles_ci) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int co = co0 + r, ci = ci0 + tx;
+        tile[r][tx] = (co < Cout && ci < Cin) ? __ldg(w + ((int64_t)co * T + t) * Cin + ci) : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int ci = ci0 + r, co = co0 + tx;
+        if (ci < Cin && co < Cout) wt[((int64_t)ci * T + t) * Cout + co] = tile[tx][r];
+    }
+}
+
+extern "C" int pxl_conv_transpose_weights_batched(const float* src_base, float* dst_base, const int64_t* table, int n,
+                                                  int64_t total_tiles, void* stream) {
+    if (!src_base || !dst_base || !table || n <= 0 || total_tiles <= 0 || total_tiles >= (1ll << 31)) return PXL_ERR_BAD_ARG;
+    transpose_w_batched_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)stream>>>(
+        src_base, dst_base, reinterpret_cast<const long long*>(table), n);
+    PXL_CHECK_LAUNCH();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // bias gradient: dbias[co] (+)= sum_rows dy[row*ldo + co]
 // ------------------------------------------------------------------------------------------

@@ -37,6 +37,60 @@ class ParamArena:
                 p.data = view
                 p.grad = self._view_like(self.grad, o, p)
                 self._index[id(p)] = (o, n)
+        # conv weights (4-D, stored [Cout][kh*kw][Cin]): table for the batched transpose / tf32 split of a step
+        rows, tiles = [], 0
+        self._conv_at = {}
+        for p, o in zip(params, offs):
+            if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last):
+                co, ci, kh, kw = p.shape
+                rows.append([o, o, co, kh * kw, ci, tiles])
+                self._conv_at[o] = (co, kh * kw, ci)
+                tiles += ((ci + 31) // 32) * ((co + 31) // 32) * kh * kw
+        self._conv_table = torch.tensor(rows, dtype=torch.int64, device=dev) if rows else None
+        self._conv_tiles = tiles
+        self._derived = {}            # name -> flat tensor; valid for self._derived_key
+        self._derived_key = None
+        ops.register_param_arena(self)
+
+    def derived(self, name):
+        """Per-step derived copies of the whole arena, produced with ONE launch each and cached until the parameters
+        change: 't' = every conv weight transposed to [Cin][taps][Cout] (dgrad operand), 'hi'/'lo' = tf32 split of
+        the arena, 't_hi'/'t_lo' = split of the transposed arena.  Views are taken by element offset."""
+        key = (ops.step_epoch(), self.data._version)
+        if key != self._derived_key:
+            self._derived_key, self._derived_valid = key, set()
+        if name in self._derived_valid:
+            return self._derived[name]
+        if name not in self._derived:
+            self._derived[name] = torch.zeros_like(self.data)
+        if name == 't':
+            if self._conv_table is None:
+                raise ValueError('arena holds no convolution weights')
+            ops.transpose_weights_batched(self.data, self._derived['t'], self._conv_table, self._conv_tiles)
+        elif name in ('hi', 'lo'):
+            for other in ('hi', 'lo'):
+                if other not in self._derived:
+                    self._derived[other] = torch.zeros_like(self.data)
+            ops.split_tf32_into(self.data, self._derived['hi'], self._derived['lo'])
+            self._derived_valid.update(('hi', 'lo'))
+        elif name in ('t_hi', 't_lo'):
+            src = self.derived('t')
+            for other in ('t_hi', 't_lo'):
+                if other not in self._derived:
+                    self._derived[other] = torch.zeros_like(self.data)
+            ops.split_tf32_into(src, self._derived['t_hi'], self._derived['t_lo'])
+            self._derived_valid.update(('t_hi', 't_lo'))
+        else:
+            raise KeyError(name)
+        self._derived_valid.add(name)
+        return self._derived[name]
+
+    def locate(self, t):
+        """Element offset of tensor ``t`` inside this arena's parameter buffer, or None."""
+        d = t.data_ptr() - self.data.data_ptr()
+        if d < 0 or d >= 4 * self.numel or d % 4:
+            return None
+        return d // 4
 
     @staticmethod
     def _view_like(flat, off, p):

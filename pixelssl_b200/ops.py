@@ -323,6 +323,7 @@ _epoch = 0
 ACCUM_WGRAD_INPLACE = True      # wgrad kernels add straight into weight.grad (the flat gradient arena)
 import os as _os
 FUSE_BN_FINALIZE = _os.environ.get('PXL_BN_FUSED_FINALIZE', '1') != '0'     # finalize inside the apply launch
+BATCH_WEIGHT_PREP = _os.environ.get('PXL_BATCH_WEIGHT_PREP', '1') != '0'    # arena-wide weight transposes / tf32 splits
 
 
 def new_step():
@@ -360,6 +361,41 @@ def _stat_pool_reset():
             ent[1] = 0
 
 
+def step_epoch():
+    return _epoch
+
+
+# parameter arenas (nn/arena.py) register here so that per-layer requests for a split / transposed weight can be
+# served from the arena-wide copies made with one launch per step
+_param_arenas = []
+
+
+def register_param_arena(arena):
+    import weakref
+    _param_arenas.append(weakref.ref(arena))
+
+
+def _arena_of(t):
+    for ref in list(_param_arenas):
+        a = ref()
+        if a is None:
+            _param_arenas.remove(ref)
+            continue
+        off = a.locate(t)
+        if off is not None:
+            return a, off
+    return None, None
+
+
+def transpose_weights_batched(src, dst, table, total_tiles):
+    call('pxl_conv_transpose_weights_batched', _p(src), _p(dst), ctypes.c_void_p(table.data_ptr()), int(table.shape[0]),
+         int(total_tiles), _stream())
+
+
+def split_tf32_into(x, hi, lo):
+    call('pxl_split_tf32', _p(x), _p(hi), _p(lo), x.numel(), _stream())
+
+
 def split_tf32(x):
     """x (any shape, numel % 4 == 0) -> (hi, lo): hi = tf32(x) with a zero low mantissa, lo = x - hi."""
     hi, lo = torch.empty_like(x), torch.empty_like(x)
@@ -370,6 +406,10 @@ def split_tf32(x):
 def split_cached(x):
     """split_tf32 memoised on the tensor object (an activation feeding two convolutions, a weight
     used by several launches of one step).  Invalidated by in-place edits and by new_step()."""
+    arena, off = _arena_of(x) if (x.dim() == 4 and BATCH_WEIGHT_PREP) else (None, None)
+    if arena is not None and off in arena._conv_at:
+        n = x.numel()
+        return arena.derived('hi')[off:off + n], arena.derived('lo')[off:off + n]
     ent = getattr(x, '_pxl_parts', None)
     if ent is not None and ent[0] == _epoch and ent[1] == x._version and ent[2] == x.data_ptr():
         return ent[3]
@@ -560,7 +600,15 @@ class _Conv2d(torch.autograd.Function):
         dx = dw = db = None
         dyin = dy
         if ctx.needs_input_grad[0]:
-            if _conv_precision == 2 and tc_supported(Cout, 1, stride):
+            want_split = _conv_precision == 2 and tc_supported(Cout, 1, stride)
+            arena, off = _arena_of(weight) if BATCH_WEIGHT_PREP else (None, None)
+            if arena is not None and arena._conv_at.get(off) == (Cout, T, Cin):
+                n = weight.numel()          # arena-wide transposed (and split) copies: one launch per step each
+                if want_split:
+                    wt = (arena.derived('t_hi')[off:off + n], arena.derived('t_lo')[off:off + n])
+                else:
+                    wt = arena.derived('t')[off:off + n]
+            elif want_split:
                 w_hi, w_lo = split_cached(weight)
                 wt = (transpose_weights(w_hi, Cout, T, Cin), transpose_weights(w_lo, Cout, T, Cin))
             else:
