@@ -83,39 +83,60 @@ def device_prefetch(data_loader):
     """Iterate ``data_loader`` one batch ahead: the host->HBM copy of batch k+1 (``Variable(i).cuda()`` of the
     reference's ``_batch_prehandle``, e.g. ssl_mt.py:337-357) is enqueued on a side stream before step k's kernels
     are, so it overlaps the compute instead of sitting in front of it.  Yields ``(inp, gt)`` tuples of DEVICE
-    tensors (``to_device`` then passes them through); falls back to plain iteration without CUDA."""
+    tensors (``to_device`` then passes them through); falls back to plain iteration without CUDA.
+
+    The device side is two fixed staging slots (allocated once per tensor shape): slot k % 2 is rewritten only after
+    the step that consumed it has finished, so no allocator traffic (and no cudaMalloc stall) sits in the loop.  A
+    yielded batch is valid until the iteration after next."""
     import torch
     if not torch.cuda.is_available():
         for batch in data_loader:
             yield batch
         return
     copy_stream = torch.cuda.Stream()
+    slots = [{}, {}]                 # slot -> {(position, shape, dtype): device tensor}
+    done = [None, None]              # event on the main stream: the step that read this slot is enqueued
 
-    def stage(batch):
+    def stage(batch, k):
         inp, gt = batch
+        b = k % 2
+        if done[b] is not None:
+            copy_stream.wait_event(done[b])
+        out = []
         with torch.cuda.stream(copy_stream):
-            d_inp = tuple(t.cuda(non_blocking=True) for t in inp)
-            d_gt = tuple(t.cuda(non_blocking=True) for t in gt)
+            for pos, t in enumerate(tuple(inp) + tuple(gt)):
+                if t.is_cuda:
+                    out.append(t)
+                    continue
+                key = (pos, tuple(t.shape), t.dtype)
+                buf = slots[b].get(key)
+                if buf is None:
+                    buf = slots[b][key] = torch.empty(t.shape, dtype=t.dtype, device='cuda')
+                buf.copy_(t, non_blocking=True)
+                out.append(buf)
         ev = torch.cuda.Event()
         ev.record(copy_stream)
-        return d_inp, d_gt, ev
+        return tuple(out[:len(inp)]), tuple(out[len(inp):]), ev
 
     it = iter(data_loader)
     try:
-        nxt = stage(next(it))
+        nxt = stage(next(it), 0)
     except StopIteration:
         return
+    k = 0
     while nxt is not None:
         cur = nxt
         try:
-            nxt = stage(next(it))
+            nxt = stage(next(it), k + 1)
         except StopIteration:
             nxt = None
         main = torch.cuda.current_stream()
         main.wait_event(cur[2])
-        for t in cur[0] + cur[1]:
-            t.record_stream(main)
         yield cur[0], cur[1]
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        done[k % 2] = ev
+        k += 1
 
 
 def to_device(tensors, non_blocking=True):
