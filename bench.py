@@ -179,8 +179,9 @@ def run_engine(args):
 
     def timed_public_api(batches):
         """End to end through the plugin API a PixelSSL user calls: ``algorithm.train(data_loader, epoch)``
-        (ssl_base.py:77-90) on a loader of pinned HOST batches, log_freq = 1 so that every step formats its log
-        line, i.e. reads the step's losses back to the host exactly like the reference's training loop does."""
+        (ssl_base.py:77-90) on a loader of pinned HOST batches, log_freq = 1: every step's losses are read back to the
+        host for its log line (the engine copies them asynchronously and prints one step late; all of them are on the
+        host when train() returns)."""
         a.log_freq = 1
         loader_w = [((batches[i % nb][0],), (batches[i % nb][1],)) for i in range(args.warmup)]
         loader_t = [((batches[i % nb][0],), (batches[i % nb][1],)) for i in range(args.steps)]

@@ -168,7 +168,7 @@ class SSLADV(ssl_base._SSLBase):
             self.train_step(inp, gt)
             self.meters.update('batch_time', time.time() - timer)
             if idx % self.args.log_freq == 0:
-                logger.log_info('step: [{0}][{1}/{2}]\tbatch-time: {meters[batch_time]:.3f}\n'
+                self._log_step(lambda m, a=(epoch + 1, idx, len(data_loader), self.args.task): ('step: [{0}][{1}/{2}]\tbatch-time: {meters[batch_time]:.3f}\n'
                                 '  task-{3}\t=>\t'
                                 'task-loss: {meters[task_loss]:.6f}\t'
                                 'labeled-adv-loss: {meters[labeled_adv_loss]:.6f}\t'
@@ -176,7 +176,7 @@ class SSLADV(ssl_base._SSLBase):
                                 '  fc-discriminator\t=>\t'
                                 'fake-d-loss: {meters[fake_d_loss]:.6f}\t'
                                 'real-d-loss: {meters[real_d_loss]:.6f}\n'
-                                .format(epoch + 1, idx, len(data_loader), self.args.task, meters=self.meters))
+                                ).format(*a, meters=m))
             self.d_lrer.step()
             if not self.args.is_epoch_lrer:
                 self.lrer.step()

@@ -25,9 +25,27 @@ class _SSLBase:
 
     def train(self, data_loader, epoch):
         self._train(data_loader, epoch)
+        self._flush_log()
 
     def validate(self, data_loader, epoch):
+        self._flush_log()
         self._validate(data_loader, epoch)
+
+    def _log_step(self, make_line):
+        """The per-step log line of every reference ``_train`` (e.g. ssl_mt.py:199-207), emitted ONE logging
+        interval late: formatting the meters right away is a device->host read that drains the launch queue every
+        ``log_freq`` steps (at log_freq = 1 the GPU idles while the host re-fills it).  The meter values of this
+        step are copied to pinned host memory asynchronously now and printed at the next call / at the end of
+        ``train()``, by which time the copy has long completed.  Same text, same values."""
+        snap = self.meters.snapshot()
+        prev, self._pending_log = getattr(self, '_pending_log', None), (make_line, snap)
+        if prev is not None:
+            logger.log_info(prev[0](prev[1]))
+
+    def _flush_log(self):
+        prev, self._pending_log = getattr(self, '_pending_log', None), None
+        if prev is not None:
+            logger.log_info(prev[0](prev[1]))
 
     def save_checkpoint(self, epoch):
         self._save_checkpoint(epoch)

@@ -165,11 +165,11 @@ class SSLCUTMIX(ssl_base._SSLBase):
             self.train_step(inp, gt, cur_step, total_steps)
             self.meters.update('batch_time', time.time() - timer)
             if idx % self.args.log_freq == 0:
-                logger.log_info('step: [{0}][{1}/{2}]\tbatch-time: {meters[batch_time]:.3f}\n'
+                self._log_step(lambda m, a=(epoch + 1, idx, len(data_loader), self.args.task): ('step: [{0}][{1}/{2}]\tbatch-time: {meters[batch_time]:.3f}\n'
                                 '  student-{3}\t=>\t'
                                 's-task-loss: {meters[task_loss]:.6f}\t'
                                 's-cons-loss: {meters[cons_loss]:.6f}\n'
-                                .format(epoch + 1, idx, len(data_loader), self.args.task, meters=self.meters))
+                                ).format(*a, meters=m))
             if not self.args.is_epoch_lrer:
                 self.s_lrer.step()
         if self.args.is_epoch_lrer:

@@ -242,13 +242,13 @@ class SSLGCT(ssl_base._SSLBase):
             self.train_step(inp, gt, cur_steps, total_steps)
             self.meters.update('batch_time', time.time() - timer)
             if idx % self.args.log_freq == 0:
-                logger.log_info('step: [{0}][{1}/{2}]\tbatch-time: {meters[batch_time]:.3f}\n'
+                self._log_step(lambda m, a=(epoch + 1, idx, len(data_loader), self.args.task): ('step: [{0}][{1}/{2}]\tbatch-time: {meters[batch_time]:.3f}\n'
                                 '  l-{3}\t=>\tl-task-loss: {meters[l_task_loss]:.6f}\tl-dc-loss: {meters[l_dc_loss]:.6f}\t'
                                 'l-fc-loss: {meters[l_fc_loss]:.6f}\n'
                                 '  r-{3}\t=>\tr-task-loss: {meters[r_task_loss]:.6f}\tr-dc-loss: {meters[r_dc_loss]:.6f}\t'
                                 'r-fc-loss: {meters[r_fc_loss]:.6f}\n'
                                 '  fd\t=>\tl-fd-loss: {meters[l_fd_loss]:.6f}\tr-fd-loss: {meters[r_fd_loss]:.6f}\n'
-                                .format(epoch + 1, idx, len(data_loader), self.args.task, meters=self.meters))
+                                ).format(*a, meters=m))
             self.fd_lrer.step()
             if not self.args.is_epoch_lrer:
                 self.l_lrer.step()
