@@ -321,7 +321,8 @@ int pxl_gaussian_noise(float* inp, const float* noise, int n, int64_t CHW, float
  * (CUDA-IPC mapped), waits for all lanes, adds them in rank order and (count > 0) finalizes the layer.
  *   pxl_peer_alloc/export/open: mailbox of pxl_peer_mailbox_bytes() bytes, 64-byte IPC handle, peer mapping.
  *   pxl_peer_allreduce_bn: sums [n = 2C] in place; mailboxes = host array of `world` device pointers (own one at
- *   index rank); seq = 1, 2, 3, ... identical on all ranks; count <= 0: plain all-reduce (backward dsums).
+ *   index rank); seq = 1, 2, 3, ... identical on all ranks; count <= 0: plain all-reduce (backward dsums), where
+ *   dgamma_acc / dbeta_acc (both or neither) first receive += the LOCAL sums (the BN parameter gradients).
  * --------------------------------------------------------------------------------------------- */
 int64_t pxl_peer_mailbox_bytes(void);
 int pxl_peer_alloc(void** ptr);
@@ -332,7 +333,8 @@ int pxl_peer_close(void* ptr);
 int pxl_peer_allreduce_bn(double* sums, int n, void* const* mailboxes, int rank, int world, int64_t seq,
                           double count, int C, const float* gamma, const float* beta, float* running_mean,
                           float* running_var, float momentum, float eps, int clamp_mode, float* mean,
-                          float* invstd, float* scale, float* shift, void* stream);
+                          float* invstd, float* scale, float* shift, float* dgamma_acc, float* dbeta_acc,
+                          void* stream);
 int pxl_peer_status(void);
 
 #ifdef __cplusplus

@@ -96,7 +96,7 @@ SIGNATURES = {
     'pxl_peer_open': (c_int, [P, P]),
     'pxl_peer_close': (c_int, [P]),
     'pxl_peer_allreduce_bn': (c_int, [P, c_int, P, c_int, c_int, c_int64, c_double, c_int, P, P, P, P, c_float, c_float,
-                                      c_int, P, P, P, P, P]),
+                                      c_int, P, P, P, P, P, P, P]),
     'pxl_peer_status': (c_int, []),
     'pxl_sgd_ema': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, P]),
     'pxl_ema': (c_int, [P, P, c_int64, c_float, P]),

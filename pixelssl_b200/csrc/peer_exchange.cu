@@ -80,8 +80,18 @@ __global__ void __launch_bounds__(512)
 peer_allreduce_bn_kernel(double* __restrict__ sums, int n, PxPeers peers, int rank, int world, unsigned long long seq,
                          double count, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                          float* running_mean, float* running_var, float momentum, float eps, int clamp_mode,
-                         float* mean, float* invstd, float* scale, float* shift, int* err) {
+                         float* mean, float* invstd, float* scale, float* shift,
+                         float* dgamma_acc, float* dbeta_acc, int* err) {
     const int slot = (int)(seq % PX_NSLOT);
+    // backward: the parameter gradients come from the LOCAL sums (DDP averages them with the other gradients):
+    // dbeta += sum dz, dgamma += sum dz*xhat, straight into the gradient arena, before the lanes are exchanged
+    if (dgamma_acc) {
+        const int Ch = n >> 1;
+        for (int c = threadIdx.x; c < Ch; c += blockDim.x) {
+            dbeta_acc[c] += (float)sums[c];
+            dgamma_acc[c] += (float)sums[Ch + c];
+        }
+    }
     __shared__ int failed;
     if (threadIdx.x == 0) failed = 0;
     // 1. push this rank's lane to every mailbox, then publish
@@ -139,7 +149,9 @@ static int* g_peer_err = nullptr;
 extern "C" int pxl_peer_allreduce_bn(double* sums, int n, void* const* mailboxes, int rank, int world, int64_t seq,
                                      double count, int C, const float* gamma, const float* beta, float* running_mean,
                                      float* running_var, float momentum, float eps, int clamp_mode, float* mean,
-                                     float* invstd, float* scale, float* shift, void* stream) {
+                                     float* invstd, float* scale, float* shift, float* dgamma_acc, float* dbeta_acc,
+                                     void* stream) {
+    if ((dgamma_acc == nullptr) != (dbeta_acc == nullptr) || (n & 1)) return PXL_ERR_BAD_ARG;
     if (!sums || !mailboxes || n <= 0 || n > PX_MAXN || world < 1 || world > PX_MAXW || rank < 0 || rank >= world || seq <= 0)
         return PXL_ERR_BAD_ARG;
     if (count > 0.0 && (!gamma || !beta || !mean || !invstd || !scale || !shift || C <= 0 || 2 * C != n)) return PXL_ERR_BAD_ARG;
@@ -154,7 +166,7 @@ extern "C" int pxl_peer_allreduce_bn(double* sums, int n, void* const* mailboxes
     }
     peer_allreduce_bn_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(sums, n, peers, rank, world, (unsigned long long)seq, count, C,
                                                                  gamma, beta, running_mean, running_var, momentum, eps, clamp_mode,
-                                                                 mean, invstd, scale, shift, g_peer_err);
+                                                                 mean, invstd, scale, shift, dgamma_acc, dbeta_acc, g_peer_err);
     PXL_CHECK_LAUNCH();
     return 0;
 }

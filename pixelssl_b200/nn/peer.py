@@ -45,9 +45,10 @@ class PeerExchange:
         self._ptrs = ptrs
         dist.barrier(group=self.group)          # every mailbox is mapped everywhere before the first exchange
 
-    def allreduce_bn(self, sums, finalize=None):
+    def allreduce_bn(self, sums, finalize=None, param_grads=None):
         """In-place sum of ``sums`` (fp64, <= 4096 values) over the ranks.  finalize = (count, C, gamma, beta,
-        running_mean, running_var, momentum, eps, clamp, mean, invstd, scale, shift) also finishes the layer."""
+        running_mean, running_var, momentum, eps, clamp, mean, invstd, scale, shift) also finishes the layer;
+        param_grads = (dgamma_acc, dbeta_acc) receive += the local sums before the exchange (backward)."""
         n = sums.numel()
         if n > MAX_VALUES or sums.dtype != torch.float64 or not sums.is_cuda or not sums.is_contiguous():
             raise ValueError('peer exchange takes a contiguous CUDA fp64 vector of at most %d values' % MAX_VALUES)
@@ -56,13 +57,14 @@ class PeerExchange:
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         if finalize is None:
             z = ctypes.c_void_p(0)
+            dg, db = (P(param_grads[0]), P(param_grads[1])) if param_grads is not None else (z, z)
             call('pxl_peer_allreduce_bn', P(sums), n, self._ptrs, self.rank, self.world, self.seq, 0.0, 0,
-                 z, z, z, z, 0.0, 0.0, 0, z, z, z, z, stream)
+                 z, z, z, z, 0.0, 0.0, 0, z, z, z, z, dg, db, stream)
         else:
             count, C, gamma, beta, rm, rv, momentum, eps, clamp, mean, invstd, scale, shift = finalize
             call('pxl_peer_allreduce_bn', P(sums), n, self._ptrs, self.rank, self.world, self.seq, float(count), int(C),
                  P(gamma), P(beta), P(rm), P(rv), float(momentum), float(eps), int(clamp), P(mean), P(invstd), P(scale),
-                 P(shift), stream)
+                 P(shift), ctypes.c_void_p(0), ctypes.c_void_p(0), stream)
         return sums
 
     def status(self):

@@ -828,18 +828,24 @@ class _BnAct(torch.autograd.Function):
         call('pxl_bn_bwd_reduce', _p(x), _p(ymask), _p(dy), _p(coeff[0]), _p(coeff[1]), int(relu), rows, C, _p(dsums),
              _p(coeff[2]), _p(coeff[3]), _stream())
         # single GPU with arena gradients in place: the dx launch adds d(gamma), d(beta) straight into .grad
-        acc_inplace = (group is None and ACCUM_WGRAD_INPLACE and gamma.grad is not None and beta.grad is not None
-                       and gamma.grad.is_contiguous() and beta.grad.is_contiguous())
+        grads_in_arena = (ACCUM_WGRAD_INPLACE and gamma.grad is not None and beta.grad is not None
+                          and gamma.grad.is_contiguous() and beta.grad.is_contiguous())
+        px = _peer_exchanges.get(id(group)) if group is not None else None
+        if px is not None and 2 * C > 4096:
+            px = None
+        # d(gamma), d(beta) come from the LOCAL sums (DDP averages them with the other gradients); whenever the
+        # gradient arena is in place they are accumulated by a launch that runs anyway: the dx kernel (single GPU)
+        # or the peer-exchange kernel (before it exchanges the sums)
+        acc_inplace = grads_in_arena and group is None
+        acc_in_exchange = grads_in_arena and px is not None
         dgamma = dbeta = None
-        if not acc_inplace:
+        if not (acc_inplace or acc_in_exchange):
             dgamma = torch.empty(C, dtype=torch.float32, device=dev)
             dbeta = torch.empty(C, dtype=torch.float32, device=dev)
-            # parameter gradients use the LOCAL sums (DDP averages them with the other grads)
             call('pxl_bn_bwd_params', _p(dsums), C, _p(dgamma), _p(dbeta), 0, _stream())
         if group is not None:
-            px = _peer_exchanges.get(id(group))
-            if px is not None and 2 * C <= 4096:
-                px.allreduce_bn(dsums)
+            if px is not None:
+                px.allreduce_bn(dsums, param_grads=(gamma.grad, beta.grad) if acc_in_exchange else None)
             else:
                 import torch.distributed as dist
                 dist.all_reduce(dsums, group=group)
