@@ -13,8 +13,15 @@
 // * precision 1: single TF32 pass on the raw fp32 data.  precision 2 ("3xTF32"): operands are
 //   pre-split into hi = tf32(x), lo = x - hi; D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo recovers
 //   fp32-grade products with fp32 accumulation (error ~2^-21 per product).
+//   Weights are split once per step; activations arrive raw and are split in shared memory by the
+//   transform warps ("a_inkernel").
 // * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-//   warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).  mbarrier full/empty ring.
+//   warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4), warps 6..9 (persistent kernels) =
+//   operand transform.  mbarrier full/empty ring.
+// * three kernels share this scheme: conv_tc_kernel (one tile per CTA, up to two CTAs per SM),
+//   conv_tc_persist_kernel (default: one CTA per SM walks over tiles, accumulator double-buffered in
+//   TMEM, epilogue through a swizzled staging slab + TMA store, overlapped with the next tile) and
+//   conv_tc_pair_kernel (opt-in cta_group::2 variant).  The wgrad kernel is at the end of the file.
 //
 // Every mbarrier wait has a watchdog: on expiry the kernel raises a device-side flag and bails
 // out, so a protocol bug can never hang the GPU.
