@@ -173,3 +173,32 @@ def test_summarize_confusion_matrix_matches_golden():
         v = summarize_confusion_matrix(g['metrics_cmat_sum%d' % k])
         got = np.array([v['acc'], v['acc-class'], v['mIoU'], v['fwIoU']])
         np.testing.assert_allclose(got, g['metrics_values%d' % k], rtol=1e-12)
+
+
+def test_device_prefetch_falls_back_to_plain_iteration_without_cuda():
+    from pixelssl_b200.ssl_algorithm import ssl_base
+    if torch.cuda.is_available():
+        pytest.skip('GPU present: the CUDA path is covered by the gpu tests')
+    batches = [((torch.full((2, 3), float(i)),), (torch.full((2, 1), float(-i)),)) for i in range(4)]
+    got = list(ssl_base.device_prefetch(batches))
+    assert len(got) == 4
+    for (gi, gg), (bi, bg) in zip(got, batches):
+        assert gi[0] is bi[0] and gg[0] is bg[0]
+    assert list(ssl_base.device_prefetch([])) == []
+
+
+def test_deferred_step_log_prints_same_text_one_interval_late(monkeypatch):
+    """_SSLBase._log_step: line k is emitted at call k+1 (or at flush) with the values it had at call k."""
+    from pixelssl_b200.ssl_algorithm import ssl_base
+    from pixelssl_b200.utils import logger
+    emitted = []
+    monkeypatch.setattr(logger, 'log_info', lambda msg: emitted.append(msg))
+    alg = ssl_base._SSLBase(args=None)
+    for k in range(3):
+        alg.meters.update('task_loss', float(k) + 0.5)
+        alg._log_step(lambda m, a=(k,): 'step {0}: {meters[task_loss]:.3f}'.format(*a, meters=m))
+        assert len(emitted) == k                      # nothing for this step yet
+    alg._flush_log()
+    assert emitted == ['step 0: 0.500 (0.500)', 'step 1: 1.500 (1.000)', 'step 2: 2.500 (1.500)']
+    alg._flush_log()
+    assert len(emitted) == 3
