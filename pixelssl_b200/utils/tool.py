@@ -1,14 +1,17 @@
+"""Small helpers shared by the algorithm modules."""
 from . import logger
 
 
 def dict_value(dictionary, name, default=None, err=False):
-    """pixelssl/utils/tool.py:4-17."""
+    """Look ``name`` up in ``dictionary``.  A missing key (or no dictionary at all) yields ``default`` - or, when
+    ``err`` is set, the reference's error convention: banner + exit (pixelssl/utils/tool.py:4-17)."""
+    problem = None
     if dictionary is None:
-        if err:
-            logger.log_err('The given dictionary is None\n')
-        return default
-    if name in dictionary:
+        problem = 'The given dictionary is None\n'
+    elif name not in dictionary:
+        problem = 'Cannot find key: {0}'.format(name)
+    else:
         return dictionary[name]
     if err:
-        logger.log_err('Cannot find key: {0}'.format(name))
+        logger.log_err(problem)
     return default
