@@ -24,6 +24,10 @@ def register_into_pixelssl(pixelssl_module=None, task_sseg_modules=None):
         mod = getattr(ssl_algorithm, name)
         pixelssl_module.ssl_algorithm.__dict__[name] = mod
         setattr(pixelssl_module.ssl_algorithm, name, mod)
+    # the proxy builds its sampler through ``pixelssl.nn.data`` by attribute (task_template/proxy.py:11,372):
+    # the rank-aware sampler has the same constructor and, at world size 1, the same index stream
+    from .nn import data as b200_data
+    pixelssl_module.nn.data.TwoStreamBatchSampler = b200_data.TwoStreamBatchSampler
     if task_sseg_modules is not None:
         from .task.sseg import model as b200_model, criterion as b200_criterion
         task_model, task_criterion = task_sseg_modules[0], task_sseg_modules[1]

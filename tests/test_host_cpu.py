@@ -117,6 +117,18 @@ def test_register_into_unmodified_pixelssl():
         assert mod.__name__.startswith('pixelssl_b200.')
         assert callable(getattr(mod, name)) and callable(mod.add_parser_arguments)
         assert name in pixelssl.ssl_algorithm.SSL_ALGORITHMS
+    # the proxy's sampler lookup (pixelssl.nn.data.TwoStreamBatchSampler) now resolves to the rank-aware one,
+    # which at world size 1 yields exactly what the reference's own class yields
+    from pixelssl.nn import data as nndata
+    import importlib
+    assert nndata.TwoStreamBatchSampler.__module__ == 'pixelssl_b200.nn.data'
+    ref_cls = importlib.reload(importlib.import_module('pixelssl.nn.data')).TwoStreamBatchSampler
+    np.random.seed(5)
+    want = [list(map(int, b)) for b in ref_cls(list(range(9)), list(range(50, 83)), 2, 3)]
+    pixelssl_b200.register_into_pixelssl(pixelssl)
+    np.random.seed(5)
+    got = [list(map(int, b)) for b in nndata.TwoStreamBatchSampler(list(range(9)), list(range(50, 83)), 2, 3)]
+    assert got == want and len(got) == 11
     # the reference's own parser builder accepts the engine's algorithm modules
     from pixelssl import runner
     parser = runner.create_parser('ssl_mt')
