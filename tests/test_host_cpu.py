@@ -214,3 +214,54 @@ def test_deferred_step_log_prints_same_text_one_interval_late(monkeypatch):
     assert emitted == ['step 0: 0.500 (0.500)', 'step 1: 1.500 (1.000)', 'step 2: 2.500 (1.500)']
     alg._flush_log()
     assert len(emitted) == 3
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree only exists in the build container')
+@pytest.mark.parametrize('name,backbone', [('deeplabv2', 'resnet101'), ('pspnet', 'resnet50'), ('pspnet', 'resnet101')])
+def test_task_model_state_dict_and_param_groups_match_reference(name, backbone):
+    """Checkpoint compatibility: same state_dict keys, shapes and dtypes as the reference task
+    model (so its .ckpt files load), same LR groups in the same order (task/sseg/model.py:45-48,103-107)."""
+    import sys
+    import torch.utils.model_zoo as mz
+    saved = (mz.load_url, torch.nn.Module.cuda, torch.Tensor.cuda)
+    mz.load_url = lambda *a, **k: {}
+    for p in ('/root/reference', '/root/reference/task/sseg'):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    try:
+        import model as ref_model                        # task/sseg/model.py of the reference
+        from pixelssl_b200 import runner
+        from pixelssl_b200.task.sseg import model as eng_model
+        args = runner.build_args({'ssl_algorithm': 'ssl_null', 'lr': 0.00025, 'momentum': 0.9, 'weight_decay': 0.0005,
+                                  'epochs': 2, 'batch_size': 2, 'unlabeled_batch_size': 0, 'ignore_unlabeled': True,
+                                  'backbone': backbone}, iters_per_epoch=5)
+        ref = getattr(ref_model, name)()(args)
+        eng = getattr(eng_model, name)()(args)
+        rs, es = ref.state_dict(), eng.state_dict()
+        assert list(rs.keys()) == list(es.keys())
+        for k in rs:
+            assert tuple(rs[k].shape) == tuple(es[k].shape) and rs[k].dtype == es[k].dtype, k
+        rid = {id(p): n for n, p in ref.named_parameters()}
+        eid = {id(p): n for n, p in eng.named_parameters()}
+        assert len(ref.param_groups) == len(eng.param_groups)
+        for rg, eg in zip(ref.param_groups, eng.param_groups):
+            assert rg['lr'] == eg['lr']
+            assert [rid[id(p)] for p in rg['params']] == [eid[id(p)] for p in eg['params']]
+    finally:
+        mz.load_url, torch.nn.Module.cuda, torch.Tensor.cuda = saved
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree only exists in the build container')
+@pytest.mark.parametrize('alg', ['ssl_null', 'ssl_mt', 'ssl_cutmix', 'ssl_adv', 'ssl_gct', 'ssl_cct'])
+def test_checkpoint_dict_keys_match_reference(alg):
+    """Every algorithm saves the same top-level checkpoint keys as the reference's ``_save_checkpoint``
+    (e.g. ssl_mt.py:296-307), so checkpoints are interchangeable between the two."""
+    def keys_of(path):
+        src = open(path).read()
+        body = src[src.index('def _save_checkpoint'):]
+        body = body[body.index('state = {'):]
+        body = body[:body.index('}') + 1]
+        return sorted(set(re.findall(r"'([a-z_]+)'\s*:", body)))
+    ref = keys_of('/root/reference/pixelssl/ssl_algorithm/%s.py' % alg)
+    eng = keys_of(os.path.join(ROOT, 'pixelssl_b200', 'ssl_algorithm', '%s.py' % alg))
+    assert ref == eng and 'algorithm' in eng and 'epoch' in eng
