@@ -22,11 +22,10 @@ def add_parser_arguments(parser):
     ssl_base.add_parser_arguments(parser)
     parser.add_argument('--cons-scale', type=float, default=-1)
     parser.add_argument('--cons-rampup-epochs', type=int, default=-1)
-    parser.add_argument('--cons-type', type=str, default='mse')
-    parser.add_argument('--cons-threshold', type=float, default=0.97)
+    parser.add_argument('--cons-type', type=str, default='mse', choices=['mse'])
+    parser.add_argument('--cons-threshold', type=float, default=-1)
     parser.add_argument('--ema-decay', type=float, default=0.99)
-    parser.add_argument('--mask-prop-range', type=cmd.str2floatlist if hasattr(cmd, 'str2floatlist') else str,
-                        default=(0.5, 0.5))
+    parser.add_argument('--mask-prop-range', type=cmd.str2floatlist, default='(0.5, 0.5)')
 
 
 def ssl_cutmix(args, model_dict, optimizer_dict, lrer_dict, criterion_dict, task_func):
@@ -85,8 +84,12 @@ class SSLCUTMIX(ssl_base._SSLBase):
                 logger.log_err('The argument - cons_scale - is not set (or invalid)\n')
             if self.args.cons_rampup_epochs < 0:
                 logger.log_err('The argument - cons_rampup_epochs - is not set (or invalid)\n')
-            if self.args.unlabeled_batch_size % 2 != 0:
-                logger.log_err('SSL_CUTMIX requires an even unlabeled_batch_size (pairs are mixed)\n')
+            if self.args.unlabeled_batch_size <= 2 or self.args.unlabeled_batch_size % 2 != 0:
+                logger.log_err('SSL_CUTMIX requires an unlabeled batch size that is larger than 2 and divisible by 2 '
+                               '(pairs of unlabeled samples are mixed)\n')
+            if self.args.cons_threshold < 0 or self.args.cons_threshold > 1:
+                logger.log_err('The argument - cons_threshold - is not set (or invalid)\n'
+                               'Please set - 0 <= cons_threshold < 1 - for training\n')
         if self.args.cons_type != 'mse':
             logger.log_err('SSL_CUTMIX only supports cons_type == mse\n')
 

@@ -265,3 +265,27 @@ def test_checkpoint_dict_keys_match_reference(alg):
     ref = keys_of('/root/reference/pixelssl/ssl_algorithm/%s.py' % alg)
     eng = keys_of(os.path.join(ROOT, 'pixelssl_b200', 'ssl_algorithm', '%s.py' % alg))
     assert ref == eng and 'algorithm' in eng and 'epoch' in eng
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree only exists in the build container')
+@pytest.mark.parametrize('alg', ['ssl_null', 'ssl_mt', 'ssl_cutmix', 'ssl_adv', 'ssl_gct', 'ssl_cct'])
+def test_algorithm_parser_arguments_match_reference(alg):
+    """add_parser_arguments of every algorithm module: same options, defaults, types and choices as the
+    reference's (e.g. ssl_mt.py:27-38), so its scripts/configs parse identically."""
+    import argparse
+    import importlib
+    import sys
+    if '/root/reference' not in sys.path:
+        sys.path.insert(0, '/root/reference')
+    ref_mod = importlib.import_module('pixelssl.ssl_algorithm.' + alg)
+    if not ref_mod.__name__.startswith('pixelssl.') or 'pixelssl_b200' in getattr(ref_mod, '__file__', ''):
+        ref_mod = importlib.reload(ref_mod)
+    from pixelssl_b200 import ssl_algorithm as eng
+    pr, pe = argparse.ArgumentParser(), argparse.ArgumentParser()
+    ref_mod.add_parser_arguments(pr)
+    getattr(eng, alg).add_parser_arguments(pe)
+
+    def table(parser):
+        return {a.dest: (a.default, getattr(a.type, '__name__', a.type), a.choices, tuple(a.option_strings))
+                for a in parser._actions if a.dest != 'help'}
+    assert table(pr) == table(pe)
