@@ -53,8 +53,14 @@ def add_proxy_arguments(parser):
     p('--task', type=str, default='')
     p('--labeled-batch-size', type=int, default=None)
     p('--checkpoint-path', type=str, default='')
+    p('--visual-debug-path', type=str, default='')      # autoset by the proxy (task_template/proxy.py:67-69)
+    p('--visual-train-path', type=str, default='')
+    p('--visual-val-path', type=str, default='')
     p('--is-epoch-lrer', type=cmd.str2bool, default=None)
     p('--iters-per-epoch', type=int, default=None)
+    # task/sseg/data.py:20-24 (used by the reference's own dataset layer)
+    p('--val-rescaling', type=cmd.str2bool, default=False)
+    p('--train-base-size', type=int, default=400)
     # task/sseg/proxy.py:13-14
     p('--num-classes', type=int, default=21)
     p('--ignore-index', type=int, default=255)

@@ -289,3 +289,27 @@ def test_algorithm_parser_arguments_match_reference(alg):
         return {a.dest: (a.default, getattr(a.type, '__name__', a.type), a.choices, tuple(a.option_strings))
                 for a in parser._actions if a.dest != 'help'}
     assert table(pr) == table(pe)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree only exists in the build container')
+def test_full_argument_set_matches_reference_runner_and_sseg_proxy():
+    """runner.create_parser + the proxy/task arguments: every option the reference's ``pixelssl.runner.create_parser``
+    + ``task/sseg/proxy.add_parser_arguments`` defines exists here with the same default and type."""
+    import sys
+    for p in ('/root/reference', '/root/reference/task/sseg'):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import importlib
+    rr = importlib.import_module('pixelssl.runner')
+    # the algorithm table may have been swapped by an earlier register_into_pixelssl test: compare with ssl_null,
+    # whose options both implementations define identically (tested above)
+    sp = importlib.import_module('proxy')
+    from pixelssl_b200 import runner as er
+    pr = rr.create_parser('ssl_null')
+    sp.add_parser_arguments(pr)
+    pe = er.create_parser('ssl_null')
+    er.add_proxy_arguments(pe)
+
+    def table(parser):
+        return {a.dest: (a.default, getattr(a.type, '__name__', a.type), a.choices) for a in parser._actions if a.dest != 'help'}
+    assert table(pr) == table(pe)
