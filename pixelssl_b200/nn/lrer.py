@@ -1,5 +1,7 @@
-"""LR schedulers used by the sseg scripts (pixelssl/nn/lrer.py): only ``polynomiallr`` is on the
-hot path (per-iteration, host scalar math)."""
+"""LR schedulers (pixelssl/nn/lrer.py).  ``polynomiallr`` is the one the sseg scripts use (per iteration, host scalar
+math); the four per-epoch wrappers of torch's own schedulers are here so that every ``lrers`` entry a PixelSSL script
+can name resolves.  All of them only edit ``optimizer.param_groups[i]['lr']``, which the fused arena optimiser
+steps read at launch time."""
 import math
 
 import torch
@@ -57,3 +59,30 @@ def polynomiallr(args):
         return PolynomialLR(optimizer, epochs=args.epochs, iters_per_epoch=args.iters_per_epoch,
                             power=args.power, last_epoch=args.last_epoch)
     return polynomiallr_wrapper
+
+
+def _epoch_lrer(scheduler_cls, resolve):
+    """Export function for a torch per-epoch scheduler: ``resolve(args)`` replaces the parser's -1 / [] placeholders
+    by the reference's per-scheduler defaults (lrer.py:51-119) and returns the scheduler's keyword arguments."""
+    def export(args):
+        kwargs = resolve(args)
+
+        def wrapper(optimizer):
+            return scheduler_cls(optimizer, last_epoch=args.last_epoch, **kwargs)
+        return wrapper
+    return export
+
+
+def _pick(args, name, default, unset=-1):
+    if getattr(args, name) == unset:
+        setattr(args, name, default)
+    return getattr(args, name)
+
+
+steplr = _epoch_lrer(torch.optim.lr_scheduler.StepLR, lambda a: {
+    'step_size': _pick(a, 'step_size', a.epochs), 'gamma': _pick(a, 'gamma', 0.1)})
+multisteplr = _epoch_lrer(torch.optim.lr_scheduler.MultiStepLR, lambda a: {
+    'milestones': _pick(a, 'milestones', list(range(1, a.epochs)), unset=[]), 'gamma': _pick(a, 'gamma', 0.1)})
+exponentiallr = _epoch_lrer(torch.optim.lr_scheduler.ExponentialLR, lambda a: {'gamma': _pick(a, 'gamma', 0.1)})
+cosineannealinglr = _epoch_lrer(torch.optim.lr_scheduler.CosineAnnealingLR, lambda a: {
+    'T_max': _pick(a, 'T_max', a.epochs), 'eta_min': _pick(a, 'eta_min', 0)})

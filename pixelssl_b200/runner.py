@@ -77,7 +77,18 @@ def build_args(config, iters_per_epoch=100):
     args.task = 'sseg'
     args.labeled_batch_size = args.batch_size - args.unlabeled_batch_size
     args.iters_per_epoch = iters_per_epoch
-    args.is_epoch_lrer = False
+    # proxy.py:239-250: per-epoch schedulers step once per epoch, 'polynomiallr' every iteration
+    from .nn import lrer as _lrer
+    kinds = set()
+    for n in (args.lrers or {'model': 'polynomiallr'}).values():
+        if n not in _lrer.VALID_LRER:
+            logger.log_err('Unknown learning rate scheduler ({0}) type\n  EPOCH_LRERS\t=>\t{1}\n  ITER_LRERS\t=>\t{2}\n'
+                           .format(n, _lrer.EPOCH_LRERS, _lrer.ITER_LRERS))
+        kinds.add(n in _lrer.EPOCH_LRERS)
+    if len(kinds) > 1:
+        logger.log_err('Unmatched lr scheduler types\t=>\t{0}\nAll lrers of the task models should have the same '
+                       'types (either EPOCH_LRERS or ITER_LRERS)\n'.format(args.lrers))
+    args.is_epoch_lrer = kinds.pop()
     return args
 
 

@@ -313,3 +313,34 @@ def test_full_argument_set_matches_reference_runner_and_sseg_proxy():
     def table(parser):
         return {a.dest: (a.default, getattr(a.type, '__name__', a.type), a.choices) for a in parser._actions if a.dest != 'help'}
     assert table(pr) == table(pe)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree only exists in the build container')
+@pytest.mark.parametrize('name', ['steplr', 'multisteplr', 'exponentiallr', 'cosineannealinglr', 'polynomiallr'])
+def test_lr_scheduler_wrappers_follow_the_reference(name):
+    """Every lrer export yields the reference's learning-rate trajectory (pixelssl/nn/lrer.py:51-179) on a toy
+    two-group optimizer, including the per-scheduler defaults behind the parser's -1 placeholders."""
+    import argparse
+    import importlib
+    import sys
+    if '/root/reference' not in sys.path:
+        sys.path.insert(0, '/root/reference')
+    ref = importlib.import_module('pixelssl.nn.lrer')
+    from pixelssl_b200.nn import lrer as eng
+
+    def run(mod):
+        parser = argparse.ArgumentParser()
+        mod.add_parser_arguments(parser)
+        args = parser.parse_args([])
+        args.epochs, args.iters_per_epoch = 6, 4
+        w = [torch.nn.Parameter(torch.zeros(2)), torch.nn.Parameter(torch.zeros(2))]
+        opt = torch.optim.SGD([{'params': [w[0]], 'lr': 0.1}, {'params': [w[1]], 'lr': 1.0}], lr=0.1, momentum=0.9)
+        sched = getattr(mod, name)(args)(opt)
+        traj = []
+        steps = args.epochs * args.iters_per_epoch - 1 if name == 'polynomiallr' else args.epochs
+        for _ in range(steps):
+            traj.append([g['lr'] for g in opt.param_groups])
+            opt.step()
+            sched.step()
+        return traj
+    np.testing.assert_allclose(run(eng), run(ref), rtol=1e-12)
