@@ -344,3 +344,59 @@ def test_lr_scheduler_wrappers_follow_the_reference(name):
             sched.step()
         return traj
     np.testing.assert_allclose(run(eng), run(ref), rtol=1e-12)
+
+
+_BASE_CFG = {'lr': 0.00025, 'momentum': 0.9, 'weight_decay': 0.0005, 'epochs': 20, 'log_freq': 10 ** 6,
+             'batch_size': 16, 'unlabeled_batch_size': 8}
+_VALID = {
+    'ssl_mt': {'cons_scale': 1.0, 'cons_rampup_epochs': 3},
+    'ssl_cutmix': {'cons_scale': 20.0, 'cons_rampup_epochs': 0, 'cons_threshold': 0.97},
+    'ssl_adv': {'adv_for_labeled': True, 'labeled_adv_scale': 0.01, 'unlabeled_adv_scale': 0.001, 'discriminator_scale': 1.0},
+    'ssl_gct': {'fc_ssl_scale': 1.0, 'dc_ssl_scale': 100.0, 'dc_threshold': 0.6, 'dc_rampup_epochs': 5, 'mu': 0.5, 'nu': 1,
+                'im_size': 65},
+    'ssl_cct': {'cons_scale': 30.0, 'cons_rampup_epochs': 5, 'ad_lr_scale': 10.0},
+}
+_CASES = [(alg, None) for alg in _VALID] + [
+    ('ssl_mt', {'cons_scale': -1.0}), ('ssl_mt', {'cons_rampup_epochs': -1}),
+    ('ssl_cutmix', {'cons_threshold': -1.0}), ('ssl_cutmix', {'unlabeled_batch_size': 2, 'batch_size': 4}),
+    ('ssl_cutmix', {'cons_scale': -1.0}),
+    ('ssl_adv', {'labeled_adv_scale': -1.0}), ('ssl_adv', {'unlabeled_adv_scale': -1.0}),
+    ('ssl_gct', {'dc_threshold': -1.0}), ('ssl_gct', {'mu': -1.0}), ('ssl_gct', {'nu': -1}),
+    ('ssl_gct', {'fc_ssl_scale': -1.0}), ('ssl_gct', {'dc_rampup_epochs': -1}),
+    ('ssl_cct', {'cons_scale': -1.0}), ('ssl_cct', {'cons_rampup_epochs': -1}), ('ssl_cct', {'ad_lr_scale': -1.0}),
+]
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree only exists in the build container')
+@pytest.mark.parametrize('alg,override', _CASES)
+def test_algorithm_constructors_validate_arguments_like_the_reference(alg, override, capsys):
+    """``log_err`` (banner + exit) for the same unset / invalid SSL arguments as the reference's ``__init__`` checks
+    (e.g. ssl_mt.py:76-92, ssl_cutmix.py:79-94), acceptance of the shipped-script values."""
+    import importlib
+    import sys
+    if '/root/reference' not in sys.path:
+        sys.path.insert(0, '/root/reference')
+    from pixelssl_b200 import runner
+    cfg = dict(_BASE_CFG, ssl_algorithm=alg, **_VALID[alg])
+    cfg.update(override or {})
+    ref_mod = importlib.import_module('pixelssl.ssl_algorithm.' + alg)
+    eng_mod = importlib.import_module('pixelssl_b200.ssl_algorithm.' + alg)
+    cls = {'ssl_mt': 'SSLMT', 'ssl_cutmix': 'SSLCUTMIX', 'ssl_adv': 'SSLADV', 'ssl_gct': 'SSLGCT', 'ssl_cct': 'SSLCCT'}[alg]
+
+    def rejected(mod):
+        try:
+            getattr(mod, cls)(runner.build_args(dict(cfg), iters_per_epoch=5))
+            return False
+        except SystemExit:
+            return True
+    saved = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self          # the reference's GCT constructor moves a buffer to the GPU
+    try:
+        want = rejected(ref_mod)
+    finally:
+        torch.Tensor.cuda = saved
+    got = rejected(eng_mod)
+    capsys.readouterr()
+    assert got == want, 'reference rejects: %s, engine rejects: %s' % (want, got)
+    if override is None:
+        assert not got
