@@ -37,14 +37,28 @@ class SemanticSegmentationFunc:
         for k, name in names.items():
             meters.update(name, values[k])
 
+    def _arch(self, hook):
+        arch = (self.args.models or {'model': 'deeplabv2'})['model']
+        if arch not in ('pspnet', 'deeplabv2'):
+            from ...utils import logger
+            logger.log_err('In the SSL_CCT algorithm, the task model \'{0}\' is not supported by the hook \'{1}\'\n'
+                           .format(arch, hook))
+        return arch
+
     def sslcct_ad_in_channels(self):
-        return 2048
+        """Channels of ``resulter['sslcct_ad_inp']`` (task/sseg/func.py:222-236): the PSP feature for pspnet, the
+        backbone latent for deeplabv2."""
+        return {'pspnet': 512, 'deeplabv2': 2048}[self._arch('sslcct_ad_in_channels')]
 
     def sslcct_ad_out_channels(self):
         return self.args.num_classes
 
     def sslcct_ad_upsample_scale(self):
+        self._arch('sslcct_ad_upsample_scale')
         return 8
+
+    def ssls4l_rc_in_channels(self):
+        return self.args.num_classes
 
     def sslgct_fd_in_channels(self):
         return self.args.num_classes + 3

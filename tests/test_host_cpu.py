@@ -400,3 +400,30 @@ def test_algorithm_constructors_validate_arguments_like_the_reference(alg, overr
     assert got == want, 'reference rejects: %s, engine rejects: %s' % (want, got)
     if override is None:
         assert not got
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree only exists in the build container')
+@pytest.mark.parametrize('arch', ['deeplabv2', 'pspnet'])
+def test_task_func_shape_hooks_match_reference(arch):
+    """The scalar TaskFunc hooks the algorithms size their auxiliary networks with (task/sseg/func.py:134-253)."""
+    import importlib
+    import sys
+    for p in ('/root/reference', '/root/reference/task/sseg'):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from pixelssl_b200 import runner
+    from pixelssl_b200.task.sseg import func as eng_func
+    args = runner.build_args(dict(_BASE_CFG, ssl_algorithm='ssl_cct', models={'model': arch}, im_size=65, **_VALID['ssl_cct']),
+                             iters_per_epoch=5)
+    saved = (torch.Tensor.cuda, torch.nn.Module.cuda)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    try:
+        ref = importlib.import_module('func').task_func()(args)
+    finally:
+        torch.Tensor.cuda, torch.nn.Module.cuda = saved
+    eng = eng_func.task_func()(args)
+    for hook in ('sslcct_ad_in_channels', 'sslcct_ad_out_channels', 'sslcct_ad_upsample_scale', 'sslgct_fd_in_channels',
+                 'ssladv_fcd_in_channels', 'ssls4l_rc_in_channels'):
+        assert getattr(eng, hook)() == getattr(ref, hook)(), hook
+    assert eng.METRIC_STR == ref.METRIC_STR
