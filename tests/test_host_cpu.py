@@ -427,3 +427,31 @@ def test_task_func_shape_hooks_match_reference(arch):
                  'ssladv_fcd_in_channels', 'ssls4l_rc_in_channels'):
         assert getattr(eng, hook)() == getattr(ref, hook)(), hook
     assert eng.METRIC_STR == ref.METRIC_STR
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree only exists in the build container')
+@pytest.mark.parametrize('name', ['sgd', 'adam'])
+def test_optimizer_wrappers_build_the_reference_optimizer(name):
+    """optimizer export functions (pixelssl/nn/optimizer.py:57-123): same torch optimizer class and the same
+    hyper-parameters in every param group, including the defaults behind the parser's -1 placeholders."""
+    import argparse
+    import importlib
+    import sys
+    if '/root/reference' not in sys.path:
+        sys.path.insert(0, '/root/reference')
+    ref = importlib.import_module('pixelssl.nn.optimizer')
+    from pixelssl_b200.nn import optimizer as eng
+
+    def build(mod):
+        parser = argparse.ArgumentParser()
+        mod.add_parser_arguments(parser)
+        args = parser.parse_args(['--lr', '0.00025'])
+        w = [torch.nn.Parameter(torch.zeros(2)), torch.nn.Parameter(torch.zeros(3))]
+        groups = [{'params': [w[0]], 'lr': args.lr}, {'params': [w[1]], 'lr': 10 * args.lr}]
+        return getattr(mod, name)(args)(groups)
+    a, b = build(ref), build(eng)
+    assert type(a) is type(b)
+    for ga, gb in zip(a.param_groups, b.param_groups):
+        ka = {k: v for k, v in ga.items() if k != 'params'}
+        kb = {k: v for k, v in gb.items() if k != 'params'}
+        assert ka == kb
