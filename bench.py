@@ -11,11 +11,15 @@ A "step" is one full ``SSLMT.train_step``: zero_grad, student fwd, CE, teacher f
 consistency, backward, gradient all-reduce (N>1), fused SGD+EMA, LR step.
 
 Printed JSON line (rank 0): see the contract in the task statement.  ``value`` times the step
-with the batch already in HBM; ``e2e`` times the same public call with pinned HOST batches
-(H2D inside the timed region) plus a D2H read of the step's loss.  ``roofline`` is for the
+with the batch already in HBM; ``e2e`` times the plugin API a PixelSSL user calls,
+``algorithm.train(data_loader, epoch)``, on pinned HOST batches with log_freq = 1 (H2D of every batch
+and a D2H read of every step's losses inside the timed region).  ``roofline`` is for the
 metric kernel (fused MSE consistency fwd+bwd, 12 B/element), timed live with CUDA events around
-each of its launches inside the timed steps.  ``cpu_baseline`` / ``--impl reference`` time the
-CPU oracle port of the reference step (torch CPU fp32, all host threads) on a bounded sample."""
+each of its launches inside the timed steps.  ``alt_precision`` repeats ``value`` with single-pass
+TF32 convolutions (the default is the fp32-grade 3xTF32 path).  ``cpu_baseline`` / ``--impl
+reference`` time the CPU oracle port of the reference step (torch CPU fp32, up to 32 host threads)
+on a bounded sample; ``--impl reference --ref-device cuda`` (informational) runs the same port with
+stock PyTorch ops on the GPU."""
 import argparse
 import json
 import os
