@@ -1,5 +1,5 @@
 """CPU oracle of the GCT step (pixelssl/ssl_algorithm/ssl_gct.py).  TEST INFRASTRUCTURE ONLY (see
-oracle/sseg_oracle.py).  Pinned by tests/golden/gct_step_65.npz (oracle/make_golden.py:golden_gct)."""
+oracle/sseg_oracle.py).  Pinned by tests/golden/gct_step_129.npz (oracle/make_golden.py:golden_gct)."""
 import math
 
 import numpy as np
