@@ -39,7 +39,16 @@ def _worker(rank, world, port, q):
         wrap.arena.grad.fill_(float(rank + 1))
         wrap.arena.all_reduce_grads()
         avg = float(wrap.arena.grad[0])
-        q.put((rank, same_after_broadcast, bn_synced, avg, float(wrap.arena.grad.min()), float(wrap.arena.grad.max())))
+        # the rank-aware sampler reads rank / world size from the process group; gloo ranks do not get the
+        # CUDA-IPC statistics exchange
+        import numpy as np
+        from pixelssl_b200 import ops
+        from pixelssl_b200.nn.data import TwoStreamBatchSampler
+        np.random.seed(7)
+        smp = TwoStreamBatchSampler(list(range(12)), list(range(100, 140)), 2, 3)
+        batches = [list(map(int, b)) for b in smp]
+        q.put((rank, same_after_broadcast, bn_synced, avg, float(wrap.arena.grad.min()), float(wrap.arena.grad.max()),
+               (smp.rank, smp.world_size), batches, len(ops._peer_exchanges)))
     finally:
         dist.destroy_process_group()
 
@@ -56,7 +65,18 @@ def test_two_rank_broadcast_and_grad_average():
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0
-    for rank, same, bn_synced, avg, lo, hi in res:
+    by_rank = {}
+    for rank, same, bn_synced, avg, lo, hi, who, batches, n_peer in res:
         assert same, 'parameters differ after the rank-0 broadcast'
         assert bn_synced, 'BN layers were not put into cross-rank statistics mode'
         assert avg == lo == hi == 1.5          # mean of 1 and 2
+        assert who == (rank, 2) and n_peer == 0
+        by_rank[rank] = batches
+    # same permutations on both ranks, disjoint slices: together they are the reference's global batches (4 + 6)
+    import numpy as np
+    from pixelssl_b200.nn.data import TwoStreamBatchSampler
+    np.random.seed(7)
+    whole = [list(map(int, b)) for b in TwoStreamBatchSampler(list(range(12)), list(range(100, 140)), 4, 6, rank=0, world_size=1)]
+    assert len(whole) == len(by_rank[0]) == len(by_rank[1])
+    for gb, b0, b1 in zip(whole, by_rank[0], by_rank[1]):
+        assert b0 == gb[0:2] + gb[4:7] and b1 == gb[2:4] + gb[7:10]
