@@ -8,6 +8,7 @@ Conventions
     reference; labels: float [n,1,H,W] holding integers (task/sseg/data.py:179-182).
 All tensors must be fp32 CUDA tensors; anything else raises (no silent fallback)."""
 import ctypes
+import os as _os
 
 import torch
 
@@ -321,7 +322,6 @@ def _ctaps(t):
 
 _epoch = 0
 ACCUM_WGRAD_INPLACE = True      # wgrad kernels add straight into weight.grad (the flat gradient arena)
-import os as _os
 FUSE_BN_FINALIZE = _os.environ.get('PXL_BN_FUSED_FINALIZE', '1') != '0'     # finalize inside the apply launch
 BATCH_WEIGHT_PREP = _os.environ.get('PXL_BATCH_WEIGHT_PREP', '1') != '0'    # arena-wide weight transposes / tf32 splits
 
