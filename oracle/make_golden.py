@@ -446,6 +446,32 @@ def golden_val(pixelssl, sseg_proxy):
     print('val.npz written:', {k: v.shape for k, v in out.items() if not k.startswith('sampler_')})
 
 
+def golden_input(pixelssl, sseg_proxy):
+    """Training input pipeline (task/sseg/data.py:90-123,142-256) run through the reference's own transform classes on
+    synthetic 8-bit images: the pin of oracle/input_oracle.py (and of a future GPU augmentation path)."""
+    import types
+    import data as sseg_data
+    from PIL import Image
+    out = {}
+    rs = np.random.RandomState(77)
+    cases = [(37, 53, 40, 33, True), (64, 41, 40, 33, True), (50, 50, 24, 40, True), (45, 70, 40, 33, False),
+             (33, 90, 60, 33, False)]
+    out['cases'] = np.array([[h, w, b, c, int(l)] for h, w, b, c, l in cases])
+    for k, (h, w, base, crop, labeled) in enumerate(cases):
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        lab = rs.randint(0, 21, (h, w)).astype(np.uint8)
+        lab[rs.rand(h, w) < 0.1] = 255
+        fake = types.SimpleNamespace(args=types.SimpleNamespace(train_base_size=base, im_size=crop),
+                                     IMAGE=sseg_data.PascalVocDataset.IMAGE, LABEL=sseg_data.PascalVocDataset.LABEL)
+        random.seed(500 + k)
+        x, y = sseg_data.PascalVocDataset._train_prehandle(
+            fake, Image.fromarray(img), Image.fromarray(lab) if labeled else None)
+        out['img%d' % k], out['lab%d' % k] = img, lab
+        out['x%d' % k], out['y%d' % k] = x.numpy(), y.numpy()
+    np.savez_compressed(os.path.join(OUT, 'input_pipeline.npz'), **out)
+    print('input_pipeline.npz written:', {k: v.shape for k, v in out.items() if k.startswith(('x', 'y'))})
+
+
 def golden_fp64():
     """Exact-arithmetic (fp64) evaluation of the SAME steps with the oracle, to measure the
     reference's own fp32 rounding noise on these (ill-conditioned, random-init) networks.  The GPU
@@ -502,7 +528,7 @@ if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     pixelssl, sseg_proxy = patch_and_import()
-    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 'gct', 'cct', 'pspnet', 'val', 'fp64']
+    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 'gct', 'cct', 'pspnet', 'val', 'input', 'fp64']
     if which == ['fp64']:
         golden_fp64()
         sys.exit(0)
@@ -524,5 +550,7 @@ if __name__ == '__main__':
         golden_pspnet(pixelssl)
     if 'val' in which:
         golden_val(pixelssl, sseg_proxy)
+    if 'input' in which:
+        golden_input(pixelssl, sseg_proxy)
     if 'fp64' in which:
         golden_fp64()

@@ -301,3 +301,34 @@ def test_gaussian_noise_layer_matches_reference():
     g = load('val.npz')
     out = O.gaussian_noise_layer(torch.from_numpy(g['gn_inp']), torch.from_numpy(g['gn_noise']))
     assert np.array_equal(out.numpy(), g['gn_out'])
+
+
+def test_input_pipeline_oracle_matches_reference_transforms():
+    """oracle/input_oracle.py against the reference's own transform classes (fixture generated by
+    oracle/make_golden.py input): random scale + crop + flip + normalise, labeled and unlabeled samples, bit for bit."""
+    import random
+    from oracle import input_oracle as I
+    g = load('input_pipeline.npz')
+    for k, (h, w, base, crop, labeled) in enumerate(g['cases']):
+        random.seed(500 + k)
+        x, y = I.train_prehandle(g['img%d' % k], g['lab%d' % k] if labeled else None, int(base), int(crop))
+        assert x.dtype == np.float32 and x.shape == (3, crop, crop)
+        assert np.array_equal(x, g['x%d' % k]), k
+        assert np.array_equal(np.asarray(y, dtype=np.float32), g['y%d' % k]), k
+        if not labeled:
+            assert np.all(y == -1.0)
+
+
+def test_resize_restatements_are_bit_exact_against_pillow():
+    """The Pillow arithmetic behind ``Image.resize`` (BILINEAR with antialiasing, NEAREST), up- and down-scaling."""
+    PIL = pytest.importorskip('PIL')
+    from PIL import Image
+    from oracle import input_oracle as I
+    rs = np.random.RandomState(3)
+    for _ in range(25):
+        h, w = rs.randint(5, 120), rs.randint(5, 120)
+        oh, ow = rs.randint(3, 200), rs.randint(3, 200)
+        a = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        m = rs.randint(0, 22, (h, w)).astype(np.uint8)
+        assert np.array_equal(I.resize_bilinear_u8(a, ow, oh), np.array(Image.fromarray(a).resize((ow, oh), Image.BILINEAR)))
+        assert np.array_equal(I.resize_nearest(m, ow, oh), np.array(Image.fromarray(m).resize((ow, oh), Image.NEAREST)))
