@@ -143,3 +143,30 @@ def train_prehandle(image, label, base_size, crop_size, rng=_random):
     if label is None:
         return x, x[0] * 0.0 - 1.0
     return x, y
+
+
+def fixed_scale_resize(img, mask, size):
+    """FixedScaleResize.__call__ (data.py:259-292): short edge -> ``size`` (float ratio, truncated), BILINEAR / NEAREST,
+    then zero padding on the right / bottom up to ``size`` (cv2.copyMakeBorder, constant 0)."""
+    h, w = img.shape[:2]
+    if w <= h:
+        ow = size
+        oh = h * ow / w
+    else:
+        oh = size
+        ow = w * oh / h
+    oh, ow = int(oh), int(ow)
+    img = resize_bilinear_u8(img, ow, oh)
+    mask = resize_nearest(mask, ow, oh)
+    pad_w, pad_h = max(size - ow, 0), max(size - oh, 0)
+    if pad_w > 0 or pad_h > 0:
+        img = np.pad(img, ((0, pad_h), (0, pad_w)) + ((0, 0),) * (img.ndim - 2), constant_values=0)
+        mask = np.pad(mask, ((0, pad_h), (0, pad_w)), constant_values=0)
+    return img, mask
+
+
+def val_prehandle(image, label, im_size=None, rescaling=False):
+    """PascalVocDataset._val_prehandle (data.py:111-125)."""
+    if rescaling:
+        image, label = fixed_scale_resize(image, label, im_size)
+    return normalize_to_chw(image, label)

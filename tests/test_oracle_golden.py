@@ -332,3 +332,25 @@ def test_resize_restatements_are_bit_exact_against_pillow():
         m = rs.randint(0, 22, (h, w)).astype(np.uint8)
         assert np.array_equal(I.resize_bilinear_u8(a, ow, oh), np.array(Image.fromarray(a).resize((ow, oh), Image.BILINEAR)))
         assert np.array_equal(I.resize_nearest(m, ow, oh), np.array(Image.fromarray(m).resize((ow, oh), Image.NEAREST)))
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree only exists in the build container')
+@pytest.mark.parametrize('h,w,size,rescaling', [(37, 53, 33, True), (64, 41, 48, True), (30, 30, 30, True), (45, 70, 0, False)])
+def test_validation_input_pipeline_matches_reference_transforms(h, w, size, rescaling):
+    """_val_prehandle (optional FixedScaleResize + Normalize + ToTensor) against the reference classes, bit for bit."""
+    import sys
+    import types
+    for p in ('/root/reference', '/root/reference/task/sseg'):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import data as sseg_data
+    from PIL import Image
+    from oracle import input_oracle as I
+    rs = np.random.RandomState(h * 100 + w)
+    img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    lab = rs.randint(0, 21, (h, w)).astype(np.uint8)
+    fake = types.SimpleNamespace(args=types.SimpleNamespace(val_rescaling=rescaling, im_size=size),
+                                 IMAGE=sseg_data.PascalVocDataset.IMAGE, LABEL=sseg_data.PascalVocDataset.LABEL)
+    x_ref, y_ref = sseg_data.PascalVocDataset._val_prehandle(fake, Image.fromarray(img), Image.fromarray(lab))
+    x, y = I.val_prehandle(img, lab, size, rescaling)
+    assert np.array_equal(x, x_ref.numpy()) and np.array_equal(y, y_ref.numpy())
