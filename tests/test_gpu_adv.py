@@ -10,18 +10,23 @@ import torch.nn.functional as F
 from oracle import sseg_oracle as O
 from oracle import adv_oracle as A
 
+from conftest import TEST_PRECISIONS
+
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), 'golden')
 CL = torch.channels_last
 
 
-@pytest.fixture(scope='module')
-def ops():
+@pytest.fixture(scope='module', params=TEST_PRECISIONS)
+def ops(request):
+    """Every test of this module runs once per convolution precision mode (tests/conftest.py): the exact FFMA
+    path and the tcgen05 paths bench.py measures are held to the same goldens."""
     if not torch.cuda.is_available():
         pytest.skip('needs a GPU')
     from pixelssl_b200 import ops as _ops
-    _ops.set_conv_precision(os.environ.get('PXL_TEST_PRECISION', 'fp32'))
-    return _ops
+    _ops.set_conv_precision(request.param)
+    yield _ops
+    _ops.set_conv_precision('fp32')
 
 
 def rel(a, b):

@@ -19,20 +19,24 @@ import torch
 
 from oracle import sseg_oracle as O
 
+from conftest import TEST_PRECISIONS
+
 pytestmark = pytest.mark.gpu
 FACTOR = 3.0
 G = os.path.join(os.path.dirname(__file__), 'golden')
 
 
-@pytest.fixture(scope='module')
-def eng():
+@pytest.fixture(scope='module', params=TEST_PRECISIONS)
+def eng(request):
+    """Every whole-network / whole-step golden runs once per convolution precision mode (tests/conftest.py):
+    the exact FFMA path AND the tcgen05 paths that bench.py measures are held to the same reference vectors."""
     if not torch.cuda.is_available():
         pytest.skip('needs a GPU')
     import pixelssl_b200
     from pixelssl_b200 import ops
-    # PXL_TEST_PRECISION=tf32x3 runs the same whole-network parity tests on the tcgen05 3xTF32 path
-    ops.set_conv_precision(os.environ.get('PXL_TEST_PRECISION', 'fp32'))
-    return pixelssl_b200
+    ops.set_conv_precision(request.param)
+    yield pixelssl_b200
+    ops.set_conv_precision('fp32')
 
 
 def _state(seeds):
