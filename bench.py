@@ -210,13 +210,14 @@ def run_engine(args):
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed_public_api(host)
     alt = None
-    if args.precision == 'tf32x3':
+    if args.precision in ('tf32x3', 'f16x3'):
         # secondary figure: the same step with single-pass TF32 convolutions (what cuDNN does by default for the
         # reference on a GPU); not the headline because it is outside the 1e-3 tolerance against the CPU reference
-        ops.set_conv_precision('tf32')
+        alt_name = 'tf32' if args.precision == 'tf32x3' else 'f16'
+        ops.set_conv_precision(alt_name)
         ms_alt, _, _ = timed(dev, read_loss=False)
         ops.set_conv_precision(args.precision)
-        alt = {'conv_precision': 'tf32', 'value': (LBS + UBS) * world * args.steps / (ms_alt / 1e3), 'unit': 'images/s',
+        alt = {'conv_precision': alt_name, 'value': (LBS + UBS) * world * args.steps / (ms_alt / 1e3), 'unit': 'images/s',
                'ms_per_step': ms_alt / args.steps}
 
     imgs = (LBS + UBS) * world * args.steps
@@ -230,7 +231,7 @@ def run_engine(args):
         'metric': 'images/sec DeepLab-v2-R101 MT 513x513 bs16', 'value': value, 'unit': 'images/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'tf32x3': 'tf32x3'}[args.precision], 'data': 'synthetic',
+        'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'tf32x3': 'tf32x3', 'f16x3': 'f16x3 (fp16 pairs, fp32 accumulate)', 'f16': 'f16 (fp32 accumulate)'}[args.precision], 'data': 'synthetic',
         'config': {'workload': 'MT (ssl_mt) DeepLab-v2-ResNet101 OS16, per-GPU batch 16 = 8 labeled + 8 unlabeled, '
                                '513x513x3 synthetic, 21 classes, cons_for_labeled=False (BASELINE.json configs[1])',
                    'global_batch': (LBS + UBS) * world, 'parallelism': 'dp%d' % world,
@@ -356,7 +357,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='engine', choices=['engine', 'reference'])
     ap.add_argument('--precision', type=str, default=os.environ.get('PXL_CONV_PRECISION', 'tf32x3'),
-                    choices=['fp32', 'tf32', 'tf32x3'])
+                    choices=['fp32', 'tf32', 'tf32x3', 'f16x3', 'f16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ref-device', type=str, default='cpu', choices=['cpu', 'cuda'],
                     help='--impl reference only: cuda = the oracle port with stock PyTorch ops on cuda:0 (informational)')

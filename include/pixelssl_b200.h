@@ -137,6 +137,24 @@ int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, const float* 
                   const float* scale, const float* shift, float* dgamma_acc, float* dbeta_acc, void* stream);
 /* dgamma_acc / dbeta_acc (both or neither): dgamma_acc[c] += dsums[C+c], dbeta_acc[c] += dsums[c] by the same launch
  * (single-GPU path: dsums are the local sums; replaces pxl_bn_bwd_params + the optimizer-side accumulation). */
+/* fp16-pair variants (csrc/h16_prep.cu) of the BatchNorm launches: the SAME pass that writes y (dx) also, or only
+ * (y / dx NULL), writes it as the fp16 pair the next tcgen05 convolution reads, so the pair costs no extra trip
+ * through HBM.  hi / lo: __half NHWC planes, lo nullable.  Forward: fixed scale `hscale`.  Backward: the reduce
+ * launch leaves absmax(dz) in slot[2] (DEVICE float[4], zeroed), the dx launch derives the power-of-two scale from
+ * it, max|gamma*invstd| and target_log2, and stores s / 1/s in slot[0] / slot[1]. */
+int pxl_bn_apply_h16(const float* x, const float* scale, const float* shift, const float* residual, int relu, float* y,
+                     int64_t rows, int C, void* hi, void* lo, float hscale, void* stream);
+int pxl_bn_finalize_apply_h16(const float* x, const double* sums, double count, const float* gamma, const float* beta,
+                              float* running_mean, float* running_var, float momentum, float eps, int clamp_mode,
+                              float* mean, float* invstd, float* scale, float* shift, const float* residual, int relu,
+                              float* y, int64_t rows, int C, void* hi, void* lo, float hscale, void* stream);
+int pxl_bn_bwd_reduce_h16(const float* x, const float* y, const float* dy, const float* mean, const float* invstd,
+                          int relu, int64_t rows, int C, double* dsums, const float* scale, const float* shift,
+                          float* amax_slot, void* stream);
+int pxl_bn_bwd_dx_h16(const float* x, const float* y, const float* dy, const float* mean, const float* invstd,
+                      const float* gamma, const double* dsums, double count, int relu, float* dx, float* dres,
+                      int64_t rows, int C, const float* scale, const float* shift, float* dgamma_acc, float* dbeta_acc,
+                      void* dhi, void* dlo, float* slot, int target_log2, void* stream);
 int pxl_bn_bwd_params(const double* dsums, int C, float* dgamma, float* dbeta, int accumulate,
                       void* stream);
 
@@ -197,6 +215,8 @@ typedef struct {
     double* bn_stats;        /* nullable DEVICE pointer [2*Cout] fp64: the epilogue adds sum(y), sum(y^2) per
                               * output channel (the statistics pass of the BatchNorm that follows,
                               * sync_batchnorm/batchnorm.py:60-62) */
+    float out_scale;         /* 0 is read as 1: the accumulator is multiplied by out_scale * (*out_scale_dev) before */
+    const float* out_scale_dev;   /* bias / statistics / store (undoes the power-of-two scales of fp16 pairs); nullable */
 } pxl_conv_tc_ext;
 int pxl_conv_tc_launch_ex(const pxl_conv_geom* geom_host, const int* taps_dydx_host, const pxl_conv_tc_ext* ext_host,
                           const float* in_hi, const float* in_lo, const float* w_hi, const float* w_lo,
@@ -207,6 +227,29 @@ int pxl_conv_tc_launch_ex(const pxl_conv_geom* geom_host, const int* taps_dydx_h
 int pxl_conv_wgrad_tc_launch(const pxl_conv_geom* geom_host, const int* taps_dydx_host, const float* in_hi,
                              const float* in_lo, const float* dy_hi, const float* dy_lo, float* dw,
                              void* stream);
+/* ---- fp16 pairs: the operand format of the kind::f16 tcgen05 path (csrc/h16_prep.cu) -------------------------
+ * x*s = hi + lo, hi = fp16(x*s), lo = fp16(x*s - hi), s a power of two.  precision 3 ("f16x3"): hi*hi + lo*hi +
+ * hi*lo in fp32 (products good to ~2^-21: fp32-grade, like 3xTF32, at twice its MMA rate); precision 4 ("f16"):
+ * hi*hi only (11-bit significands = the TF32 numerics of the reference's cuDNN path).  Same geometry contract as
+ * pxl_conv_tc_launch_ex with Cin % 64 == 0 (wgrad: Cin % 64 == 0 and ldo % 64 == 0); operands are __half NHWC /
+ * [Cout][taps][Cin] tensors; ext->out_scale(_dev) undo the operand scales.  These replace the same reference
+ * calls as pxl_conv_nhwc (nn.Conv2d forward / backward, resnet.py:18-25). */
+int pxl_conv_h16_launch(const pxl_conv_geom* geom_host, const int* taps_dydx_host, const pxl_conv_tc_ext* ext_host,
+                        const void* in_hi, const void* in_lo, const void* w_hi, const void* w_lo,
+                        const float* bias, float* out, void* stream);
+int pxl_conv_wgrad_h16_launch(const pxl_conv_geom* geom_host, const int* taps_dydx_host, const void* in_hi,
+                              const void* in_lo, const void* dy_hi, const void* dy_lo, float* dw, float out_scale,
+                              const float* out_scale_dev, void* stream);
+/* x -> (hi, lo).  slot == NULL: fixed `scale`.  slot != NULL (DEVICE float[4], zeroed, then filled by
+ * pxl_h16_absmax on the same stream): s = 2^(target_log2 - ceil(log2 absmax)); the kernel stores s in slot[0] and
+ * 1/s in slot[1] (what out_scale_dev points at).  lo nullable; n % 4 == 0.  Out-of-range values saturate at
+ * +-65504 and are counted (pxl_h16_status). */
+int pxl_h16_split(const float* x, void* hi, void* lo, int64_t n, float scale, float* slot, int target_log2,
+                  void* stream);
+int pxl_h16_absmax(const float* x, int64_t n, float* slot, void* stream);
+int* pxl_h16_sat_counter(void);      /* DEVICE int the producers of fp16 pairs add saturation events to */
+int pxl_h16_status(void);            /* number of kernels that saturated since the last reset (synchronises) */
+int pxl_h16_reset_status(void);
 /* hi = round-to-nearest tf32 of x (low 13 mantissa bits zero), lo = x - hi (exact); n % 4 == 0 */
 int pxl_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 /* watchdog of the mbarrier pipelines: 0 = healthy, else the role that timed out (synchronises) */

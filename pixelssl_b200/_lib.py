@@ -23,7 +23,7 @@ class ConvTcExt(ctypes.Structure):
     """mirror of pxl_conv_tc_ext"""
     _fields_ = [('w_ntaps', c_int), ('widx_host', ctypes.POINTER(c_int)), ('out_mul', c_int),
                 ('out_offy', c_int), ('out_offx', c_int), ('out_H', c_int), ('out_W', c_int),
-                ('bn_stats', c_void_p)]
+                ('bn_stats', c_void_p), ('out_scale', c_float), ('out_scale_dev', c_void_p)]
 
 
 P = c_void_p
@@ -52,6 +52,11 @@ SIGNATURES = {
     'pxl_bn_finalize_apply': (c_int, [P, P, c_double, P, P, P, P, c_float, c_float, c_int, P, P, P, P, P, c_int, P, c_int64,
                                       c_int, P]),
     'pxl_bn_bwd_params': (c_int, [P, c_int, P, P, c_int, P]),
+    'pxl_bn_apply_h16': (c_int, [P, P, P, P, c_int, P, c_int64, c_int, P, P, c_float, P]),
+    'pxl_bn_finalize_apply_h16': (c_int, [P, P, c_double, P, P, P, P, c_float, c_float, c_int, P, P, P, P, P, c_int, P, c_int64,
+                                          c_int, P, P, c_float, P]),
+    'pxl_bn_bwd_reduce_h16': (c_int, [P, P, P, P, P, c_int, c_int64, c_int, P, P, P, P, P]),
+    'pxl_bn_bwd_dx_h16': (c_int, [P, P, P, P, P, P, P, c_double, c_int, P, P, c_int64, c_int, P, P, P, P, P, P, P, c_int, P]),
     'pxl_maxpool3x3s2_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'pxl_maxpool3x3s2_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'pxl_conv_nhwc': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P]),
@@ -59,6 +64,13 @@ SIGNATURES = {
     'pxl_conv_tc_launch': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P, P, P]),
     'pxl_conv_tc_launch_ex': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), ctypes.POINTER(ConvTcExt), P, P, P, P, P, P, P]),
     'pxl_conv_wgrad_tc_launch': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P, P]),
+    'pxl_conv_h16_launch': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), ctypes.POINTER(ConvTcExt), P, P, P, P, P, P, P]),
+    'pxl_conv_wgrad_h16_launch': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P, c_float, P, P]),
+    'pxl_h16_split': (c_int, [P, P, P, c_int64, c_float, P, c_int, P]),
+    'pxl_h16_absmax': (c_int, [P, c_int64, P, P]),
+    'pxl_h16_sat_counter': (c_void_p, []),
+    'pxl_h16_status': (c_int, []),
+    'pxl_h16_reset_status': (c_int, []),
     'pxl_split_tf32': (c_int, [P, P, P, c_int64, P]),
     'pxl_conv_tc_status': (c_int, []),
     'pxl_conv_transpose_weights': (c_int, [P, P, c_int, c_int, c_int, P]),

@@ -44,3 +44,15 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+
+// power-of-two scale s = 2^(target_log2 - e) with amax <= 2^e: amax * s lands in (2^(target-1), 2^target]
+// (fp16 pairs of gradient tensors, csrc/h16_prep.cu); 1 for a zero / non-finite absmax
+__device__ __forceinline__ float pxl_pow2_scale(float amax, int target_log2) {
+    if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+    int e;
+    frexpf(amax, &e);
+    int k = target_log2 - e;
+    if (k > 126) k = 126;
+    if (k < -126) k = -126;
+    return ldexpf(1.f, k);
+}

@@ -50,15 +50,17 @@ static EncodeTiledFn get_encode() {
 // NHWC fp32 tensor viewed as (C, W, H, N), box {32, bw, bh, 1}, 128-byte swizzle, zero OOB fill
 // estride = traversal stride of the W/H dims (2 for stride-2 convolutions: the box spans 2x the pixels
 // and the TMA unit picks every 2nd one)
-static int make_act_map(CUtensorMap* m, const float* base, int C, int W, int H, int N, int bw, int bh, int estride = 1) {
+// f16: the tensor holds __half (one half of an fp16 pair, see h16_prep.cu); a 128-byte row is then 64 channels
+static int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int bw, int bh, int estride = 1, int f16 = 0) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return PXL_ERR_UNSUPPORTED;
+    const cuuint64_t eb = f16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), 1};
+    cuuint64_t strides[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
+    cuuint32_t box[4] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
     if (box[1] > 256 || box[2] > 256) return PXL_ERR_UNSUPPORTED;
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : PXL_ERR_BAD_ARG;
@@ -81,14 +83,14 @@ static int make_out_map(CUtensorMap* m, const float* base, int Cout, int ldo, in
 }
 
 // weights [rows][K] fp32, box {32, bn}
-static int make_w_map(CUtensorMap* m, const float* base, int64_t K, int rows, int bn) {
+static int make_w_map(CUtensorMap* m, const void* base, int64_t K, int rows, int bn, int f16 = 0) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return PXL_ERR_UNSUPPORTED;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-    cuuint32_t box[2] = {32, (cuuint32_t)bn};
+    cuuint64_t strides[1] = {(cuuint64_t)K * (f16 ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)bn};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : PXL_ERR_BAD_ARG;
@@ -181,6 +183,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// one K step (32 bytes of K per operand row: 8 tf32 or 16 fp16 values) of the selected kind
+__device__ __forceinline__ void umma_any(int f16, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (f16) umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+    else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -220,6 +235,10 @@ __device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t smem_addr) {
 __device__ __forceinline__ uint32_t tf32_idesc(int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+// kind::f16 with fp16 operands (a_format = b_format = 0), D fp32, K-major, M = 128, N
+__device__ __forceinline__ uint32_t f16_idesc(int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
 
 // ------------------------------------------------------------------------------------------
 struct TcParams {
@@ -233,6 +252,9 @@ struct TcParams {
     int out_mul, out_offy, out_offx, outH, outW;   // output pixel (oy,ox) is stored at (oy*out_mul+offy, ox*out_mul+offx)
     int ntilesN, total_tiles;   // persistent kernel: N tiles per pixel tile, tiles in total
     int tma_store;  // epilogue stages 32-channel slabs in the (drained) operand ring and writes them with TMA
+    int f16;        // operands are fp16 (kind::f16); nsplit == 3 then means the fp16 pair hi/lo of both operands
+    int kc;         // K elements per 128-byte operand row: 32 (tf32) or 64 (fp16)
+    float out_scale;   // the accumulator is multiplied by this (and by *oscale_ptr) before bias / statistics / store
     short dy[PXL_MAX_TAPS], dx[PXL_MAX_TAPS], widx[PXL_MAX_TAPS];
 };
 
@@ -243,7 +265,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
                const __grid_constant__ CUtensorMap mapOut,
                const TcParams p, const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats,
-               int* __restrict__ err_flag) {
+               int* __restrict__ err_flag, const float* __restrict__ oscale_ptr) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full_bar[8], empty_bar[8], ready_bar[8], acc_bar;
     __shared__ uint32_t tmem_base_slot;
@@ -288,7 +310,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                 ok = mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 1);
                 if (!ok) break;
-                const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * 32;
+                const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * p.kc;
                 uint8_t* sa = smem + (size_t)s * stage_bytes;
                 mbar_expect_tx(&full_bar[s], tx);
                 const int ax = w0 * p.in_mul + p.dx[tap], ay = h0 * p.in_mul + p.dy[tap];
@@ -304,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
-            const uint32_t idesc = tf32_idesc(p.BN);
+            const uint32_t idesc = p.f16 ? f16_idesc(p.BN) : tf32_idesc(p.BN);
             bool ok = true;
             for (int it = 0; it < iters && ok; ++it) {
                 const int s = it % p.stages;
@@ -317,13 +339,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint32_t acc = tmem_d + (uint32_t)(it % p.nacc) * acc_cols;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)      // UMMA_K = 8 tf32 = 32 B: advance the start address by 2 x 16 B
-                    umma_tf32(acc, da + 2 * k, db + 2 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
+                    umma_any(p.f16, acc, da + 2 * k, db + 2 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
                 if (p.nsplit == 3) {
                     const uint64_t dal = kmajor_sw128_desc(sa + per_op), dbl = kmajor_sw128_desc(sa + per_op + TC_A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_tf32(acc, dal + 2 * k, db + 2 * k, idesc, 1);
+                    for (int k = 0; k < 4; ++k) umma_any(p.f16, acc, dal + 2 * k, db + 2 * k, idesc, 1);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_tf32(acc, da + 2 * k, dbl + 2 * k, idesc, 1);
+                    for (int k = 0; k < 4; ++k) umma_any(p.f16, acc, da + 2 * k, dbl + 2 * k, idesc, 1);
                 }
                 umma_commit(&empty_bar[s]);      // frees the smem slot once these MMAs have read it
             }
@@ -373,6 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const bool valid = hy < p.BH && oy < p.OH && ox < p.OW;
             float* orow = out + ((int64_t)(n * p.outH + oy * p.out_mul + p.out_offy) * p.outW + ox * p.out_mul + p.out_offx) * p.ldo;
             const int used = iters < p.nacc ? iters : p.nacc;
+            const float osc = p.out_scale * (oscale_ptr ? __ldg(oscale_ptr) : 1.f);
             for (int j = 0; j < p.BN; j += 32) {
                 float v[32];
                 tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)j, v);   // warp-collective
@@ -381,6 +404,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)a * acc_cols + (uint32_t)j, u);
 #pragma unroll
                     for (int c = 0; c < 32; ++c) v[c] += u[c];
+                }
+                if (osc != 1.f) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] *= osc;
                 }
                 const int cb = n0 + j;
                 if (stats) {
@@ -491,7 +518,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                        const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
                        const __grid_constant__ CUtensorMap mapOut,
                        const TcParams p, const float* __restrict__ bias, float* __restrict__ out,
-                       double* __restrict__ stats, int* __restrict__ err_flag) {
+                       double* __restrict__ stats, int* __restrict__ err_flag, const float* __restrict__ oscale_ptr) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full_bar[8], empty_bar[8], ready_bar[8], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
@@ -534,7 +561,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                     const uint32_t ph = (gs / p.stages) & 1u;
                     ok = mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 1);
                     if (!ok) break;
-                    const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * 32;
+                    const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * p.kc;
                     uint8_t* sa = smem + (size_t)s * stage_bytes;
                     mbar_expect_tx(&full_bar[s], tx);
                     const int ax = w0 * p.in_mul + p.dx[tap], ay = h0 * p.in_mul + p.dy[tap];
@@ -551,7 +578,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc = tf32_idesc(p.BN);
+            const uint32_t idesc = p.f16 ? f16_idesc(p.BN) : tf32_idesc(p.BN);
             uint32_t gs = 0, tcount = 0;
             bool ok = true;
             for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++tcount) {
@@ -571,13 +598,13 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                     const uint32_t acc = set_base + (uint32_t)(it % p.nacc) * acc_cols;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_tf32(acc, da + 2 * k, db + 2 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
+                        umma_any(p.f16, acc, da + 2 * k, db + 2 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
                     if (p.nsplit == 3) {
                         const uint64_t dal = kmajor_sw128_desc(sa + per_op), dbl = kmajor_sw128_desc(sa + per_op + TC_A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_tf32(acc, dal + 2 * k, db + 2 * k, idesc, 1);
+                        for (int k = 0; k < 4; ++k) umma_any(p.f16, acc, dal + 2 * k, db + 2 * k, idesc, 1);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_tf32(acc, da + 2 * k, dbl + 2 * k, idesc, 1);
+                        for (int k = 0; k < 4; ++k) umma_any(p.f16, acc, da + 2 * k, dbl + 2 * k, idesc, 1);
                     }
                     umma_commit(&empty_bar[s]);
                 }
@@ -590,6 +617,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         const int r = q * 32 + lane;
         const int et = threadIdx.x - 64;                 // 0..127
         uint32_t tcount = 0, sc = 0;
+        const float osc = p.out_scale * (oscale_ptr ? __ldg(oscale_ptr) : 1.f);
         bool ok = true;
         for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++tcount) {
             const uint32_t set = tcount & 1u, aph = (tcount >> 1) & 1u;
@@ -614,6 +642,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                     tmem_ld32(tbase + (uint32_t)a * acc_cols + (uint32_t)j, u);
 #pragma unroll
                     for (int c = 0; c < 32; ++c) v[c] += u[c];
+                }
+                if (osc != 1.f) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] *= osc;
                 }
                 if (bias) {
 #pragma unroll
@@ -768,6 +800,18 @@ __device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_any(int f16, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (f16) umma2_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+    else umma2_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+}
 __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
@@ -785,7 +829,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
                     const __grid_constant__ CUtensorMap mapOut,
                     const TcParams p, const float* __restrict__ bias, float* __restrict__ out,
-                    double* __restrict__ stats, int* __restrict__ err_flag) {
+                    double* __restrict__ stats, int* __restrict__ err_flag, const float* __restrict__ oscale_ptr) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full_bar[8], empty_bar[8], ready_bar[8], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
@@ -833,7 +877,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const uint32_t ph = (gs / p.stages) & 1u;
                     ok = mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 1);
                     if (!ok) break;
-                    const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * 32;
+                    const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * p.kc;
                     uint8_t* sa = smem + (size_t)s * stage_bytes;
                     const int ax = w0 * p.in_mul + p.dx[tap], ay = h0 * p.in_mul + p.dy[tap];
                     const int bk = p.widx[tap] * p.Cin + c0;
@@ -861,7 +905,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         // ================= MMA issuer (leader CTA, one thread) =================
         if (leader && lane == 0) {
             // M = 256 (bits 24..28 = M >> 4), N = BN
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (p.f16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
             uint32_t gs = 0, tcount = 0;
             bool ok = true;
             for (int work = cid; work < p.total_tiles && ok; work += nclusters, ++tcount) {
@@ -881,13 +925,13 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const uint32_t acc = set_base + (uint32_t)(it % p.nacc) * acc_cols;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma2_tf32(acc, da + 2 * k, db + 2 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
+                        umma2_any(p.f16, acc, da + 2 * k, db + 2 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
                     if (p.nsplit == 3) {
                         const uint64_t dal = kmajor_sw128_desc(sa + per_op), dbl = kmajor_sw128_desc(sa + per_op + TC_A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma2_tf32(acc, dal + 2 * k, db + 2 * k, idesc, 1);
+                        for (int k = 0; k < 4; ++k) umma2_any(p.f16, acc, dal + 2 * k, db + 2 * k, idesc, 1);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma2_tf32(acc, da + 2 * k, dbl + 2 * k, idesc, 1);
+                        for (int k = 0; k < 4; ++k) umma2_any(p.f16, acc, da + 2 * k, dbl + 2 * k, idesc, 1);
                     }
                     umma2_commit_mc(&empty_bar[s]);          // frees the slot in both CTAs
                 }
@@ -900,6 +944,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         const int r = q * 32 + lane;
         const int et = threadIdx.x - 64;
         uint32_t tcount = 0, sc = 0;
+        const float osc = p.out_scale * (oscale_ptr ? __ldg(oscale_ptr) : 1.f);
         bool ok = true;
         for (int work = cid; work < p.total_tiles && ok; work += nclusters, ++tcount) {
             const uint32_t set = tcount & 1u, aph = (tcount >> 1) & 1u;
@@ -924,6 +969,10 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     tmem_ld32(tbase + (uint32_t)a * acc_cols + (uint32_t)j, u);
 #pragma unroll
                     for (int c = 0; c < 32; ++c) v[c] += u[c];
+                }
+                if (osc != 1.f) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] *= osc;
                 }
                 if (bias) {
 #pragma unroll
@@ -1075,33 +1124,55 @@ static void pick_tile(int OH, int OW, bool flat, int& BW, int& BH) {
     }
 }
 
-extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, const pxl_conv_tc_ext* ext,
-                                     const float* in_hi, const float* in_lo, const float* w_hi, const float* w_lo,
-                                     const float* bias, float* out, void* stream);
+static int conv_tc_launch_core(const pxl_conv_geom* g, const int* taps, const pxl_conv_tc_ext* ext,
+                               const void* in_hi, const void* in_lo, const void* w_hi, const void* w_lo,
+                               const float* bias, float* out, void* stream);
 
 // lo parts: for precision 2 the caller passes hi/lo through `in`/`w` (hi) and the extra pointers
 extern "C" int pxl_conv_tc_launch(const pxl_conv_geom* g, const int* taps, const float* in_hi, const float* in_lo,
                                   const float* w_hi, const float* w_lo, const float* bias, float* out, void* stream) {
-    return pxl_conv_tc_launch_ex(g, taps, nullptr, in_hi, in_lo, w_hi, w_lo, bias, out, stream);
+    if (g && g->precision > 2) return PXL_ERR_BAD_ARG;      // fp16 operands go through pxl_conv_h16_launch
+    return conv_tc_launch_core(g, taps, nullptr, in_hi, in_lo, w_hi, w_lo, bias, out, stream);
 }
 
 extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, const pxl_conv_tc_ext* ext,
                                      const float* in_hi, const float* in_lo, const float* w_hi, const float* w_lo,
                                      const float* bias, float* out, void* stream) {
+    if (g && g->precision > 2) return PXL_ERR_BAD_ARG;
+    return conv_tc_launch_core(g, taps, ext, in_hi, in_lo, w_hi, w_lo, bias, out, stream);
+}
+
+// fp16-pair operands (h16_prep.cu): precision 3 = hi*hi + lo*hi + hi*lo (fp32-grade), 4 = hi*hi only (11-bit
+// significands = TF32-grade)
+extern "C" int pxl_conv_h16_launch(const pxl_conv_geom* g, const int* taps, const pxl_conv_tc_ext* ext,
+                                   const void* in_hi, const void* in_lo, const void* w_hi, const void* w_lo,
+                                   const float* bias, float* out, void* stream) {
+    if (!g || (g->precision != 3 && g->precision != 4)) return PXL_ERR_BAD_ARG;
+    return conv_tc_launch_core(g, taps, ext, in_hi, in_lo, w_hi, w_lo, bias, out, stream);
+}
+
+static int conv_tc_launch_core(const pxl_conv_geom* g, const int* taps, const pxl_conv_tc_ext* ext,
+                               const void* in_hi, const void* in_lo, const void* w_hi, const void* w_lo,
+                               const float* bias, float* out, void* stream) {
     if (!g || !taps || !in_hi || !w_hi || !out) return PXL_ERR_BAD_ARG;
     if ((g->mul != 1 && g->mul != 2) || g->div != 1) return PXL_ERR_UNSUPPORTED;
-    if (g->Cin % 32 != 0 || g->ntaps > PXL_MAX_TAPS) return PXL_ERR_UNSUPPORTED;
+    const int f16 = g->precision >= 3 ? 1 : 0;
+    const int kc = f16 ? 64 : 32;
+    if (g->Cin % kc != 0 || g->ntaps > PXL_MAX_TAPS) return PXL_ERR_UNSUPPORTED;
     const int wtaps = ext && ext->w_ntaps > 0 ? ext->w_ntaps : g->ntaps;    // taps in the weight tensor
-    const int nsplit = g->precision == 2 ? 3 : 1;
+    const int nsplit = (g->precision == 2 || g->precision == 3) ? 3 : 1;
     if (nsplit == 3 && !w_lo) return PXL_ERR_BAD_ARG;
-    const int a_inkernel = (nsplit == 3 && !in_lo) ? 1 : 0;       // in_hi then holds the raw fp32 activations
+    if (f16 && nsplit == 3 && !in_lo) return PXL_ERR_BAD_ARG;    // fp16 pairs are always split by their producer
+    const int a_inkernel = (!f16 && nsplit == 3 && !in_lo) ? 1 : 0;       // in_hi then holds the raw fp32 activations
     const int omul = (ext && ext->out_mul > 0) ? ext->out_mul : 1;
     const bool has_out_xform = ext && (omul != 1 || ext->out_offy != 0 || ext->out_offx != 0);
     bool flat = (g->ntaps == 1 && taps[0] == 0 && taps[1] == 0 && g->OH == g->H && g->OW == g->W && g->mul == 1 &&
                  !has_out_xform);
     TcParams p;
-    p.Cin = g->Cin; p.Cout = g->Cout; p.ldo = g->ldo; p.ntaps = g->ntaps; p.kchunks = g->Cin / 32;
-    p.nsplit = nsplit; p.a_inkernel = a_inkernel;
+    p.Cin = g->Cin; p.Cout = g->Cout; p.ldo = g->ldo; p.ntaps = g->ntaps; p.kchunks = g->Cin / kc;
+    p.nsplit = nsplit; p.a_inkernel = a_inkernel; p.f16 = f16; p.kc = kc;
+    p.out_scale = (ext && ext->out_scale != 0.f) ? ext->out_scale : 1.f;
+    const float* oscale_ptr = ext ? ext->out_scale_dev : nullptr;
     for (int t = 0; t < g->ntaps; ++t) {
         p.dy[t] = (short)taps[2 * t]; p.dx[t] = (short)taps[2 * t + 1];
         p.widx[t] = (short)((ext && ext->widx_host) ? ext->widx_host[t] : t);
@@ -1126,14 +1197,19 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
     // tuning knobs (environment, read once): shared-memory budget per CTA in KB (<= ~100 lets two CTAs share
     // an SM so one CTA's epilogue overlaps the other's main loop), N-tile cap, accumulator count
     static int cfg_budget_kb = -1, cfg_bn_max1 = 256, cfg_bn_max3 = 128, cfg_nacc3 = 4;
+    static int cfg_bn_max_h3 = 128, cfg_bn_max_h1 = 256, cfg_nacc_h3 = 2, cfg_nacc_h1 = 1;
     if (cfg_budget_kb < 0) {
         const char* e = getenv("PXL_TC_SMEM_KB"); cfg_budget_kb = e ? atoi(e) : 200;
         if ((e = getenv("PXL_TC_BN_MAX_TF32"))) cfg_bn_max1 = atoi(e);
         if ((e = getenv("PXL_TC_BN_MAX_TF32X3"))) cfg_bn_max3 = atoi(e);
         if ((e = getenv("PXL_TC_NACC_TF32X3"))) cfg_nacc3 = atoi(e);
+        if ((e = getenv("PXL_TC_BN_MAX_F16X3"))) cfg_bn_max_h3 = atoi(e);
+        if ((e = getenv("PXL_TC_BN_MAX_F16"))) cfg_bn_max_h1 = atoi(e);
+        if ((e = getenv("PXL_TC_NACC_F16X3"))) cfg_nacc_h3 = atoi(e);
+        if ((e = getenv("PXL_TC_NACC_F16"))) cfg_nacc_h1 = atoi(e);
     }
     p.BN = g->Cout > 128 ? 256 : (g->Cout > 64 ? 128 : (g->Cout > 32 ? 64 : 32));
-    const int bn_cap = nsplit == 3 ? cfg_bn_max3 : cfg_bn_max1;
+    const int bn_cap = f16 ? (nsplit == 3 ? cfg_bn_max_h3 : cfg_bn_max_h1) : (nsplit == 3 ? cfg_bn_max3 : cfg_bn_max1);
     if (p.BN > bn_cap) p.BN = bn_cap;
     static int cfg_persist = -1;
     if (cfg_persist < 0) { const char* e = getenv("PXL_TC_PERSIST"); cfg_persist = e ? atoi(e) : 1; }
@@ -1158,7 +1234,8 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
         if (pix_tiles >= 2) use_pair = 1;
     }
     if (use_pair) use_persist = 1;
-    p.nacc = nsplit == 3 ? cfg_nacc3 : 1;
+    p.nacc = f16 ? (nsplit == 3 ? cfg_nacc_h3 : cfg_nacc_h1) : (nsplit == 3 ? cfg_nacc3 : 1);
+    if (p.nacc < 1) p.nacc = 1;
     // TMEM: 512 columns per SM; the persistent kernel keeps two accumulator sets (epilogue / main loop overlap)
     while (p.nacc > 1 && (p.BN < 32 ? 32 : p.BN) * p.nacc * (use_persist ? 2 : 1) > 512) p.nacc >>= 1;
     const int per_op = TC_A_BYTES + (use_pair ? p.BN / 2 : p.BN) * 128;
@@ -1180,18 +1257,18 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
     const size_t smem = use_persist ? (size_t)p.stages * stage_bytes + persist_fixed : (size_t)p.stages * stage_bytes + 1024;
 
     CUtensorMap mA, mAlo, mB, mBlo;
-    int rc = make_act_map(&mA, in_hi, g->Cin, mapW, mapH, mapN, p.BW, p.BH, g->mul);
+    int rc = make_act_map(&mA, in_hi, g->Cin, mapW, mapH, mapN, p.BW, p.BH, g->mul, f16);
     if (rc) return rc;
     const int b_box_rows = use_pair ? p.BN / 2 : p.BN;
-    rc = make_w_map(&mB, w_hi, (int64_t)wtaps * g->Cin, g->Cout, b_box_rows);
+    rc = make_w_map(&mB, w_hi, (int64_t)wtaps * g->Cin, g->Cout, b_box_rows, f16);
     if (rc) return rc;
     if (nsplit == 3) {
         if (a_inkernel) mAlo = mA;
         else {
-            rc = make_act_map(&mAlo, in_lo, g->Cin, mapW, mapH, mapN, p.BW, p.BH, g->mul);
+            rc = make_act_map(&mAlo, in_lo, g->Cin, mapW, mapH, mapN, p.BW, p.BH, g->mul, f16);
             if (rc) return rc;
         }
-        rc = make_w_map(&mBlo, w_lo, (int64_t)wtaps * g->Cin, g->Cout, b_box_rows);
+        rc = make_w_map(&mBlo, w_lo, (int64_t)wtaps * g->Cin, g->Cout, b_box_rows, f16);
         if (rc) return rc;
     } else {
         mAlo = mA; mBlo = mB;
@@ -1238,7 +1315,7 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         double* st_ptr = ext ? (double*)ext->bn_stats : nullptr;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, mA, mAlo, mB, mBlo, mO, p, bias, out, st_ptr, g_err_flag);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, mA, mAlo, mB, mBlo, mO, p, bias, out, st_ptr, g_err_flag, oscale_ptr);
         if (e != cudaSuccess) return (int)e;
         pxl_count_launch_(1);
         return 0;
@@ -1251,12 +1328,12 @@ extern "C" int pxl_conv_tc_launch_ex(const pxl_conv_geom* g, const int* taps, co
             attr2 = true;
         }
         const unsigned nblk = (unsigned)(p.total_tiles < PXL_NUM_SMS ? p.total_tiles : PXL_NUM_SMS);
-        conv_tc_persist_kernel<<<nblk, 320, smem, st>>>(mA, mAlo, mB, mBlo, mO, p, bias, out, ext ? ext->bn_stats : nullptr, g_err_flag);
+        conv_tc_persist_kernel<<<nblk, 320, smem, st>>>(mA, mAlo, mB, mBlo, mO, p, bias, out, ext ? ext->bn_stats : nullptr, g_err_flag, oscale_ptr);
         PXL_CHECK_LAUNCH();
         return 0;
     }
     dim3 grid((unsigned)((int64_t)p.N * p.tilesH * p.tilesW), (unsigned)((g->Cout + p.BN - 1) / p.BN));
-    conv_tc_kernel<<<grid, 192, smem, st>>>(mA, mAlo, mB, mBlo, mO, p, bias, out, ext ? ext->bn_stats : nullptr, g_err_flag);
+    conv_tc_kernel<<<grid, 192, smem, st>>>(mA, mAlo, mB, mBlo, mO, p, bias, out, ext ? ext->bn_stats : nullptr, g_err_flag, oscale_ptr);
     PXL_CHECK_LAUNCH();
     return 0;
 }
@@ -1294,6 +1371,9 @@ struct WgParams {
     int BW, BH, tilesW, tilesH, rows, rows_alloc;
     int BN, stages, nsplit, nacc;
     int inkernel;      // 3xTF32: dY / X arrive raw and are split hi/lo in shared memory by the epilogue warps
+    int f16;           // fp16 operands (kind::f16): 64-channel slabs, 16 pixel rows per MMA, plain SWIZZLE_128B
+    int slab_ch;       // channels per 128-byte slab row: 32 (tf32) or 64 (fp16)
+    float out_scale;   // the tile is multiplied by this (and by *oscale_ptr) before it is added into dW
     int tiles_ci, ktiles_per_cta, ktiles_total;
     short dy[PXL_MAX_TAPS], dx[PXL_MAX_TAPS];
 };
@@ -1313,18 +1393,32 @@ __device__ __forceinline__ uint64_t mnmajor_sw128_desc(uint32_t smem_addr, uint3
     return d;
 }
 
+// MN-major 16-bit operands use the plain SWIZZLE_128B layout (cute Layout_MN_SW128_Atom: 64 elements x 8 K-rows,
+// Swizzle<3,4,3>): LBO = byte distance between 64-element MN slabs, SBO = 1024 B between 8-row K groups.
+__device__ __forceinline__ uint64_t mnmajor_sw128_f16_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;       // LayoutType::SWIZZLE_128B
+    return d;
+}
+
 __global__ void __launch_bounds__(320, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapDyLo,
                      const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapXLo,
-                     const WgParams p, float* __restrict__ dw, int* __restrict__ err_flag) {
+                     const WgParams p, float* __restrict__ dw, int* __restrict__ err_flag,
+                     const float* __restrict__ oscale_ptr) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full_bar[8], empty_bar[8], ready_bar[8], acc_bar;
     __shared__ uint32_t tmem_base_slot;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 
     const int slab_bytes = p.rows_alloc * 128;
-    const int slabsB = p.BN / 32;
-    const int per_op = (4 + slabsB) * slab_bytes;
+    const int slabsA = 128 / p.slab_ch;                  // dY slabs (128 output channels)
+    const int slabsB = p.BN / p.slab_ch;
+    const int per_op = (slabsA + slabsB) * slab_bytes;
     const int stage_bytes = per_op * (p.nsplit == 3 ? 2 : 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_co = blockIdx.x / p.tiles_ci, tile_ci = blockIdx.x % p.tiles_ci;
@@ -1337,8 +1431,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
     const uint32_t acc_cols = p.BN < 32 ? 32 : p.BN;
     const uint32_t tmem_cols = acc_cols * p.nacc;
     // slabs that actually exist (the others stay zero)
-    int nsA = (p.ldo - co0 + 31) / 32; if (nsA > 4) nsA = 4;
-    int nsB = (p.Cin - ci0 + 31) / 32; if (nsB > slabsB) nsB = slabsB;
+    int nsA = (p.ldo - co0 + p.slab_ch - 1) / p.slab_ch; if (nsA > slabsA) nsA = slabsA;
+    int nsB = (p.Cin - ci0 + p.slab_ch - 1) / p.slab_ch; if (nsB > slabsB) nsB = slabsB;
 
     // zero the operand ring once: rows the TMA never writes must contribute nothing
     {
@@ -1380,18 +1474,20 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
                         const CUtensorMap* mdy = part ? &mapDyLo : &mapDy;
                         const CUtensorMap* mx = part ? &mapXLo : &mapX;
                         for (int j = 0; j < nsA; ++j)
-                            tma_load_4d(base + (size_t)j * slab_bytes, mdy, &full_bar[s], co0 + 32 * j, w0, h0, n);
+                            tma_load_4d(base + (size_t)j * slab_bytes, mdy, &full_bar[s], co0 + p.slab_ch * j, w0, h0, n);
                         for (int j = 0; j < nsB; ++j)
-                            tma_load_4d(base + (size_t)(4 + j) * slab_bytes, mx, &full_bar[s], ci0 + 32 * j,
+                            tma_load_4d(base + (size_t)(slabsA + j) * slab_bytes, mx, &full_bar[s], ci0 + p.slab_ch * j,
                                         w0 * p.mul + tdx, h0 * p.mul + tdy, n);
                     }
                 }
             }
         } else if (warp == 1) {
             if (lane == 0) {
-                // D fp32, A/B tf32, both MN-major (bits 15,16), M = 128, N = BN
-                const uint32_t idesc = tf32_idesc(p.BN) | (1u << 15) | (1u << 16);
-                const int kmma = p.rows_alloc / 8;
+                // D fp32, A/B tf32 or fp16, both MN-major (bits 15,16), M = 128, N = BN
+                const uint32_t idesc = (p.f16 ? f16_idesc(p.BN) : tf32_idesc(p.BN)) | (1u << 15) | (1u << 16);
+                const int krows = p.f16 ? 16 : 8;                 // pixel rows one MMA consumes
+                const int kmma = p.rows_alloc / krows;
+                const uint64_t kstep = (uint64_t)(krows * 128 / 16);   // descriptor start-address advance per MMA
                 bool ok = true;
                 for (int it = 0; it < iters && ok; ++it) {
                     const int s = it % p.stages;
@@ -1401,15 +1497,16 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t acc = tmem_d + (uint32_t)(it % p.nacc) * acc_cols;
-                    const uint64_t da = mnmajor_sw128_desc(sa, (uint32_t)slab_bytes);
-                    const uint64_t db = mnmajor_sw128_desc(sa + 4 * slab_bytes, (uint32_t)slab_bytes);
-                    for (int k = 0; k < kmma; ++k)       // 8 pixel rows = 1024 B per MMA: +64 (x16 B)
-                        umma_tf32(acc, da + 64 * k, db + 64 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
+                    const uint32_t sb = sa + (uint32_t)(slabsA * slab_bytes);
+                    const uint64_t da = p.f16 ? mnmajor_sw128_f16_desc(sa, (uint32_t)slab_bytes) : mnmajor_sw128_desc(sa, (uint32_t)slab_bytes);
+                    const uint64_t db = p.f16 ? mnmajor_sw128_f16_desc(sb, (uint32_t)slab_bytes) : mnmajor_sw128_desc(sb, (uint32_t)slab_bytes);
+                    for (int k = 0; k < kmma; ++k)
+                        umma_any(p.f16, acc, da + kstep * k, db + kstep * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
                     if (p.nsplit == 3) {
-                        const uint64_t dal = mnmajor_sw128_desc(sa + per_op, (uint32_t)slab_bytes);
-                        const uint64_t dbl = mnmajor_sw128_desc(sa + per_op + 4 * slab_bytes, (uint32_t)slab_bytes);
-                        for (int k = 0; k < kmma; ++k) umma_tf32(acc, dal + 64 * k, db + 64 * k, idesc, 1);
-                        for (int k = 0; k < kmma; ++k) umma_tf32(acc, da + 64 * k, dbl + 64 * k, idesc, 1);
+                        const uint64_t dal = p.f16 ? mnmajor_sw128_f16_desc(sa + per_op, (uint32_t)slab_bytes) : mnmajor_sw128_desc(sa + per_op, (uint32_t)slab_bytes);
+                        const uint64_t dbl = p.f16 ? mnmajor_sw128_f16_desc(sb + per_op, (uint32_t)slab_bytes) : mnmajor_sw128_desc(sb + per_op, (uint32_t)slab_bytes);
+                        for (int k = 0; k < kmma; ++k) umma_any(p.f16, acc, dal + kstep * k, db + kstep * k, idesc, 1);
+                        for (int k = 0; k < kmma; ++k) umma_any(p.f16, acc, da + kstep * k, dbl + kstep * k, idesc, 1);
                     }
                     umma_commit(&empty_bar[s]);
                 }
@@ -1456,6 +1553,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
             tc_fence_after();
             if (ok) {
                 const int used = iters < p.nacc ? iters : p.nacc;
+                const float osc = p.out_scale * (oscale_ptr ? __ldg(oscale_ptr) : 1.f);
                 float* drow = dw + ((int64_t)co * p.ntaps + tap) * p.Cin;
                 for (int j = 0; j < p.BN; j += 32) {
                     float v[32];
@@ -1470,7 +1568,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const int ci = ci0 + j + c;
-                        if (ci < p.Cin) atomicAdd(drow + ci, v[c]);
+                        if (ci < p.Cin) atomicAdd(drow + ci, v[c] * osc);
                     }
                 }
             }
@@ -1482,45 +1580,70 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
 }
 
 // activation map for wgrad: optional traversal stride (stride-2 convolutions read every 2nd pixel)
-static int make_act_map_strided(CUtensorMap* m, const float* base, int C, int W, int H, int N, int bw, int bh, int estride) {
+static int make_act_map_strided(CUtensorMap* m, const void* base, int C, int W, int H, int N, int bw, int bh, int estride, int f16 = 0) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return PXL_ERR_UNSUPPORTED;
+    const cuuint64_t eb = f16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), 1};
+    cuuint64_t strides[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
+    cuuint32_t box[4] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
     if (box[1] > 256 || box[2] > 256) return PXL_ERR_UNSUPPORTED;
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : PXL_ERR_BAD_ARG;
 }
 
-static void pick_ktile(int OH, int OW, bool flat, int maxrows, int& BW, int& BH) {
+static void pick_ktile(int OH, int OW, bool flat, int maxrows, int& BW, int& BH, int unit = 8) {
     if (flat) { BW = maxrows; BH = 1; return; }
     double best = -1.0;
     BW = 8; BH = maxrows / 8;
-    for (int bw = 1; bw <= maxrows; ++bw) {
-        const int bh = maxrows / bw;
+    for (int bw = 1; bw <= maxrows && bw <= 256; ++bw) {
+        int bh = maxrows / bw;
         if (bh < 1) break;
-        const int alloc = (bw * bh + 7) / 8 * 8;
+        if (bh > 256) bh = 256;
+        const int alloc = (bw * bh + unit - 1) / unit * unit;
         const int64_t tiles = (int64_t)((OW + bw - 1) / bw) * ((OH + bh - 1) / bh);
         const double eff = (double)OH * OW / ((double)tiles * alloc);
         if (eff > best + 1e-9) { best = eff; BW = bw; BH = bh; }
     }
 }
 
+static int conv_wgrad_tc_core(const pxl_conv_geom* g, const int* taps, const void* in_hi, const void* in_lo,
+                              const void* dy_hi, const void* dy_lo, float* dw, float out_scale, const float* oscale_ptr,
+                              void* stream);
+
 extern "C" int pxl_conv_wgrad_tc_launch(const pxl_conv_geom* g, const int* taps, const float* in_hi, const float* in_lo,
                                         const float* dy_hi, const float* dy_lo, float* dw, void* stream) {
+    if (g && g->precision > 2) return PXL_ERR_BAD_ARG;      // fp16 operands go through pxl_conv_wgrad_h16_launch
+    return conv_wgrad_tc_core(g, taps, in_hi, in_lo, dy_hi, dy_lo, dw, 1.f, nullptr, stream);
+}
+
+// fp16-pair operands; dw += out_scale * (*out_scale_dev) * sum(dy * x)
+extern "C" int pxl_conv_wgrad_h16_launch(const pxl_conv_geom* g, const int* taps, const void* in_hi, const void* in_lo,
+                                         const void* dy_hi, const void* dy_lo, float* dw, float out_scale,
+                                         const float* out_scale_dev, void* stream) {
+    if (!g || (g->precision != 3 && g->precision != 4)) return PXL_ERR_BAD_ARG;
+    return conv_wgrad_tc_core(g, taps, in_hi, in_lo, dy_hi, dy_lo, dw, out_scale != 0.f ? out_scale : 1.f, out_scale_dev, stream);
+}
+
+static int conv_wgrad_tc_core(const pxl_conv_geom* g, const int* taps, const void* in_hi, const void* in_lo,
+                              const void* dy_hi, const void* dy_lo, float* dw, float out_scale, const float* oscale_ptr,
+                              void* stream) {
     if (!g || !taps || !in_hi || !dy_hi || !dw) return PXL_ERR_BAD_ARG;
     if (g->div != 1 || (g->mul != 1 && g->mul != 2)) return PXL_ERR_UNSUPPORTED;   // stride 2 via TMA traversal stride
-    if (g->Cin % 32 != 0 || g->ldo % 32 != 0 || g->ntaps > PXL_MAX_TAPS) return PXL_ERR_UNSUPPORTED;
-    const int nsplit = g->precision == 2 ? 3 : 1;
+    const int f16 = g->precision >= 3 ? 1 : 0;
+    const int slab_ch = f16 ? 64 : 32;
+    if (g->Cin % slab_ch != 0 || g->ldo % slab_ch != 0 || g->ntaps > PXL_MAX_TAPS) return PXL_ERR_UNSUPPORTED;
+    const int nsplit = (g->precision == 2 || g->precision == 3) ? 3 : 1;
     if (nsplit == 3 && ((in_lo == nullptr) != (dy_lo == nullptr))) return PXL_ERR_BAD_ARG;
-    const int inkernel = (nsplit == 3 && !in_lo) ? 1 : 0;         // in_hi / dy_hi then hold the raw fp32 tensors
+    if (f16 && nsplit == 3 && !in_lo) return PXL_ERR_BAD_ARG;
+    const int inkernel = (!f16 && nsplit == 3 && !in_lo) ? 1 : 0;         // in_hi / dy_hi then hold the raw fp32 tensors
     const bool flat = (g->ntaps == 1 && taps[0] == 0 && taps[1] == 0 && g->OH == g->H && g->OW == g->W && g->mul == 1);
     WgParams p;
     p.Cin = g->Cin; p.Cout = g->Cout; p.ldo = g->ldo; p.ntaps = g->ntaps; p.mul = g->mul; p.nsplit = nsplit; p.inkernel = inkernel;
+    p.f16 = f16; p.slab_ch = slab_ch; p.out_scale = out_scale;
     for (int t = 0; t < g->ntaps; ++t) { p.dy[t] = (short)taps[2 * t]; p.dx[t] = (short)taps[2 * t + 1]; }
     int mapW, mapH, mapN, inW, inH;
     if (flat) {
@@ -1530,19 +1653,32 @@ extern "C" int pxl_conv_wgrad_tc_launch(const pxl_conv_geom* g, const int* taps,
     } else {
         p.N = g->N; p.OH = g->OH; p.OW = g->OW; mapW = g->OW; mapH = g->OH; mapN = g->N; inW = g->W; inH = g->H;
     }
-    static int cfg_wg_bn_max = -1;
-    if (cfg_wg_bn_max < 0) { const char* e = getenv("PXL_WG_BN_MAX"); cfg_wg_bn_max = e ? atoi(e) : 128; }
-    const bool wide = nsplit == 1 && cfg_wg_bn_max >= 256 && g->Cin >= 256;     // 128 x 256 tile, 32-row stages
-    const int maxrows = nsplit == 3 ? 32 : (wide ? 32 : 64);
-    pick_ktile(p.OH, p.OW, flat, maxrows, p.BW, p.BH);
+    static int cfg_wg_bn_max = -1, cfg_wg_bn_max_h3 = 128, cfg_wg_bn_max_h1 = 256, cfg_wg_rows_h3 = 64, cfg_wg_rows_h1 = 64;
+    if (cfg_wg_bn_max < 0) {
+        const char* e = getenv("PXL_WG_BN_MAX"); cfg_wg_bn_max = e ? atoi(e) : 128;
+        if ((e = getenv("PXL_WG_BN_MAX_F16X3"))) cfg_wg_bn_max_h3 = atoi(e);
+        if ((e = getenv("PXL_WG_BN_MAX_F16"))) cfg_wg_bn_max_h1 = atoi(e);
+        if ((e = getenv("PXL_WG_ROWS_F16X3"))) cfg_wg_rows_h3 = atoi(e);
+        if ((e = getenv("PXL_WG_ROWS_F16"))) cfg_wg_rows_h1 = atoi(e);
+    }
+    const bool wide = !f16 && nsplit == 1 && cfg_wg_bn_max >= 256 && g->Cin >= 256;     // 128 x 256 tile, 32-row stages
+    int maxrows = nsplit == 3 ? 32 : (wide ? 32 : 64);
+    if (f16) maxrows = nsplit == 3 ? cfg_wg_rows_h3 : cfg_wg_rows_h1;
+    const int kunit = f16 ? 16 : 8;                      // pixel rows per MMA
+    pick_ktile(p.OH, p.OW, flat, maxrows, p.BW, p.BH, kunit);
     p.rows = p.BW * p.BH;
-    p.rows_alloc = (p.rows + 7) / 8 * 8;
+    p.rows_alloc = (p.rows + kunit - 1) / kunit * kunit;
     p.tilesW = (p.OW + p.BW - 1) / p.BW; p.tilesH = (p.OH + p.BH - 1) / p.BH;
     p.BN = wide ? 256 : (g->Cin > 64 ? 128 : (g->Cin > 32 ? 64 : 32));
+    if (f16) {
+        const int cap = nsplit == 3 ? cfg_wg_bn_max_h3 : cfg_wg_bn_max_h1;
+        p.BN = g->Cin > 128 ? 256 : (g->Cin > 64 ? 128 : 64);
+        if (p.BN > cap) p.BN = cap < 64 ? 64 : cap;
+    }
     p.nacc = 512 / (p.BN < 32 ? 32 : p.BN); if (p.nacc > 4) p.nacc = 4;
     p.tiles_ci = (g->Cin + p.BN - 1) / p.BN;
     const int tiles_co = (g->Cout + 127) / 128;
-    const int stage_bytes = (4 + p.BN / 32) * p.rows_alloc * 128 * (nsplit == 3 ? 2 : 1);
+    const int stage_bytes = (128 / slab_ch + p.BN / slab_ch) * p.rows_alloc * 128 * (nsplit == 3 ? 2 : 1);
     p.stages = (200 * 1024) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return PXL_ERR_UNSUPPORTED;
@@ -1572,14 +1708,14 @@ extern "C" int pxl_conv_wgrad_tc_launch(const pxl_conv_geom* g, const int* taps,
     split = pxl_cdiv(p.ktiles_total, p.ktiles_per_cta);
 
     CUtensorMap mDy, mDyLo, mX, mXLo;
-    int rc = make_act_map_strided(&mDy, dy_hi, g->ldo, mapW, mapH, mapN, p.BW, p.BH, 1);
+    int rc = make_act_map_strided(&mDy, dy_hi, g->ldo, mapW, mapH, mapN, p.BW, p.BH, 1, f16);
     if (rc) return rc;
-    rc = make_act_map_strided(&mX, in_hi, g->Cin, inW, inH, mapN, p.BW, p.BH, g->mul);
+    rc = make_act_map_strided(&mX, in_hi, g->Cin, inW, inH, mapN, p.BW, p.BH, g->mul, f16);
     if (rc) return rc;
     if (nsplit == 3 && !inkernel) {
-        rc = make_act_map_strided(&mDyLo, dy_lo, g->ldo, mapW, mapH, mapN, p.BW, p.BH, 1);
+        rc = make_act_map_strided(&mDyLo, dy_lo, g->ldo, mapW, mapH, mapN, p.BW, p.BH, 1, f16);
         if (rc) return rc;
-        rc = make_act_map_strided(&mXLo, in_lo, g->Cin, inW, inH, mapN, p.BW, p.BH, g->mul);
+        rc = make_act_map_strided(&mXLo, in_lo, g->Cin, inW, inH, mapN, p.BW, p.BH, g->mul, f16);
         if (rc) return rc;
     } else { mDyLo = mDy; mXLo = mX; }
     if (!g_err_flag) {
@@ -1596,7 +1732,7 @@ extern "C" int pxl_conv_wgrad_tc_launch(const pxl_conv_geom* g, const int* taps,
     }
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     dim3 grid((unsigned)(tiles_co * p.tiles_ci), (unsigned)g->ntaps, (unsigned)split);
-    conv_wgrad_tc_kernel<<<grid, inkernel ? 320 : 192, smem, (cudaStream_t)stream>>>(mDy, mDyLo, mX, mXLo, p, dw, g_err_flag);
+    conv_wgrad_tc_kernel<<<grid, inkernel ? 320 : 192, smem, (cudaStream_t)stream>>>(mDy, mDyLo, mX, mXLo, p, dw, g_err_flag, oscale_ptr);
     PXL_CHECK_LAUNCH();
     return 0;
 }

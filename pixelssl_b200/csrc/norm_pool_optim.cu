@@ -3,6 +3,7 @@
 // tensor, with per-channel reductions finished in fp64 atomics (tiny: 2*C doubles per layer).
 #include "common.cuh"
 #include <math_constants.h>
+#include <cuda_fp16.h>
 
 // ------------------------------------------------------------------------------------------
 // thread layout shared by the per-channel reductions: a block covers CW = 4*TX channels
@@ -57,6 +58,28 @@ __device__ __forceinline__ void block_reduce_cols(float4 s0, float4 s1, int TX, 
         atomicAdd(out1 + 4 * c4 + 0, (double)b.x); atomicAdd(out1 + 4 * c4 + 1, (double)b.y);
         atomicAdd(out1 + 4 * c4 + 2, (double)b.z); atomicAdd(out1 + 4 * c4 + 3, (double)b.w);
     }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// fp16-pair outputs (csrc/h16_prep.cu): v*s = hi + lo, 4 channels -> one 8-byte store per plane.
+// Returns true when a value had to be clipped to the fp16 range.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool h16_store4(float4 v, float s, uint2* __restrict__ hi, uint2* __restrict__ lo, int64_t i) {
+    const float t[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
+    unsigned short h[4], l[4];
+    bool clipped = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float c = fminf(fmaxf(t[k], -65504.f), 65504.f);
+        clipped |= (c != t[k]) && (t[k] == t[k]);
+        const __half hh = __float2half_rn(c);
+        h[k] = __half_as_ushort(hh);
+        l[k] = __half_as_ushort(__float2half_rn(c - __half2float(hh)));
+    }
+    hi[i] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    if (lo) lo[i] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+    return clipped;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -150,8 +173,10 @@ extern "C" int pxl_bn_eval_coeffs(int C, const float* gamma, const float* beta, 
 template <bool RES, bool RELU>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float4* __restrict__ x, const float4* __restrict__ scale, const float4* __restrict__ shift,
-                const float4* __restrict__ res, float4* __restrict__ y, int64_t n4, int c4max) {
+                const float4* __restrict__ res, float4* __restrict__ y, int64_t n4, int c4max,
+                uint2* __restrict__ hi, uint2* __restrict__ lo, float hscale, int* __restrict__ sat) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool clipped = false;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const int c = (int)(i % c4max);
         float4 v = __ldcs(x + i);
@@ -160,22 +185,39 @@ bn_apply_kernel(const float4* __restrict__ x, const float4* __restrict__ scale, 
         v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
         if (RES) { float4 r = __ldcs(res + i); v = f4add(v, r); }
         if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        y[i] = v;
+        if (y) y[i] = v;
+        if (hi) clipped |= h16_store4(v, hscale, hi, lo, i);
     }
+    if (clipped && sat) atomicAdd(sat, 1);
 }
+
+extern "C" int* pxl_h16_sat_counter(void);
+
+extern "C" int pxl_bn_apply_h16(const float* x, const float* scale, const float* shift, const float* residual,
+                                int relu, float* y, int64_t rows, int C, void* hi, void* lo, float hscale, void* stream);
 
 extern "C" int pxl_bn_apply(const float* x, const float* scale, const float* shift, const float* residual,
                             int relu, float* y, int64_t rows, int C, void* stream) {
-    if (!x || !scale || !shift || !y || rows <= 0 || C <= 0 || (C & 3)) return PXL_ERR_BAD_ARG;
+    if (!y) return PXL_ERR_BAD_ARG;
+    return pxl_bn_apply_h16(x, scale, shift, residual, relu, y, rows, C, nullptr, nullptr, 1.f, stream);
+}
+
+// y nullable when the fp16 pair (hi, lo nullable) is the only output wanted
+extern "C" int pxl_bn_apply_h16(const float* x, const float* scale, const float* shift, const float* residual,
+                                int relu, float* y, int64_t rows, int C, void* hi, void* lo, float hscale, void* stream) {
+    if (!x || !scale || !shift || (!y && !hi) || rows <= 0 || C <= 0 || (C & 3)) return PXL_ERR_BAD_ARG;
     const int64_t n4 = rows * (C / 4);
     int blocks = (int)(pxl_cdiv(n4, 256 * 2) < PXL_NUM_SMS * 8 ? pxl_cdiv(n4, 256 * 2) : PXL_NUM_SMS * 8);
     cudaStream_t st = (cudaStream_t)stream;
     const float4 *x4 = (const float4*)x, *s4 = (const float4*)scale, *h4 = (const float4*)shift, *r4 = (const float4*)residual;
     float4* y4 = (float4*)y;
-    if (residual && relu) bn_apply_kernel<true, true><<<blocks, 256, 0, st>>>(x4, s4, h4, r4, y4, n4, C / 4);
-    else if (residual) bn_apply_kernel<true, false><<<blocks, 256, 0, st>>>(x4, s4, h4, r4, y4, n4, C / 4);
-    else if (relu) bn_apply_kernel<false, true><<<blocks, 256, 0, st>>>(x4, s4, h4, r4, y4, n4, C / 4);
-    else bn_apply_kernel<false, false><<<blocks, 256, 0, st>>>(x4, s4, h4, r4, y4, n4, C / 4);
+    int* sat = hi ? pxl_h16_sat_counter() : nullptr;
+#define PXL_AP_ARGS x4, s4, h4, r4, y4, n4, C / 4, (uint2*)hi, (uint2*)lo, hscale, sat
+    if (residual && relu) bn_apply_kernel<true, true><<<blocks, 256, 0, st>>>(PXL_AP_ARGS);
+    else if (residual) bn_apply_kernel<true, false><<<blocks, 256, 0, st>>>(PXL_AP_ARGS);
+    else if (relu) bn_apply_kernel<false, true><<<blocks, 256, 0, st>>>(PXL_AP_ARGS);
+    else bn_apply_kernel<false, false><<<blocks, 256, 0, st>>>(PXL_AP_ARGS);
+#undef PXL_AP_ARGS
     PXL_CHECK_LAUNCH();
     return 0;
 }
@@ -192,10 +234,12 @@ bn_finalize_apply_kernel(const float4* __restrict__ x, const double* __restrict_
                          float* running_mean, float* running_var, float momentum, float eps, int clamp_mode,
                          float* mean, float* invstd, float* scale, float* shift,
                          const float4* __restrict__ res, float4* __restrict__ y,
-                         int64_t rows, int C, int TX, int TY, int64_t rowsPerBlock) {
+                         int64_t rows, int C, int TX, int TY, int64_t rowsPerBlock,
+                         uint2* __restrict__ hi, uint2* __restrict__ lo, float hscale, int* __restrict__ sat) {
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
     if (c4 >= c4max) return;
+    bool clipped = false;
     float sc[4], sh[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -230,8 +274,10 @@ bn_finalize_apply_kernel(const float4* __restrict__ x, const double* __restrict_
         v.z = fmaf(v.z, sc[2], sh[2]); v.w = fmaf(v.w, sc[3], sh[3]);
         if (RES) { const float4 q = __ldcs(res + i); v = f4add(v, q); }
         if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        y[i] = v;
+        if (y) y[i] = v;
+        if (hi) clipped |= h16_store4(v, hscale, hi, lo, i);
     }
+    if (clipped && sat) atomicAdd(sat, 1);
 }
 
 static RedLayout stream_layout(int64_t rows, int C) {
@@ -252,17 +298,36 @@ static RedLayout stream_layout(int64_t rows, int C) {
     return L;
 }
 
+extern "C" int pxl_bn_finalize_apply_h16(const float* x, const double* sums, double count, const float* gamma,
+                                         const float* beta, float* running_mean, float* running_var, float momentum,
+                                         float eps, int clamp_mode, float* mean, float* invstd, float* scale, float* shift,
+                                         const float* residual, int relu, float* y, int64_t rows, int C,
+                                         void* hi, void* lo, float hscale, void* stream);
+
 extern "C" int pxl_bn_finalize_apply(const float* x, const double* sums, double count, const float* gamma,
                                      const float* beta, float* running_mean, float* running_var, float momentum,
                                      float eps, int clamp_mode, float* mean, float* invstd, float* scale, float* shift,
                                      const float* residual, int relu, float* y, int64_t rows, int C, void* stream) {
-    if (!x || !sums || !gamma || !beta || !mean || !invstd || !scale || !shift || !y || rows <= 0 || C <= 0 || (C & 3) || count <= 0)
+    if (!y) return PXL_ERR_BAD_ARG;
+    return pxl_bn_finalize_apply_h16(x, sums, count, gamma, beta, running_mean, running_var, momentum, eps, clamp_mode, mean,
+                                     invstd, scale, shift, residual, relu, y, rows, C, nullptr, nullptr, 1.f, stream);
+}
+
+// the same launch also (or only: y nullable) writes the result as the fp16 pair the next convolution reads
+extern "C" int pxl_bn_finalize_apply_h16(const float* x, const double* sums, double count, const float* gamma,
+                                         const float* beta, float* running_mean, float* running_var, float momentum,
+                                         float eps, int clamp_mode, float* mean, float* invstd, float* scale, float* shift,
+                                         const float* residual, int relu, float* y, int64_t rows, int C,
+                                         void* hi, void* lo, float hscale, void* stream) {
+    if (!x || !sums || !gamma || !beta || !mean || !invstd || !scale || !shift || (!y && !hi) || rows <= 0 || C <= 0 || (C & 3) || count <= 0)
         return PXL_ERR_BAD_ARG;
+    int* sat = hi ? pxl_h16_sat_counter() : nullptr;
     const RedLayout L = stream_layout(rows, C);
     dim3 grid(L.rowBlocks, L.colBlocks);
     cudaStream_t st = (cudaStream_t)stream;
 #define PXL_FA_ARGS (const float4*)x, sums, count, 1.0 / count, gamma, beta, running_mean, running_var, momentum, eps, clamp_mode, mean, invstd, \
-                    scale, shift, (const float4*)residual, (float4*)y, rows, C, L.TX, L.TY, L.rowsPerBlock
+                    scale, shift, (const float4*)residual, (float4*)y, rows, C, L.TX, L.TY, L.rowsPerBlock, \
+                    (uint2*)hi, (uint2*)lo, hscale, sat
     if (residual && relu) bn_finalize_apply_kernel<true, true><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
     else if (residual) bn_finalize_apply_kernel<true, false><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
     else if (relu) bn_finalize_apply_kernel<false, true><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
@@ -283,12 +348,13 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
                      const float* __restrict__ mean, const float* __restrict__ invstd, int64_t rows, int C,
                      int TX, int TY, int64_t rowsPerBlock, double* __restrict__ dsums,
-                     const float* __restrict__ scale, const float* __restrict__ shift) {
+                     const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ amax_slot) {
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
     const int64_t r0 = (int64_t)blockIdx.x * rowsPerBlock;
     const int64_t r1 = min(rows, r0 + rowsPerBlock);
     float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    float amax = 0.f;
     if (c4 < c4max) {
         const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + c4);
         const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + c4);
@@ -314,21 +380,39 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, c
             float4 xh = make_float4((v.x - m.x) * is.x, (v.y - m.y) * is.y, (v.z - m.z) * is.z, (v.w - m.w) * is.w);
             s = f4add(s, d);
             q = f4add(q, f4mul(d, xh));
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
         }
+    }
+    if (amax_slot) {
+        // absmax of dz for the fp16-pair scale of dx (bn_bwd_dx_kernel): one atomicMax per warp that saw a larger value
+        amax = warp_max(amax);
+        if ((threadIdx.x & 31) == 0 && amax > 0.f && __float_as_uint(amax) > ((volatile unsigned*)amax_slot)[2])
+            atomicMax((unsigned*)amax_slot + 2, __float_as_uint(amax));
     }
     block_reduce_cols(s, q, TX, TY, c4, c4max, dsums, dsums + C);
 }
 
+extern "C" int pxl_bn_bwd_reduce_h16(const float* x, const float* y, const float* dy, const float* mean,
+                                     const float* invstd, int relu, int64_t rows, int C, double* dsums,
+                                     const float* scale, const float* shift, float* amax_slot, void* stream);
+
 extern "C" int pxl_bn_bwd_reduce(const float* x, const float* y, const float* dy, const float* mean,
                                  const float* invstd, int relu, int64_t rows, int C, double* dsums,
                                  const float* scale, const float* shift, void* stream) {
+    return pxl_bn_bwd_reduce_h16(x, y, dy, mean, invstd, relu, rows, C, dsums, scale, shift, nullptr, stream);
+}
+
+// amax_slot (nullable DEVICE float[4], zeroed): slot[2] = max(slot[2], absmax(dz)) as a bit pattern
+extern "C" int pxl_bn_bwd_reduce_h16(const float* x, const float* y, const float* dy, const float* mean,
+                                     const float* invstd, int relu, int64_t rows, int C, double* dsums,
+                                     const float* scale, const float* shift, float* amax_slot, void* stream) {
     if (!x || !dy || !mean || !invstd || !dsums || rows <= 0 || C <= 0 || (C & 3) || (relu && !y && !(scale && shift))) return PXL_ERR_BAD_ARG;
     RedLayout L = red_layout(rows, C);
     dim3 grid(L.rowBlocks, L.colBlocks);
     cudaStream_t st = (cudaStream_t)stream;
-    if (relu && y) bn_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift);
-    else if (relu) bn_bwd_reduce_kernel<2><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift);
-    else bn_bwd_reduce_kernel<0><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift);
+    if (relu && y) bn_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot);
+    else if (relu) bn_bwd_reduce_kernel<2><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot);
+    else bn_bwd_reduce_kernel<0><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot);
     PXL_CHECK_LAUNCH();
     return 0;
 }
@@ -343,10 +427,30 @@ bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, con
                  const double* __restrict__ dsums, double inv_count, float4* __restrict__ dx, float4* __restrict__ dres,
                  int64_t rows, int C, int TX, int TY, int64_t rowsPerBlock,
                  const float* __restrict__ scale, const float* __restrict__ shift,
-                 float* dgamma_acc, float* dbeta_acc) {
+                 float* dgamma_acc, float* dbeta_acc,
+                 uint2* __restrict__ dhi, uint2* __restrict__ dlo, float* __restrict__ slot, int target_log2,
+                 int* __restrict__ sat) {
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
+    float hs = 1.f;
+    if (dhi) {
+        // fp16-pair scale of dx: |dx| <= max_c |gamma*invstd| * (absmax(dz) + |mean dz| + |xhat| |mean dz*xhat|); the
+        // first factor times absmax(dz) is mapped to <= 2^target_log2, the mean terms live in the headroom above it
+        // (values that still leave the fp16 range saturate and are counted).  Every CTA derives the same number.
+        __shared__ float smax[8];
+        float a = 0.f;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) a = fmaxf(a, fabsf(__ldg(gamma + c) * __ldg(invstd + c)));
+        a = warp_max(a);
+        if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = a;
+        __syncthreads();
+        a = smax[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) a = fmaxf(a, smax[w]);
+        hs = pxl_pow2_scale(a * __uint_as_float(((const unsigned*)slot)[2]), target_log2);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { slot[0] = hs; slot[1] = 1.f / hs; }
+    }
     if (c4 >= c4max) return;
+    bool clipped = false;
     if (dgamma_acc && blockIdx.x == 0 && ty == 0) {
         // parameter gradients (what bn_bwd_params_kernel does), accumulated straight into gamma.grad / beta.grad
 #pragma unroll
@@ -390,15 +494,37 @@ bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, con
         o4.y = fmaf(A[1], d.y, fmaf(B[1], v.y, K[1]));
         o4.z = fmaf(A[2], d.z, fmaf(B[2], v.z, K[2]));
         o4.w = fmaf(A[3], d.w, fmaf(B[3], v.w, K[3]));
-        dx[i] = o4;
+        if (dx) dx[i] = o4;
+        if (dhi) clipped |= h16_store4(o4, hs, dhi, dlo, i);
     }
+    if (clipped && sat) atomicAdd(sat, 1);
 }
+
+extern "C" int pxl_bn_bwd_dx_h16(const float* x, const float* y, const float* dy, const float* mean,
+                                 const float* invstd, const float* gamma, const double* dsums, double count,
+                                 int relu, float* dx, float* dres, int64_t rows, int C,
+                                 const float* scale, const float* shift, float* dgamma_acc, float* dbeta_acc,
+                                 void* dhi, void* dlo, float* slot, int target_log2, void* stream);
 
 extern "C" int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, const float* mean,
                              const float* invstd, const float* gamma, const double* dsums, double count,
                              int relu, float* dx, float* dres, int64_t rows, int C,
                              const float* scale, const float* shift, float* dgamma_acc, float* dbeta_acc, void* stream) {
-    if (!x || !dy || !mean || !invstd || !gamma || !dsums || !dx || rows <= 0 || C <= 0 || (C & 3) || (relu && !y && !(scale && shift))) return PXL_ERR_BAD_ARG;
+    if (!dx) return PXL_ERR_BAD_ARG;
+    return pxl_bn_bwd_dx_h16(x, y, dy, mean, invstd, gamma, dsums, count, relu, dx, dres, rows, C, scale, shift,
+                             dgamma_acc, dbeta_acc, nullptr, nullptr, nullptr, 0, stream);
+}
+
+// dx also (or only: dx nullable) as the fp16 pair (dhi, dlo nullable) the dgrad / wgrad convolutions read; slot = the
+// DEVICE float[4] pxl_bn_bwd_reduce_h16 left absmax(dz) in: this launch stores the pair's scale s / 1/s in slot[0..1]
+extern "C" int pxl_bn_bwd_dx_h16(const float* x, const float* y, const float* dy, const float* mean,
+                                 const float* invstd, const float* gamma, const double* dsums, double count,
+                                 int relu, float* dx, float* dres, int64_t rows, int C,
+                                 const float* scale, const float* shift, float* dgamma_acc, float* dbeta_acc,
+                                 void* dhi, void* dlo, float* slot, int target_log2, void* stream) {
+    if ((!dx && !dhi) || (dhi && !slot)) return PXL_ERR_BAD_ARG;
+    int* sat = dhi ? pxl_h16_sat_counter() : nullptr;
+    if (!x || !dy || !mean || !invstd || !gamma || !dsums || rows <= 0 || C <= 0 || (C & 3) || (relu && !y && !(scale && shift))) return PXL_ERR_BAD_ARG;
     const RedLayout L = stream_layout(rows, C);     // the reductions' decomposition without their atomics
     dim3 grid(L.rowBlocks, L.colBlocks);
     cudaStream_t st = (cudaStream_t)stream;
@@ -406,7 +532,7 @@ extern "C" int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, co
     float4 *o4 = (float4*)dx, *r4 = (float4*)dres;
     const double ic = 1.0 / count;
 #define PXL_DX_ARGS x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock, scale, shift, \
-                    (dgamma_acc && dbeta_acc) ? dgamma_acc : nullptr, dbeta_acc
+                    (dgamma_acc && dbeta_acc) ? dgamma_acc : nullptr, dbeta_acc, (uint2*)dhi, (uint2*)dlo, slot, target_log2, sat
     const int mode = relu ? (y ? 1 : 2) : 0;
     if (mode == 1 && dres) bn_bwd_dx_kernel<1, true><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
     else if (mode == 1) bn_bwd_dx_kernel<1, false><<<grid, 256, 0, st>>>(PXL_DX_ARGS);

@@ -80,6 +80,13 @@ class ParamArena:
                     self._derived[other] = torch.zeros_like(self.data)
             ops.split_tf32_into(src, self._derived['t_hi'], self._derived['t_lo'])
             self._derived_valid.update(('t_hi', 't_lo'))
+        elif name in ('h16', 'h16_t'):
+            # fp16 pairs (hi plane, lo plane) of the whole arena / of the transposed arena, one launch each
+            src = self.data if name == 'h16' else self.derived('t')
+            if self._derived[name].dtype != torch.float16:
+                self._derived[name] = torch.zeros((2, self.numel), dtype=torch.float16, device=self.data.device)
+            ops.call('pxl_h16_split', ops._p(src), ops._p(self._derived[name][0]), ops._p(self._derived[name][1]),
+                     self.numel, float(ops.H16_W_SCALE), ops._p(None), 0, ops._stream())
         else:
             raise KeyError(name)
         self._derived_valid.add(name)

@@ -16,8 +16,13 @@ from . import _lib
 from ._lib import ConvGeom, ConvTcExt, call
 
 CL = torch.channels_last
-# conv precision policy (pxl_conv_geom.precision): 0 fp32 FFMA, 1 TF32 tcgen05, 2 3xTF32 tcgen05
-PRECISION = {'fp32': 0, 'tf32': 1, 'tf32x3': 2}
+# conv precision policy (pxl_conv_geom.precision): 0 fp32 FFMA, 1 TF32 tcgen05, 2 3xTF32 tcgen05,
+# 3 fp16-pair x3 tcgen05 (fp32-grade), 4 single fp16 tcgen05 (TF32-grade)
+PRECISION = {'fp32': 0, 'tf32': 1, 'tf32x3': 2, 'f16x3': 3, 'f16': 4}
+H16_FALLBACK = {3: 2, 4: 1}     # shapes the kind::f16 kernels do not cover run on the tf32 kernels of the same grade
+H16_ACT_SCALE = 16.0            # fixed power-of-two scales of fp16 pairs (csrc/h16_prep.cu): activations saturate
+H16_W_SCALE = 256.0             # beyond +-4094, weights beyond +-255 (counted: h16_status())
+H16_GRAD_TARGET_LOG2 = 14       # gradients: per-tensor scale putting the absmax in (2^13, 2^14]
 _conv_precision = 0
 _WGRAD_TC_STRIDES = (1, 2)      # convolution strides the tcgen05 wgrad kernel handles
 
@@ -40,6 +45,8 @@ def _stream():
 
 
 def _chk(t, name, cl=False):
+    if getattr(t, '_pxl_carrier', False):
+        raise TypeError('%s is an fp16-pair carrier (its storage holds no fp32 values); only conv_bn_act may consume it' % name)
     if not (t.is_cuda and t.dtype == torch.float32):
         raise TypeError('%s must be a CUDA float32 tensor (got %s on %s)' % (name, t.dtype, t.device))
     if cl:
@@ -421,10 +428,104 @@ def split_cached(x):
     return parts
 
 
+class H16:
+    """fp16 pair of a tensor (csrc/h16_prep.cu): ``buf`` = [2, numel] half (hi plane, lo plane; ``lo`` is None in
+    single-fp16 mode), value * scale = hi + lo.  ``scale`` is the fixed power of two, or None when the scale is
+    dynamic and lives on the device in ``slot`` ([s, 1/s, absmax bits, -])."""
+    __slots__ = ('buf', 'numel', 'scale', 'slot', 'has_lo')
+
+    def __init__(self, buf, numel, scale, slot, has_lo):
+        self.buf, self.numel, self.scale, self.slot, self.has_lo = buf, numel, scale, slot, has_lo
+
+    @property
+    def hi(self):
+        return self.buf[0]
+
+    @property
+    def lo(self):
+        return self.buf[1] if self.has_lo else None
+
+    @property
+    def device(self):
+        return self.buf.device
+
+    def inv_scale(self):
+        """(host factor, device pointer or None) undoing this operand's scale in a consumer's epilogue."""
+        if self.slot is None:
+            return 1.0 / self.scale, None
+        return 1.0, self.slot[1:]
+
+
+def _scale_slot(device):
+    """A zeroed device float[4] carved out of the per-step statistics pool."""
+    return _stat_zeros(2, device).view(torch.float32)
+
+
+def h16_split(x, scale=None, want_lo=True):
+    """fp32 tensor (any layout, numel % 4 == 0) -> H16.  scale None: dynamic (absmax pass + split)."""
+    n = x.numel()
+    buf = torch.empty((2 if want_lo else 1, n), dtype=torch.float16, device=x.device)
+    slot = None
+    if scale is None:
+        slot = _scale_slot(x.device)
+        call('pxl_h16_absmax', _p(x), n, _p(slot), _stream())
+    call('pxl_h16_split', _p(x), _p(buf[0]), _p(buf[1] if want_lo else None), n, float(scale or 1.0), _p(slot),
+         H16_GRAD_TARGET_LOG2, _stream())
+    return H16(buf, n, scale, slot, want_lo)
+
+
+def h16_status():
+    """Number of fp16-pair producers that saturated since the last reset (0 = every operand was in range)."""
+    return int(_lib.load().pxl_h16_status())
+
+
+def h16_cached(x, scale, want_lo=True):
+    """h16_split memoised on the tensor object for one step (a weight used by several launches)."""
+    ent = getattr(x, '_pxl_h16', None)
+    if ent is not None and ent[0] == _epoch and ent[1] == x._version and ent[2] == x.data_ptr() and ent[3].has_lo >= want_lo:
+        return ent[3]
+    h = h16_split(x, scale, want_lo)
+    try:
+        x._pxl_h16 = (_epoch, x._version, x.data_ptr(), h)
+    except Exception:
+        pass
+    return h
+
+
+def h16_weight(w, transposed_of=None):
+    """fp16 pair of a packed conv weight; arena weights are served from the arena-wide pair made once per step."""
+    want_lo = _conv_precision == 3
+    arena, off = _arena_of(w) if (w.dim() == 4 and BATCH_WEIGHT_PREP) else (None, None)
+    if arena is not None and off in arena._conv_at:
+        n = w.numel()
+        return H16(arena.derived('h16')[:, off:off + n], n, H16_W_SCALE, None, True)
+    return h16_cached(w, H16_W_SCALE, want_lo)
+
+
+def h16_supported(Cin, mul, div):
+    return Cin % 64 == 0 and ((div == 1 and mul in (1, 2)) or (div == 2 and mul == 1))
+
+
 def tc_supported(Cin, mul, div):
     """Shapes covered by the tcgen05 forward/dgrad kernel (csrc/conv_tc.cu): stride 1 and 2 forward
     (mul), and the dgrad of a stride-2 convolution (div == 2, decomposed by output parity)."""
     return Cin % 32 == 0 and ((div == 1 and mul in (1, 2)) or (div == 2 and mul == 1))
+
+
+def _stride2_dgrad_classes(taps, ntaps):
+    """dgrad of a stride-2 convolution: output pixel (iy, ix) only receives the taps with (iy + dy) and (ix + dx)
+    even; per output parity class that is a stride-1 problem over dY.  -> [(py, px, halved taps, tap indices)]"""
+    classes = []
+    for py in (0, 1):
+        for px in (0, 1):
+            sub, widx = [], []
+            for t in range(ntaps):
+                dy, dx = taps[2 * t], taps[2 * t + 1]
+                if (py + dy) % 2 == 0 and (px + dx) % 2 == 0:
+                    sub += [(py + dy) // 2, (px + dx) // 2]
+                    widx.append(t)
+            classes.append((py, px, sub, widx))
+    return classes
 
 
 def _tc_launch(geom, taps, ext, x_parts, w_parts, bias, out):
@@ -438,11 +539,50 @@ def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div,
     fly).  Shapes the tensor-core kernel does not cover (Cin % 32 != 0, other strides) use the FFMA kernel."""
     ntaps = len(taps) // 2
     prec = _conv_precision if precision is None else precision
-    if out is None:
+    if out is None and not isinstance(x, H16):
         dev = x[0].device if isinstance(x, tuple) else x.device
         out = torch.empty((N, ldo, OH, OW), dtype=torch.float32, device=dev, memory_format=CL)
         if ldo != Cout:
             out.zero_()
+    if prec >= 3 and not h16_supported(Cin, mul, div):
+        if isinstance(x, H16) or isinstance(w_packed, H16):
+            raise ValueError('fp16-pair operands given for a shape the kind::f16 kernel does not cover')
+        prec = H16_FALLBACK[prec]
+    if prec >= 3:
+        want_lo = prec == 3
+        xh = x if isinstance(x, H16) else h16_cached(x, H16_ACT_SCALE, want_lo)
+        wh = w_packed if isinstance(w_packed, H16) else h16_weight(w_packed)
+        fx, px = xh.inv_scale()
+        fw, pw = wh.inv_scale()
+        if px is not None and pw is not None:
+            raise ValueError('at most one operand may carry a device-side scale')
+        oscale, odev = fx * fw, (px if px is not None else pw)
+        if out is None:
+            out = torch.empty((N, ldo, OH, OW), dtype=torch.float32, device=xh.device, memory_format=CL)
+            if ldo != Cout:
+                out.zero_()
+
+        def launch(geom, tp, ext):
+            ext.out_scale, ext.out_scale_dev = oscale, (odev.data_ptr() if odev is not None else None)
+            call('pxl_conv_h16_launch', ctypes.byref(geom), _ctaps(tp), ctypes.byref(ext), _p(xh.hi), _p(xh.lo),
+                 _p(wh.hi), _p(wh.lo if want_lo else None), _p(bias), _p(out), _stream())
+        if div == 1:
+            ext = ConvTcExt(0, None, 0, 0, 0, 0, 0, None)
+            if bn_stats is not None:
+                ext.bn_stats = bn_stats.data_ptr()
+                bn_stats._pxl_filled = True
+            launch(ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, 1, ntaps, prec), taps, ext)
+            return out
+        classes = _stride2_dgrad_classes(taps, ntaps)
+        if any(len(c[3]) == 0 for c in classes):
+            out.zero_()
+        for py, px_, sub, widx in classes:
+            ohs, ows = (OH - py + 1) // 2, (OW - px_ + 1) // 2
+            if not widx or ohs <= 0 or ows <= 0:
+                continue
+            ext = ConvTcExt(ntaps, (ctypes.c_int * len(widx))(*widx), 2, py, px_, OH, OW, None)
+            launch(ConvGeom(N, H, W, Cin, ohs, ows, Cout, ldo, 1, 1, len(widx), prec), sub, ext)
+        return out
     if prec != 0 and tc_supported(Cin, mul, div):
         if prec == 2:
             # activations go in raw: the kernel splits them hi/lo in shared memory; the (small, per-step
@@ -459,18 +599,7 @@ def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div,
                 bn_stats._pxl_filled = True
             _tc_launch(geom, taps, ext, x_parts, w_parts, bias, out)
             return out
-        # dgrad of a stride-2 convolution: output pixel (iy, ix) only receives the taps with
-        # (iy + dy) and (ix + dx) even; per output parity class that is a stride-1 problem over dY
-        classes = []
-        for py in (0, 1):
-            for px in (0, 1):
-                sub, widx = [], []
-                for t in range(ntaps):
-                    dy, dx = taps[2 * t], taps[2 * t + 1]
-                    if (py + dy) % 2 == 0 and (px + dx) % 2 == 0:
-                        sub += [(py + dy) // 2, (px + dx) // 2]
-                        widx.append(t)
-                classes.append((py, px, sub, widx))
+        classes = _stride2_dgrad_classes(taps, ntaps)
         if any(len(c[3]) == 0 for c in classes):
             out.zero_()
         for py, px, sub, widx in classes:
@@ -499,6 +628,22 @@ def conv_wgrad_raw(x, dy, dw, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, p
     """dw[Cout][ntaps][Cin] += ...  (dw must be initialised by the caller)."""
     ntaps = len(taps) // 2
     prec = _conv_precision if precision is None else precision
+    if prec >= 3 and not (div == 1 and mul in _WGRAD_TC_STRIDES and Cin % 64 == 0 and ldo % 64 == 0):
+        if isinstance(x, H16) or isinstance(dy, H16):
+            raise ValueError('fp16-pair operands given for a shape the kind::f16 wgrad kernel does not cover')
+        prec = H16_FALLBACK[prec]
+    if prec >= 3:
+        want_lo = prec == 3
+        xh = x if isinstance(x, H16) else h16_split(x, H16_ACT_SCALE, want_lo)
+        dh = dy if isinstance(dy, H16) else h16_split(dy, None, want_lo)
+        fx, px = xh.inv_scale()
+        fd, pd = dh.inv_scale()
+        if px is not None and pd is not None:
+            raise ValueError('at most one operand may carry a device-side scale')
+        geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
+        call('pxl_conv_wgrad_h16_launch', ctypes.byref(geom), _ctaps(taps), _p(xh.hi), _p(xh.lo), _p(dh.hi), _p(dh.lo),
+             _p(dw), float(fx * fd), _p(pd if pd is not None else px), _stream())
+        return dw
     if prec != 0 and div == 1 and mul in _WGRAD_TC_STRIDES and Cin % 32 == 0 and ldo % 32 == 0:
         geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
         if prec == 2:
@@ -544,10 +689,21 @@ class _Conv2d(torch.autograd.Function):
         OH = (H + 2 * padding - dilation * (kh - 1) - 1) // stride + 1
         OW = (W + 2 * padding - dilation * (kw - 1) - 1) // stride + 1
         taps = _taps(kh, kw, dilation, padding)
+        ctx.split, ctx.h16 = False, None
+        ctx.meta = (taps, N, H, W, Cin, OH, OW, Cout, stride, kh * kw, bias is not None)
+        if _conv_precision >= 3 and h16_supported(Cin, stride, 1):
+            # fp16-pair path: the pair of x (4 B/element, like x itself) is what the backward keeps
+            xh = h16_cached(x, H16_ACT_SCALE, _conv_precision == 3)
+            out = conv_raw(xh, weight, bias, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1, bn_stats=bn_stats)
+            wg_ok = Cin % 64 == 0 and Cout % 64 == 0 and stride in _WGRAD_TC_STRIDES
+            if wg_ok or not ctx.needs_input_grad[1]:
+                ctx.save_for_backward(xh.buf, weight)
+                ctx.h16 = (xh.scale, xh.has_lo)
+            else:
+                ctx.save_for_backward(x, weight)
+            return out
         out = conv_raw(x, weight, bias, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1, bn_stats=bn_stats)
         ctx.save_for_backward(x, weight)
-        ctx.split = False
-        ctx.meta = (taps, N, H, W, Cin, OH, OW, Cout, stride, kh * kw, bias is not None)
         return out
 
     @staticmethod
@@ -599,10 +755,25 @@ class _Conv2d(torch.autograd.Function):
         dy = as_cl(dy)
         dx = dw = db = None
         dyin = dy
+        if ctx.h16 is not None:
+            x = H16(x, x.shape[1], ctx.h16[0], None, ctx.h16[1])
+        prec = _conv_precision
+        if prec >= 3:
+            dgrad_h16 = ctx.needs_input_grad[0] and h16_supported(Cout, 1, stride)
+            wgrad_h16 = ctx.needs_input_grad[1] and isinstance(x, H16)
+            if dgrad_h16 or wgrad_h16:
+                dyin = h16_split(dy, None, prec == 3)        # one pair of dY serves dgrad and wgrad
+        eff = H16_FALLBACK.get(prec, prec)
         if ctx.needs_input_grad[0]:
-            want_split = _conv_precision == 2 and tc_supported(Cout, 1, stride)
+            want_split = eff == 2 and tc_supported(Cout, 1, stride)
             arena, off = _arena_of(weight) if BATCH_WEIGHT_PREP else (None, None)
-            if arena is not None and arena._conv_at.get(off) == (Cout, T, Cin):
+            if isinstance(dyin, H16) and h16_supported(Cout, 1, stride):
+                if arena is not None and arena._conv_at.get(off) == (Cout, T, Cin):
+                    n = weight.numel()
+                    wt = H16(arena.derived('h16_t')[:, off:off + n], n, H16_W_SCALE, None, True)
+                else:
+                    wt = h16_split(transpose_weights(weight, Cout, T, Cin), H16_W_SCALE, prec == 3)
+            elif arena is not None and arena._conv_at.get(off) == (Cout, T, Cin):
                 n = weight.numel()          # arena-wide transposed (and split) copies: one launch per step each
                 if want_split:
                     wt = (arena.derived('t_hi')[off:off + n], arena.derived('t_lo')[off:off + n])
@@ -614,11 +785,12 @@ class _Conv2d(torch.autograd.Function):
             else:
                 wt = transpose_weights(weight, Cout, T, Cin)
             ntaps = [-v for v in taps]
-            dx = conv_raw(dyin, wt, None, ntaps, N, OH, OW, Cout, H, W, Cin, Cin, 1, stride)
+            dgrad_in = dyin if (isinstance(dyin, H16) and isinstance(wt, H16)) else dy
+            dx = conv_raw(dgrad_in, wt, None, ntaps, N, OH, OW, Cout, H, W, Cin, Cin, 1, stride)
         if ctx.needs_input_grad[1]:
             inplace = ACCUM_WGRAD_INPLACE and weight.grad is not None and weight.grad.is_contiguous(memory_format=CL)
             dwbuf = weight.grad if inplace else torch.zeros_like(weight, memory_format=torch.preserve_format)
-            conv_wgrad_raw(x, dyin, dwbuf, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1)
+            conv_wgrad_raw(x, dyin if isinstance(x, H16) else dy, dwbuf, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1)
             dw = None if inplace else dwbuf
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(Cout, dtype=torch.float32, device=dy.device)
@@ -864,6 +1036,187 @@ def bn_act(x, gamma, beta, running_mean, running_var, training=True, momentum=0.
     sums = getattr(x, '_pxl_bn_sums', None) if training else None      # produced by the conv epilogue
     return _BnAct.apply(x, gamma, beta, running_mean, running_var, residual, bool(training), float(momentum),
                         float(eps), bool(relu), group, bool(clamp_var), sums)
+
+
+# ------------------------------------------------------------------------------------------------
+# conv -> BN -> (+residual) -> (ReLU) as one node on the fp16-pair path
+# ------------------------------------------------------------------------------------------------
+
+H16_DX_TARGET_LOG2 = 12         # bn_bwd_dx: max|gamma*invstd| * absmax(dz) -> <= 2^12, 3 bits of headroom for the mean terms
+_unit_out_pair = None           # H16 of the last _ConvBnAct.forward output (picked up by conv_bn_act right after apply)
+
+
+def _pair_of(x, want_lo):
+    """The fp16 pair of an activation: attached by its producer (same step, unmodified), else split now (cached)."""
+    ent = getattr(x, '_pxl_h16', None)
+    if ent is not None and ent[0] == _epoch and ent[1] == x._version and ent[2] == x.data_ptr() and ent[3].has_lo >= want_lo:
+        return ent[3]
+    if getattr(x, '_pxl_carrier', False):
+        raise RuntimeError('fp16-pair carrier tensor without a valid pair (stale step?)')
+    return h16_cached(x, H16_ACT_SCALE, want_lo)
+
+
+def _attach_pair(t, h, carrier=False):
+    t._pxl_h16 = (_epoch, t._version, t.data_ptr(), h)
+    if carrier:
+        t._pxl_carrier = True
+    return t
+
+
+def is_carrier(t):
+    """True for tensors whose storage holds an fp16 pair instead of fp32 values (inner activations of a bottleneck
+    on the fp16-pair path): only pair-aware consumers (conv_bn_act) may read them."""
+    return getattr(t, '_pxl_carrier', False)
+
+
+class _ConvBnAct(torch.autograd.Function):
+    """Bottleneck building block (resnet.py:33-48): bias-free conv -> train-mode (Sync)BN (batchnorm.py:48-78)
+    -> (+ residual) -> (ReLU), ONE autograd node on the kind::f16 tensor-core path.
+
+    Forward: the convolution reads the fp16 pair of its input, its epilogue produces the BN statistics, and the BN
+    apply launch writes its result directly as the fp16 pair of the next convolution (``out_mode`` 'pair': only the
+    pair, carried by a float32-typed tensor over the same storage; 'both': fp32 tensor + attached pair; 'fp32').
+    Backward: the BN dx launch writes dX of the convolution output as an fp16 pair with a device-side power-of-two
+    scale; dgrad and wgrad read it.  No fp16 pair ever takes an extra trip through HBM, and gradients between nodes
+    stay fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, residual, stride, padding, dilation,
+                momentum, eps, relu, group, clamp_var, out_mode):
+        global _unit_out_pair
+        prec = _conv_precision
+        want_lo = prec == 3
+        N, Cin, H, W = x.shape
+        Cout, Cin2, kh, kw = weight.shape
+        if Cin2 != Cin:
+            raise ValueError('channel mismatch')
+        OH = (H + 2 * padding - dilation * (kh - 1) - 1) // stride + 1
+        OW = (W + 2 * padding - dilation * (kw - 1) - 1) // stride + 1
+        taps = _taps(kh, kw, dilation, padding)
+        xh = _pair_of(x, want_lo)
+        dev = xh.device
+        sums = _stat_zeros(2 * Cout, dev)
+        c = conv_raw(xh, weight, None, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1, bn_stats=sums)
+        rows = N * OH * OW
+        n = rows * Cout
+        count = float(rows)
+        clamp = 1 if clamp_var else 0
+        coeff = torch.empty((4, Cout), dtype=torch.float32, device=dev)
+        pair = torch.empty((2, n), dtype=torch.float16, device=dev) if out_mode != 'fp32' else None
+        y = torch.empty_like(c) if out_mode != 'pair' else None
+        hi = pair[0] if pair is not None else None
+        lo = pair[1] if (pair is not None and want_lo) else None
+        if residual is not None:
+            _chk(residual, 'residual', cl=True)
+        applied = fused = False
+        if group is not None:
+            import torch.distributed as dist
+            count = float(rows) * dist.get_world_size(group)
+            clamp = 1     # batchnorm.py:125: the multi-replica path clamps var instead of adding eps
+            px = _peer_exchanges.get(id(group))
+            if px is not None and 2 * Cout <= 4096:
+                px.allreduce_bn(sums, (count, Cout, gamma, beta, running_mean, running_var, momentum, eps, clamp,
+                                       coeff[0], coeff[1], coeff[2], coeff[3]))
+                fused = True
+            else:
+                dist.all_reduce(sums, group=group)
+        if group is None and FUSE_BN_FINALIZE:
+            call('pxl_bn_finalize_apply_h16', _p(c), _p(sums), count, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                 float(momentum), float(eps), clamp, _p(coeff[0]), _p(coeff[1]), _p(coeff[2]), _p(coeff[3]),
+                 _p(residual), int(relu), _p(y), rows, Cout, _p(hi), _p(lo), float(H16_ACT_SCALE), _stream())
+            applied = True
+        elif not fused:
+            call('pxl_bn_finalize', _p(sums), count, Cout, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                 float(momentum), float(eps), clamp, _p(coeff[0]), _p(coeff[1]), _p(coeff[2]), _p(coeff[3]), _stream())
+        if not applied:
+            call('pxl_bn_apply_h16', _p(c), _p(coeff[2]), _p(coeff[3]), _p(residual), int(relu), _p(y), rows, Cout,
+                 _p(hi), _p(lo), float(H16_ACT_SCALE), _stream())
+        ctx.save_for_backward(xh.buf, weight, c, y if (relu and residual is not None) else None, gamma, coeff, beta)
+        ctx.meta = (taps, N, H, W, Cin, OH, OW, Cout, stride, kh * kw, count, bool(relu), residual is not None, group,
+                    xh.scale, want_lo, prec)
+        _unit_out_pair = H16(pair, n, H16_ACT_SCALE, None, want_lo) if pair is not None else None
+        if out_mode == 'pair':
+            return pair.view(torch.float32).view(N, OH, OW, Cout).permute(0, 3, 1, 2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xbuf, weight, c, y, gamma, coeff, beta = ctx.saved_tensors
+        taps, N, H, W, Cin, OH, OW, Cout, stride, T, count, relu, has_res, group, xscale, want_lo, prec = ctx.meta
+        if is_carrier(dy):
+            raise RuntimeError('gradient tensors are never fp16-pair carriers')
+        dy = as_cl(dy)
+        dev = dy.device
+        rows = N * OH * OW
+        n = rows * Cout
+        C = Cout
+        dsums = _stat_zeros(2 * C, dev)
+        slot = _scale_slot(dev)
+        ymask = y if (relu and has_res) else None
+        call('pxl_bn_bwd_reduce_h16', _p(c), _p(ymask), _p(dy), _p(coeff[0]), _p(coeff[1]), int(relu), rows, C, _p(dsums),
+             _p(coeff[2]), _p(coeff[3]), _p(slot), _stream())
+        grads_in_arena = (ACCUM_WGRAD_INPLACE and gamma.grad is not None and beta.grad is not None
+                          and gamma.grad.is_contiguous() and beta.grad.is_contiguous())
+        px = _peer_exchanges.get(id(group)) if group is not None else None
+        if px is not None and 2 * C > 4096:
+            px = None
+        acc_inplace = grads_in_arena and group is None
+        acc_in_exchange = grads_in_arena and px is not None
+        dgamma = dbeta = None
+        if not (acc_inplace or acc_in_exchange):
+            dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+            call('pxl_bn_bwd_params', _p(dsums), C, _p(dgamma), _p(dbeta), 0, _stream())
+        if group is not None:
+            if px is not None:
+                px.allreduce_bn(dsums, param_grads=(gamma.grad, beta.grad) if acc_in_exchange else None)
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(dsums, group=group)
+        dpair = torch.empty((2, n), dtype=torch.float16, device=dev)
+        dres = torch.empty_like(c) if has_res else None
+        call('pxl_bn_bwd_dx_h16', _p(c), _p(ymask), _p(dy), _p(coeff[0]), _p(coeff[1]), _p(gamma), _p(dsums), count, int(relu),
+             _p(None), _p(dres), rows, C, _p(coeff[2]), _p(coeff[3]),
+             _p(gamma.grad if acc_inplace else None), _p(beta.grad if acc_inplace else None),
+             _p(dpair[0]), _p(dpair[1] if want_lo else None), _p(slot), H16_DX_TARGET_LOG2, _stream())
+        dh = H16(dpair, n, None, slot, want_lo)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            arena, off = _arena_of(weight) if BATCH_WEIGHT_PREP else (None, None)
+            if arena is not None and arena._conv_at.get(off) == (Cout, T, Cin):
+                nw = weight.numel()
+                wt = H16(arena.derived('h16_t')[:, off:off + nw], nw, H16_W_SCALE, None, True)
+            else:
+                wt = h16_split(transpose_weights(weight, Cout, T, Cin), H16_W_SCALE, want_lo)
+            dx = conv_raw(dh, wt, None, [-v for v in taps], N, OH, OW, Cout, H, W, Cin, Cin, 1, stride, precision=prec)
+        if ctx.needs_input_grad[1]:
+            inplace = ACCUM_WGRAD_INPLACE and weight.grad is not None and weight.grad.is_contiguous(memory_format=CL)
+            dwbuf = weight.grad if inplace else torch.zeros_like(weight, memory_format=torch.preserve_format)
+            conv_wgrad_raw(H16(xbuf, xbuf.shape[1], xscale, None, want_lo), dh, dwbuf, taps, N, H, W, Cin, OH, OW, Cout, Cout,
+                           stride, 1, precision=prec)
+            dw = None if inplace else dwbuf
+        return (dx, dw, dgamma, dbeta, None, None, dres) + (None,) * 9
+
+
+def conv_bn_unit_ok(conv, bn):
+    """True when conv -> bn can run as one _ConvBnAct node: fp16-pair precision, train-mode BN, bias-free conv with
+    64-aligned channel counts and stride 1 / 2."""
+    return (_conv_precision >= 3 and bn.training and conv.bias is None and not conv.out_lanes
+            and conv.in_channels % 64 == 0 and conv.out_channels % 64 == 0 and conv.stride in (1, 2))
+
+
+def conv_bn_act(x, conv, bn, relu=False, residual=None, out_mode='both'):
+    """conv (nn.modules.Conv2d) -> bn (nn.modules.BatchNorm2d) -> (+residual) -> (ReLU); see _ConvBnAct."""
+    global _unit_out_pair
+    if not is_carrier(x):
+        x = as_cl(x)
+    out = _ConvBnAct.apply(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
+                           int(conv.stride), int(conv.padding), int(conv.dilation), float(bn.momentum), float(bn.eps),
+                           bool(relu), bn.sync_group, bool(bn.multi_replica_formula), out_mode)
+    pair, _unit_out_pair = _unit_out_pair, None
+    if pair is not None:
+        _attach_pair(out, pair, carrier=(out_mode == 'pair'))
+    return out
 
 
 class _MaxPool(torch.autograd.Function):

@@ -29,6 +29,15 @@ class Bottleneck(nn.Module):
             conv.feeds_bn = True          # the tensor-core epilogue then produces the BN statistics
 
     def forward(self, x):
+        if all(ops.conv_bn_unit_ok(c, b) for c, b in ((self.conv1, self.bn1), (self.conv2, self.bn2), (self.conv3, self.bn3))) \
+                and (self.downsample is None or ops.conv_bn_unit_ok(self.downsample[0], self.downsample[1])):
+            # fp16-pair tensor-core path: four fused conv+BN(+ReLU/residual) nodes; the inner activations only exist
+            # as the fp16 pairs the next convolution reads
+            out = ops.conv_bn_act(x, self.conv1, self.bn1, relu=True, out_mode='pair')
+            out = ops.conv_bn_act(out, self.conv2, self.bn2, relu=True, out_mode='pair')
+            residual = x if self.downsample is None else \
+                ops.conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False, out_mode='fp32')
+            return ops.conv_bn_act(out, self.conv3, self.bn3, relu=True, residual=residual, out_mode='both')
         out = self.bn1(self.conv1(x), relu=True)
         out = self.bn2(self.conv2(out), relu=True)
         out = self.conv3(out)

@@ -26,6 +26,10 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
+# (pxl_conv_geom.precision, tolerance vs the FFMA kernel): 2 = 3xTF32 and 3 = fp16-pair x3 are fp32-grade,
+# 1 = single TF32 and 4 = single fp16 carry 11-bit operands (what cuDNN gives the reference on a GPU)
+PRECS = [(2, 5e-5), (1, 2e-3), (3, 5e-5), (4, 2e-3)]
+
 CASES = [
     # N, Cin, H, W, Cout, k, dil
     (2, 64, 17, 19, 64, 1, 1),
@@ -41,10 +45,12 @@ CASES = [
     (1, 512, 17, 17, 512, 3, 4),
     (1, 96, 20, 24, 160, 3, 1),       # Cin = 3 chunks, Cout not a power of two
     (2, 64, 129, 129, 64, 3, 1),      # layer1 conv2 shape (many tiles)
+    (1, 2048, 17, 17, 512, 1, 1),     # layer4 conv1: the longest 1x1 reduction
+    (2, 192, 21, 23, 320, 3, 1),      # 3 fp16 K chunks, Cout = 2.5 x 128
 ]
 
 
-@pytest.mark.parametrize('precision,tol', [(2, 5e-5), (1, 2e-3)])
+@pytest.mark.parametrize('precision,tol', PRECS)
 @pytest.mark.parametrize('case', CASES)
 def test_conv_tc_forward_and_dgrad(ops, case, precision, tol):
     N, Cin, H, W, Cout, k, dil = case
@@ -63,6 +69,7 @@ def test_conv_tc_forward_and_dgrad(ops, case, precision, tol):
         outs[prec] = (y.detach(), xg.grad, wg.grad)
     ops._conv_precision = 0
     assert ops.conv_tc_status() == 0, 'mbarrier watchdog fired: role %d' % ops.conv_tc_status()
+    assert ops.h16_status() == 0, 'an fp16 pair saturated' 
     ef, eb = rel(outs[precision][0], outs[0][0]), rel(outs[precision][1], outs[0][1])
     ew = rel(outs[precision][2], outs[0][2])
     print('case %s precision %d: fwd %.2e dgrad %.2e wgrad %.2e' % (case, precision, ef, eb, ew))
@@ -73,7 +80,7 @@ def test_conv_tc_forward_and_dgrad(ops, case, precision, tol):
         assert rel(outs[precision][0].cpu(), yc) <= tol
 
 
-@pytest.mark.parametrize('precision,tol', [(2, 5e-5), (1, 2e-3)])
+@pytest.mark.parametrize('precision,tol', PRECS)
 @pytest.mark.parametrize('case', [(2, 128, 33, 35, 128, 3), (2, 256, 17, 17, 512, 1), (1, 64, 65, 65, 64, 3)])
 def test_conv_tc_stride2(ops, case, precision, tol):
     """stride-2 convolutions: forward and wgrad use the TMA traversal stride, dgrad is decomposed by
@@ -97,7 +104,7 @@ def test_conv_tc_stride2(ops, case, precision, tol):
     assert ef <= tol and eb <= tol and ew <= tol, (ef, eb, ew)
 
 
-@pytest.mark.parametrize('precision,tol', [(2, 5e-5), (1, 2e-3)])
+@pytest.mark.parametrize('precision,tol', PRECS)
 def test_aspp_head_tc(ops, precision, tol):
     g = torch.Generator().manual_seed(3)
     x = torch.randn(2, 2048, 33, 33, generator=g).cuda().contiguous(memory_format=CL)
@@ -122,6 +129,29 @@ def test_aspp_head_tc(ops, precision, tol):
     assert rel(res[precision][2], res[0][2]) <= tol
 
 
+def test_h16_pair_split_is_exact_to_22_bits(ops):
+    """x * s == hi + lo to 2^-22 relative (or 2^-25 absolute in scaled units); dynamic scale puts absmax in (2^13, 2^14]."""
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(1 << 16, generator=g) * torch.logspace(-6, 2, 1 << 16)).cuda()
+    h = ops.h16_split(x, 16.0)
+    rec = (h.hi.double() + h.lo.double()) / 16.0
+    err = (rec - x.double()).abs()
+    bound = torch.maximum(x.double().abs() * 2.0 ** -21, torch.full_like(err, 2.0 ** -24 / 16.0))
+    assert bool((err <= bound).all()), float((err / bound).max())
+    gsmall = x * 1e-9
+    hd = ops.h16_split(gsmall, None)
+    s, inv = float(hd.slot[0]), float(hd.slot[1])
+    assert s * inv == 1.0 and 2.0 ** 13 < float(gsmall.abs().max()) * s <= 2.0 ** 14
+    rec = (hd.hi.double() + hd.lo.double()) * inv
+    err = (rec - gsmall.double()).abs()
+    assert float(err.max()) <= float(gsmall.abs().max()) * 2.0 ** -21
+    assert ops.h16_status() == 0
+    big = torch.full((64,), 1e6).cuda()
+    ops.h16_split(big, 16.0)
+    assert ops.h16_status() > 0                      # saturation is counted, not silent
+    ops._lib.load().pxl_h16_reset_status()
+
+
 def test_tf32_operand_rounding_probe(ops):
     """Documents what kind::tf32 does with the low 13 mantissa bits of raw fp32 operands."""
     x = torch.full((1, 32, 8, 16), 1.0 + 2.0 ** -11 + 2.0 ** -12).cuda().contiguous(memory_format=CL)   # low bits set
@@ -135,7 +165,7 @@ def test_tf32_operand_rounding_probe(ops):
     assert v in (1.0, 1.0 + 2.0 ** -10, 1.0 + 2.0 ** -11 + 2.0 ** -12)
 
 
-@pytest.mark.parametrize('precision', [1, 2])
+@pytest.mark.parametrize('precision', [1, 2, 3, 4])
 @pytest.mark.parametrize('shape', [(2, 64, 33, 33, 256, 1), (2, 128, 17, 19, 64, 3), (1, 64, 129, 129, 64, 3)])
 def test_bn_statistics_fused_in_epilogue(ops, shape, precision):
     """The conv epilogue's per-channel sum / sum-of-squares equal those of the tensor it stored."""
@@ -173,7 +203,7 @@ def test_cta_pair_kernel_opt_in_subprocess():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize('precision,tol_y,tol_w', [('tf32x3', 2e-5, 5e-5), ('tf32', 3e-3, 3e-3)])
+@pytest.mark.parametrize('precision,tol_y,tol_w', [('tf32x3', 2e-5, 5e-5), ('tf32', 3e-3, 3e-3), ('f16x3', 2e-5, 5e-5), ('f16', 3e-3, 3e-3)])
 @pytest.mark.parametrize('N,H,W', [(2, 65, 65), (1, 97, 129), (2, 40, 36)])
 def test_stem_tensor_core_path(ops, N, H, W, precision, tol_y, tol_w):
     """7x7/2 stem as im2col (pxl_stem_im2col) + flat 1x1 tcgen05 convolution, forward, weight gradient and the

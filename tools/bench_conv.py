@@ -2,7 +2,10 @@
 ResNet-101 @ 513x513, batch 16 shapes that dominate the MT step.  Scratch tool for tuning; knobs are read
 from the environment by the library once per process (PXL_TC_SMEM_KB, PXL_TC_BN_MAX_TF32, ...).
 
-    python tools/bench_conv.py tf32|tf32x3 [fwd|wgrad|both]
+    python tools/bench_conv.py tf32|tf32x3|f16x3|f16 [fwd|wgrad|both]
+
+In the fp16-pair modes the operands are split outside the timed region: in the engine the pairs are written by the
+producing BatchNorm launches (ops._ConvBnAct), not by a separate pass.
 """
 import os
 import sys
@@ -58,13 +61,16 @@ def main():
     what = sys.argv[2] if len(sys.argv) > 2 else 'both'
     prec = ops.PRECISION[prec_name]
     tot_f = tot_w = 0.0
-    print('precision %s   knobs: %s' % (prec_name, {k: v for k, v in os.environ.items() if k.startswith('PXL_TC')}))
+    print('precision %s   knobs: %s' % (prec_name, {k: v for k, v in os.environ.items() if k.startswith('PXL_TC') or k.startswith('PXL_WG')}))
     for name, N, H, W, Cin, Cout, k, dil, mult in SHAPES:
         taps = taps_of(k, dil)
         nt = k * k
         xs = [torch.randn(N, Cin, H, W, device='cuda').contiguous(memory_format=CL) for _ in range(3)]
         w = torch.randn(Cout * nt * Cin, device='cuda') * 0.05
         out = torch.empty(N, Cout, H, W, device='cuda').contiguous(memory_format=CL)
+        if prec >= 3:
+            xs = [ops.h16_split(t, ops.H16_ACT_SCALE, prec == 3) for t in xs]
+            w = ops.h16_split(w, ops.H16_W_SCALE, prec == 3)
         flop = 2.0 * N * H * W * Cin * Cout * nt
         line = '%-30s' % name
         if what in ('fwd', 'both'):
@@ -79,6 +85,8 @@ def main():
         if what in ('wgrad', 'both'):
             dw = torch.zeros(Cout * nt * Cin, device='cuda')
             dy = torch.randn(N, Cout, H, W, device='cuda').contiguous(memory_format=CL)
+            if prec >= 3:
+                dy = ops.h16_split(dy * 1e-6, None, prec == 3)
 
             def g():
                 ops.conv_wgrad_raw(xs[0], dy, dw, taps, N, H, W, Cin, H, W, Cout, Cout, 1, 1, precision=prec)
