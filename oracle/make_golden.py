@@ -472,6 +472,28 @@ def golden_input(pixelssl, sseg_proxy):
     print('input_pipeline.npz written:', {k: v.shape for k, v in out.items() if k.startswith(('x', 'y'))})
 
 
+def golden_fp64_mid(size=257):
+    """fp64 truth of the mid-size MT step (mt_steps_257.npz): same seeds as golden_mt(size=257, steps=1)."""
+    D = torch.float64
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    rec = {}
+    s = O.to_dtype(O.randomize_bn_affine(O.init_deeplabv2(11, cls_bias_std=0.01), 12), D)
+    t = O.to_dtype(O.randomize_bn_affine(O.init_deeplabv2(21, cls_bias_std=0.01), 22), D)
+    mt = O.MTOracle(s, t, lr=0.00025, momentum=0.9, weight_decay=0.0005, max_iters=10,
+                    cons_scale=1.0, rampup_steps=1, ema_decay=0.99, cons_for_labeled=False)
+    img, lab = O.synthetic_batch(100, 4, 2, size, size)
+    out = mt.step(img.to(D), lab.to(D), 2)
+    for key in ('s_task_loss', 't_task_loss', 'cons_loss'):
+        rec['mt_%s_0' % key] = float(out[key])
+    rec['mt_grad_checksum_0'] = checksums([(n, out['grads'][n]) for n in names])
+    rec['mt_s_param_checksum_0'] = checksums([(n, mt.s[n]) for n in names])
+    rec['mt_t_param_checksum_0'] = checksums([(n, mt.t[n]) for n in names])
+    for n in SAMPLE_PARAMS:
+        rec['mt_grad_0/%s' % n] = sample_of(out['grads'][n].float())
+    np.savez_compressed(os.path.join(OUT, 'fp64_truth_%d.npz' % size), **rec)
+    print('fp64 truth (mid-size) written')
+
+
 def golden_fp64():
     """Exact-arithmetic (fp64) evaluation of the SAME steps with the oracle, to measure the
     reference's own fp32 rounding noise on these (ill-conditioned, random-init) networks.  The GPU
@@ -532,6 +554,13 @@ if __name__ == '__main__':
     if which == ['fp64']:
         golden_fp64()
         sys.exit(0)
+    if which == ['fp64mid']:
+        golden_fp64_mid()
+        sys.exit(0)
+    if 'mtmid' in which:
+        # mid-size step: crosses the 257 -> 129 -> 65 -> 33 -> 17 feature-map sizes (odd tile edges on every level)
+        golden_mt(pixelssl, sseg_proxy, size=257, steps=1)
+        golden_fp64_mid()
     if 'ops' in which:
         golden_ops(pixelssl, sseg_proxy)
     if 'forward' in which:

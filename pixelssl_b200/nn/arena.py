@@ -17,11 +17,12 @@ class ParamArena:
         self.params = params
         dev = params[0].device
         total = sum(p.numel() for p in params)
-        # 16-byte aligned segments so per-parameter kernels may use 128-bit accesses
+        # segments aligned to 8 elements: 32 bytes in fp32 (128-bit accesses), 16 bytes in the arena-wide fp16 pairs
+        # (TMA descriptors over a slice need a 16-byte aligned base)
         offs, cur = [], 0
         for p in params:
             offs.append(cur)
-            cur += (p.numel() + 3) // 4 * 4
+            cur += (p.numel() + 7) // 8 * 8
         self.numel = cur
         self.offsets = offs
         self.data = torch.zeros(cur, dtype=torch.float32, device=dev)
@@ -121,7 +122,7 @@ class ParamArena:
         spans = sorted(self._index[id(p)] for p in group_params)
         runs = []
         for o, n in spans:
-            end = o + (n + 3) // 4 * 4
+            end = o + (n + 7) // 8 * 8
             if runs and runs[-1][1] == o:
                 runs[-1][1] = end
             else:
@@ -181,23 +182,47 @@ class ParamArena:
                 st['step'] = torch.tensor(float(self.steps))
         ops.new_step()
 
+    def invalidate(self):
+        """Parameters were written behind the arena's back (load_state_dict, param.copy_): drop every derived copy
+        (transposes, tf32 splits, fp16 pairs) and per-tensor split caches."""
+        self._derived_key = None
+        ops.new_step()
+
     def adopt_optimizer_state(self, optimizer):
-        """After ``optimizer.load_state_dict`` (resume): pull the loaded momentum buffers into the
-        flat arena and point the optimizer state back at the arena views."""
-        found = False
+        """After ``optimizer.load_state_dict`` (resume): pull the loaded SGD momentum buffers / Adam moments and
+        step count into the flat arena and point the optimizer state back at the arena views, so that the fused
+        update continues exactly where the checkpoint left off (torch.optim semantics on resume)."""
+        found_sgd = False
+        adam_step = None
         for g in optimizer.param_groups:
             for p in g['params']:
-                buf = optimizer.state.get(p, {}).get('momentum_buffer')
+                st = optimizer.state.get(p, {})
+                o, n = self._index[id(p)]
+                buf = st.get('momentum_buffer')
                 if buf is not None:
                     if self.mom is None:
                         self.mom = torch.zeros_like(self.data)
-                    o, n = self._index[id(p)]
                     view = self._view_like(self.mom, o, p)
                     view.copy_(buf)
-                    optimizer.state[p]['momentum_buffer'] = view
-                    found = True
-        if found:
+                    st['momentum_buffer'] = view
+                    found_sgd = True
+                if 'exp_avg' in st and 'exp_avg_sq' in st:
+                    if getattr(self, 'exp_avg', None) is None:
+                        self.exp_avg = torch.zeros_like(self.data)
+                        self.exp_avg_sq = torch.zeros_like(self.data)
+                    for key, flat in (('exp_avg', self.exp_avg), ('exp_avg_sq', self.exp_avg_sq)):
+                        view = self._view_like(flat, o, p)
+                        if st[key].data_ptr() != view.data_ptr():
+                            view.copy_(st[key])
+                        st[key] = view
+                    step = st.get('step', 0)
+                    step = int(step.item()) if torch.is_tensor(step) else int(step)
+                    adam_step = step if adam_step is None else max(adam_step, step)
+        if adam_step is not None:
+            self.steps = adam_step          # bias correction continues from the checkpoint's step count
+        elif found_sgd:
             self.steps = max(self.steps, 1)
+        self.invalidate()
 
 
 class EngineParallel(nn.Module):
@@ -231,6 +256,12 @@ class EngineParallel(nn.Module):
 
     def forward(self, *inputs, **kwargs):
         return self.module(*inputs, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        if self.arena is not None:
+            self.arena.invalidate()       # the copies into the parameter views bypass the arena's version counter
+        return out
 
 
 

@@ -71,13 +71,17 @@ def kernel_timer_start(name):
     _ktimers[name] = []
 
 
-def kernel_timer_stop(name):
+def kernel_timer_stop(name, with_meta=False):
+    """-> per-launch milliseconds; with_meta: [(ms, meta)] where meta is what the call site attached (the
+    algorithmic FLOPs of a convolution launch)."""
     pairs = _ktimers.pop(name, [])
     torch.cuda.synchronize()
-    return [a.elapsed_time(b) for a, b in pairs]
+    if with_meta:
+        return [(a.elapsed_time(b), m) for a, b, m in pairs]
+    return [a.elapsed_time(b) for a, b, _ in pairs]
 
 
-def _timed_call(name, *args):
+def _timed_call(name, *args, meta=None):
     rec = _ktimers.get(name)
     if rec is None:
         return call(name, *args)
@@ -85,7 +89,7 @@ def _timed_call(name, *args):
     a.record()
     rc = call(name, *args)
     b.record()
-    rec.append((a, b))
+    rec.append((a, b, meta))
     return rc
 
 
@@ -529,8 +533,9 @@ def _stride2_dgrad_classes(taps, ntaps):
 
 
 def _tc_launch(geom, taps, ext, x_parts, w_parts, bias, out):
-    call('pxl_conv_tc_launch_ex', ctypes.byref(geom), _ctaps(taps), ctypes.byref(ext) if ext is not None else None,
-         _p(x_parts[0]), _p(x_parts[1]), _p(w_parts[0]), _p(w_parts[1]), _p(bias), _p(out), _stream())
+    _timed_call('pxl_conv_tc_launch_ex', ctypes.byref(geom), _ctaps(taps), ctypes.byref(ext) if ext is not None else None,
+                _p(x_parts[0]), _p(x_parts[1]), _p(w_parts[0]), _p(w_parts[1]), _p(bias), _p(out), _stream(),
+                meta=2.0 * geom.N * geom.OH * geom.OW * geom.Cin * geom.Cout * geom.ntaps)
 
 
 def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, out=None, precision=None, bn_stats=None):
@@ -564,8 +569,9 @@ def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div,
 
         def launch(geom, tp, ext):
             ext.out_scale, ext.out_scale_dev = oscale, (odev.data_ptr() if odev is not None else None)
-            call('pxl_conv_h16_launch', ctypes.byref(geom), _ctaps(tp), ctypes.byref(ext), _p(xh.hi), _p(xh.lo),
-                 _p(wh.hi), _p(wh.lo if want_lo else None), _p(bias), _p(out), _stream())
+            _timed_call('pxl_conv_h16_launch', ctypes.byref(geom), _ctaps(tp), ctypes.byref(ext), _p(xh.hi), _p(xh.lo),
+                        _p(wh.hi), _p(wh.lo if want_lo else None), _p(bias), _p(out), _stream(),
+                        meta=2.0 * geom.N * geom.OH * geom.OW * geom.Cin * min(geom.Cout, Cout) * geom.ntaps)
         if div == 1:
             ext = ConvTcExt(0, None, 0, 0, 0, 0, 0, None)
             if bn_stats is not None:
@@ -641,8 +647,9 @@ def conv_wgrad_raw(x, dy, dw, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, p
         if px is not None and pd is not None:
             raise ValueError('at most one operand may carry a device-side scale')
         geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
-        call('pxl_conv_wgrad_h16_launch', ctypes.byref(geom), _ctaps(taps), _p(xh.hi), _p(xh.lo), _p(dh.hi), _p(dh.lo),
-             _p(dw), float(fx * fd), _p(pd if pd is not None else px), _stream())
+        _timed_call('pxl_conv_wgrad_h16_launch', ctypes.byref(geom), _ctaps(taps), _p(xh.hi), _p(xh.lo), _p(dh.hi), _p(dh.lo),
+                    _p(dw), float(fx * fd), _p(pd if pd is not None else px), _stream(),
+                    meta=2.0 * N * OH * OW * Cin * Cout * ntaps)
         return dw
     if prec != 0 and div == 1 and mul in _WGRAD_TC_STRIDES and Cin % 32 == 0 and ldo % 32 == 0:
         geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
@@ -652,11 +659,11 @@ def conv_wgrad_raw(x, dy, dw, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, p
                 dy = dy if isinstance(dy, tuple) else split_tf32(dy)
             x_hi, x_lo = x if isinstance(x, tuple) else (x, None)     # raw operands: split inside the kernel
             d_hi, d_lo = dy if isinstance(dy, tuple) else (dy, None)
-            call('pxl_conv_wgrad_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x_hi), _p(x_lo), _p(d_hi), _p(d_lo),
-                 _p(dw), _stream())
+            _timed_call('pxl_conv_wgrad_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x_hi), _p(x_lo), _p(d_hi), _p(d_lo),
+                        _p(dw), _stream(), meta=2.0 * N * OH * OW * Cin * Cout * ntaps)
         else:
-            call('pxl_conv_wgrad_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x), _p(None), _p(dy), _p(None),
-                 _p(dw), _stream())
+            _timed_call('pxl_conv_wgrad_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x), _p(None), _p(dy), _p(None),
+                        _p(dw), _stream(), meta=2.0 * N * OH * OW * Cin * Cout * ntaps)
         return dw
     if isinstance(x, tuple):
         x = x[0] + x[1]
@@ -978,6 +985,11 @@ class _BnAct(torch.autograd.Function):
         else:
             call('pxl_bn_eval_coeffs', C, _p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps),
                  _p(coeff[2]), _p(coeff[3]), _stream())
+            if torch.is_grad_enabled() and (x.requires_grad or gamma.requires_grad):
+                # eval-mode BN inside a training graph (freeze_bn): the backward treats the running statistics as
+                # constants; mean / inv_std slots hold them for bn_bwd_reduce (tiny per-channel torch ops)
+                coeff[0].copy_(running_mean)
+                coeff[1].copy_(torch.rsqrt(running_var + eps))
         if not applied:
             if residual is not None:
                 _chk(residual, 'residual', cl=True)
@@ -992,9 +1004,23 @@ class _BnAct(torch.autograd.Function):
         rows, C, count, relu, has_res, training, eps, group = ctx.meta
         dy = as_cl(dy)
         dev = dy.device
-        if not training:
-            raise NotImplementedError('backward through eval-mode BN is not on the training path')
         dsums = _stat_zeros(2 * C, dev)
+        if not training:
+            # F.batch_norm(training=False) backward: dx = dz * gamma / sqrt(running_var + eps), d(gamma) = sum dz * xhat,
+            # d(beta) = sum dz with xhat from the running statistics.  The reduce launch gives the parameter sums; the
+            # dx launch runs with zero batch sums, which removes its mean terms.
+            ymask = y if (relu and has_res) else None
+            call('pxl_bn_bwd_reduce', _p(x), _p(ymask), _p(dy), _p(coeff[0]), _p(coeff[1]), int(relu), rows, C, _p(dsums),
+                 _p(coeff[2]), _p(coeff[3]), _stream())
+            dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+            call('pxl_bn_bwd_params', _p(dsums), C, _p(dgamma), _p(dbeta), 0, _stream())
+            zsums = _stat_zeros(2 * C, dev)
+            dx = torch.empty_like(x)
+            dres = torch.empty_like(x) if has_res else None
+            call('pxl_bn_bwd_dx', _p(x), _p(ymask), _p(dy), _p(coeff[0]), _p(coeff[1]), _p(gamma), _p(zsums), count, int(relu),
+                 _p(dx), _p(dres), rows, C, _p(coeff[2]), _p(coeff[3]), _p(None), _p(None), _stream())
+            return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None, None
         # ReLU without residual: the mask is recomputed from x (same fmaf as the forward) instead of reading y
         ymask = y if (relu and has_res) else None
         call('pxl_bn_bwd_reduce', _p(x), _p(ymask), _p(dy), _p(coeff[0]), _p(coeff[1]), int(relu), rows, C, _p(dsums),

@@ -72,6 +72,8 @@ def build_args(config, iters_per_epoch=100):
     """config dict (as in task/sseg/script/*.py) -> argparse.Namespace with the autoset fields."""
     parser = create_parser(config['ssl_algorithm'])
     add_proxy_arguments(parser)
+    if 'pretrained_backbone' not in config:
+        config = dict(config, pretrained_backbone='none')     # programmatic builds (tests, bench): synthetic weights
     args = cmd.parse_args(parser, config)
     args.gpus = 1                     # one process drives one GPU (flags are per-GPU, proxy.py:59,260)
     args.task = 'sseg'

@@ -213,6 +213,7 @@ class SSLADV(ssl_base._SSLBase):
         self.optimizer.load_state_dict(checkpoint['optimizer'])
         self.model.arena.adopt_optimizer_state(self.optimizer)
         self.d_optimizer.load_state_dict(checkpoint['d_optimizer'])
+        self.d_model.arena.adopt_optimizer_state(self.d_optimizer)      # Adam moments + step count
         self.lrer.load_state_dict(checkpoint['lrer'])
         self.d_lrer.load_state_dict(checkpoint['d_lrer'])
         return checkpoint['epoch']

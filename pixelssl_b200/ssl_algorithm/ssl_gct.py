@@ -288,4 +288,5 @@ class SSLGCT(ssl_base._SSLBase):
             getattr(self, key).load_state_dict(checkpoint[key])
         self.l_model.arena.adopt_optimizer_state(self.l_optimizer)
         self.r_model.arena.adopt_optimizer_state(self.r_optimizer)
+        self.fd_model.arena.adopt_optimizer_state(self.fd_optimizer)    # Adam moments + step count
         return checkpoint['epoch']

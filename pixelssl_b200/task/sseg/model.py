@@ -13,6 +13,10 @@ def add_parser_arguments(parser):
     parser.add_argument('--output-stride', type=int, default=16)
     parser.add_argument('--backbone', type=str, default='resnet101')
     parser.add_argument('--freeze-bn', type=cmd.str2bool, default=False)
+    # 'auto' = the URL the reference hard-codes for args.backbone (task/sseg/model.py:69-80), served from the local
+    # torch-hub cache / $PXL_PRETRAINED_DIR when present, downloaded otherwise; 'none' = keep the reference
+    # initialisers; anything else = a local file or URL.  A requested-but-unloadable backbone is an error.
+    parser.add_argument('--pretrained-backbone', type=str, default='auto')
 
 
 def deeplabv2():
@@ -56,6 +60,24 @@ class TaskModel(nn.Module):
         self.param_groups = []
 
 
+# task/sseg/model.py:69-80 / :89-98
+PRETRAINED_BACKBONE_URLS = {
+    'resnet50': 'https://download.pytorch.org/models/resnet50-19c8e357.pth',
+    'resnet101': 'https://download.pytorch.org/models/resnet101-5d3b4d8f.pth',
+    'resnet101-coco': 'http://vllab1.ucmerced.edu/~whung/adv-semi-seg/resnet101COCO-41f33a49.pth',
+}
+
+
+def pretrained_backbone_url(args):
+    """-> URL / path handed to the backbone, or None for the reference initialisers."""
+    want = getattr(args, 'pretrained_backbone', 'auto')
+    if want in (None, '', 'none', 'None', False):
+        return None
+    if want == 'auto':
+        return PRETRAINED_BACKBONE_URLS.get(args.backbone)
+    return want
+
+
 class DeepLabV2(TaskModel):
     def __init__(self, args):
         super().__init__(args)
@@ -64,7 +86,7 @@ class DeepLabV2(TaskModel):
         self.model = deeplab_v2.DeepLabV2(backbone=args.backbone, output_stride=args.output_stride,
                                           num_classes=args.num_classes, sync_bn=True,
                                           freeze_bn=args.freeze_bn,
-                                          pretrained_backbone_url=getattr(args, 'pretrained_backbone', None))
+                                          pretrained_backbone_url=pretrained_backbone_url(args))
         self.param_groups = [
             {'params': list(self.model.get_1x_lr_params()), 'lr': args.lr},
             {'params': list(self.model.get_10x_lr_params()), 'lr': args.lr * 10},
@@ -92,7 +114,7 @@ class PSPNet(TaskModel):
             logger.log_err('PSPNet does not support the backbone: {0}\n'.format(args.backbone))
         self.model = pspnet_module.PSPNet(backbone=args.backbone, output_stride=args.output_stride,
                                           num_classes=args.num_classes, sync_bn=True, freeze_bn=args.freeze_bn,
-                                          pretrained_backbone_url=getattr(args, 'pretrained_backbone', None))
+                                          pretrained_backbone_url=pretrained_backbone_url(args))
         self.param_groups = [
             {'params': [p for p in self.model.get_backbone_params() if p.requires_grad], 'lr': args.lr},
             {'params': [p for p in self.model.get_psp_params() if p.requires_grad], 'lr': args.lr * 10},

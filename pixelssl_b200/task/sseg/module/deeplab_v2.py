@@ -41,11 +41,9 @@ class DeepLabV2(nn.Module):
         x = ops.bilinear(low, img.shape[2:], align_corners=True, channels=self.num_classes, nhwc=True)
         return x, bx
 
-    def train(self, mode=True):
-        super().train(mode)
-        if self._freeze:
-            self.freeze_bn()
-        return self
+    # No train() override: like the reference (deeplab_v2.py:46-52, model.py:69-80) freeze_bn() is applied once at
+    # construction and is undone by the .train() call that starts every epoch; BN layers that ARE in eval mode inside
+    # a training graph are supported by ops.bn_act (running statistics as constants in the backward).
 
     def freeze_bn(self):
         for m in self.modules():

@@ -96,15 +96,37 @@ class ResNet(nn.Module):
                 m.bias.data.zero_()
 
     def _load_pretrained_model(self, url):
-        """resnet.py:145-156 downloads ImageNet/COCO weights; there is no network here, so only
-        local files are honoured."""
+        """resnet.py:145-156: a local file is loaded as a complete state dict; a URL goes through the model zoo and is
+        key-filtered (torchvision / COCO checkpoints carry an ``fc`` head the dilated backbone does not have).  The zoo
+        file is looked up in $PXL_PRETRAINED_DIR and the torch-hub cache before any download is attempted; weights that
+        were requested but cannot be obtained are an error, never a silent random init."""
         if os.path.isfile(url):
-            pre = torch.load(url, map_location='cpu')
-            own = self.state_dict()
-            own.update({k: v for k, v in pre.items() if k in own})
-            self.load_state_dict(own)
-        else:
-            logger.log_warn('pretrained backbone {0} is not a local file; keeping the random init\n'.format(url))
+            self.load_state_dict(torch.load(url, map_location='cpu'))
+            return
+        pre = load_zoo_state_dict(url)
+        own = self.state_dict()
+        own.update({k: v for k, v in pre.items() if k in own})
+        self.load_state_dict(own)
+
+
+def load_zoo_state_dict(url):
+    name = os.path.basename(url)
+    cands = []
+    if os.environ.get('PXL_PRETRAINED_DIR'):
+        cands.append(os.path.join(os.environ['PXL_PRETRAINED_DIR'], name))
+    try:
+        cands.append(os.path.join(torch.hub.get_dir(), 'checkpoints', name))
+    except Exception:
+        pass
+    for path in cands:
+        if os.path.isfile(path):
+            return torch.load(path, map_location='cpu')
+    try:
+        return torch.hub.load_state_dict_from_url(url, map_location='cpu')      # model_zoo.load_url
+    except Exception as e:
+        logger.log_err('pretrained backbone {0} was requested but is neither cached ({1}) nor downloadable ({2}).\n'
+                       'Pass --pretrained-backbone none to train from the reference initialisers.\n'
+                       .format(url, ', '.join(cands), e))
 
 
 def build_backbone(backbone, output_stride, pretrained_url=None):

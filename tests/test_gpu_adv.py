@@ -107,6 +107,49 @@ def test_fc_discriminator_forward_backward(ops):
         assert rel_q(p.grad, stc[n].grad) <= 1e-2 and rel(p.grad, stc[n].grad) <= 5e-2, n   # one kink flip touches a whole filter
 
 
+def test_adam_resume_continues_moments_and_step(ops):
+    """Checkpoint resume of the arena Adam (discriminator / flaw detector optimisers, ssl_adv.py:101-102,
+    ssl_gct.py:153-154): optimizer.load_state_dict + arena.adopt_optimizer_state must continue exp_avg, exp_avg_sq and
+    the bias-correction step exactly like torch.optim.Adam does on resume."""
+    from pixelssl_b200.nn.arena import ParamArena
+    g = torch.Generator().manual_seed(5)
+    w0 = [torch.randn(7, 5, generator=g), torch.randn(12, generator=g)]
+    grads = [[torch.randn(7, 5, generator=g), torch.randn(12, generator=g)] for _ in range(4)]
+    # torch reference: 4 uninterrupted steps on CPU
+    ref = [w.clone().requires_grad_(True) for w in w0]
+    opt_ref = torch.optim.Adam(ref, lr=1e-2, betas=(0.9, 0.99))
+    for gs in grads:
+        for p, gr in zip(ref, gs):
+            p.grad = gr.clone()
+        opt_ref.step()
+
+    def make():
+        m = torch.nn.ParameterList([torch.nn.Parameter(w.clone().cuda()) for w in w0])
+        arena = ParamArena(m)
+        return m, arena, torch.optim.Adam(list(m), lr=1e-2, betas=(0.9, 0.99))
+
+    m1, a1, o1 = make()
+    for gs in grads[:2]:
+        for p, gr in zip(m1, gs):
+            p.grad.copy_(gr.cuda())
+        a1.adam_step(o1)
+    state = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in m1.state_dict().items()}
+    ostate = o1.state_dict()
+    m2, a2, o2 = make()
+    m2.load_state_dict(state)
+    o2.load_state_dict(ostate)
+    a2.adopt_optimizer_state(o2)
+    assert a2.steps == 2
+    for gs in grads[2:]:
+        for p, gr in zip(m2, gs):
+            p.grad.copy_(gr.cuda())
+        a2.adam_step(o2)
+    for p, q in zip(m2, ref):
+        assert rel(p, q) <= 1e-6
+    st = o2.state_dict()['state']
+    assert all(float(v['step']) == 4.0 for v in st.values())
+
+
 def test_adam_matches_torch(ops):
     g = torch.Generator().manual_seed(4)
     n = 10007

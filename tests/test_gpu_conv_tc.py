@@ -105,6 +105,34 @@ def test_conv_tc_stride2(ops, case, precision, tol):
 
 
 @pytest.mark.parametrize('precision,tol', PRECS)
+@pytest.mark.parametrize('case', [(2, 64, 65, 65, 128, 2), (3, 128, 33, 33, 128, 1), (2, 256, 17, 19, 512, 2), (2, 512, 9, 9, 512, 1)])
+def test_conv_tc_4x4_pad1(ops, case, precision, tol):
+    """The 4x4 / padding 1 convolutions (stride 2 and 1, with bias) of the FlawDetector (ssl_gct.py:539-585) and the
+    FC discriminator (ssl_adv.py:466-503): even kernel, so the stride-2 dgrad parity classes are asymmetric."""
+    N, Cin, H, W, Cout, stride = case
+    g = torch.Generator().manual_seed(H + Cout + stride)
+    x = torch.randn(N, Cin, H, W, generator=g).cuda().contiguous(memory_format=CL)
+    w = (torch.randn(Cout, Cin, 4, 4, generator=g) / (Cin * 16) ** 0.5).cuda().contiguous(memory_format=CL)
+    b = torch.randn(Cout, generator=g).cuda()
+    res = {}
+    for prec in (0, precision):
+        ops._conv_precision = prec
+        wg, xg, bg = w.clone().requires_grad_(True), x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        y = ops.conv2d(xg, wg, bg, stride, 1, 1)
+        y.backward(torch.ones_like(y) * 0.5 + y.detach() * 0.1)
+        res[prec] = (y.detach(), xg.grad, wg.grad, bg.grad)
+    ops._conv_precision = 0
+    assert ops.conv_tc_status() == 0 and ops.h16_status() == 0
+    errs = [rel(res[precision][i], res[0][i]) for i in range(4)]
+    print('4x4 case %s precision %d: fwd %.2e dgrad %.2e wgrad %.2e dbias %.2e' % ((case, precision) + tuple(errs)))
+    assert max(errs) <= tol, errs
+    xc, wc = x.cpu().contiguous().requires_grad_(True), w.cpu().contiguous()
+    yc = F.conv2d(xc, wc, b.cpu(), stride=stride, padding=1)
+    (yc * (0.5 + 0.1 * yc.detach())).sum().backward()
+    assert rel(res[precision][0].cpu(), yc) <= tol and rel(res[precision][1].cpu(), xc.grad) <= tol
+
+
+@pytest.mark.parametrize('precision,tol', PRECS)
 def test_aspp_head_tc(ops, precision, tol):
     g = torch.Generator().manual_seed(3)
     x = torch.randn(2, 2048, 33, 33, generator=g).cuda().contiguous(memory_format=CL)

@@ -146,10 +146,11 @@ def test_null_step_golden(eng):
                              'SupOnly params', floor_med=1e-6, floor_max=1e-4)
 
 
-def test_mt_steps_golden(eng):
-    """Three SSLMT steps: same seeds / batches as oracle/make_golden.py:golden_mt."""
+def _run_mt_golden(golden, truth):
+    """SSLMT steps on the seeds / batches of oracle/make_golden.py:golden_mt, held to the reference-generated fixture
+    ``golden`` with the fp64 oracle evaluation ``truth`` as the noise yardstick."""
     from pixelssl_b200 import runner
-    g = np.load(os.path.join(G, 'mt_steps_97.npz'))
+    g = np.load(os.path.join(G, golden))
     size, lbs, ubs = int(g['size']), int(g['lbs']), int(g['ubs'])
     args = runner.build_args(_cfg('ssl_mt', cons_for_labeled=False, cons_scale=1.0, cons_rampup_epochs=1,
                                   ema_decay=0.99, batch_size=lbs + ubs, unlabeled_batch_size=ubs), iters_per_epoch=5)
@@ -157,7 +158,7 @@ def test_mt_steps_golden(eng):
     _load(alg.s_model, _state(g['s_seed']))
     _load(alg.t_model, _state(g['t_seed']))
     names = [str(n) for n in g['names']]
-    t64 = np.load(os.path.join(G, 'fp64_truth.npz'))
+    t64 = np.load(os.path.join(G, truth))
     for k in range(int(g['steps'])):
         img, lab = O.synthetic_batch(int(g['data_seed']) + k, lbs + ubs, lbs, size, size)
         alg._train([((img,), (lab,))], k)
@@ -183,6 +184,19 @@ def test_mt_steps_golden(eng):
                 ref, tru = g['grad_0/%s' % n], t64['mt_grad_0/%s' % n]
                 yard = np.abs(ref - tru).max()
                 assert np.abs(mine - tru).max() <= FACTOR * yard + 1e-3 * np.abs(tru).max(), (n, np.abs(mine - tru).max(), yard)
+    from pixelssl_b200 import ops
+    assert ops.conv_tc_status() == 0 and ops.h16_status() == 0
+
+
+def test_mt_steps_golden(eng):
+    """Three SSLMT steps at 97x97 (ssl_mt.py:124-224)."""
+    _run_mt_golden('mt_steps_97.npz', 'fp64_truth.npz')
+
+
+def test_mt_step_golden_257(eng):
+    """One SSLMT step at 257x257, batch 2+2: feature maps 129 -> 65 -> 33 -> 17 -> 17, i.e. odd edges on every level
+    and several 128-pixel tiles per row, the tile-edge cases the 513x513 benchmark configuration hits."""
+    _run_mt_golden('mt_steps_257.npz', 'fp64_truth_257.npz')
 
 
 def test_cutmix_step_golden(eng):

@@ -312,7 +312,11 @@ def test_full_argument_set_matches_reference_runner_and_sseg_proxy():
 
     def table(parser):
         return {a.dest: (a.default, getattr(a.type, '__name__', a.type), a.choices) for a in parser._actions if a.dest != 'help'}
-    assert table(pr) == table(pe)
+    te = table(pe)
+    # engine-only option: the reference hard-codes the pretrained-backbone URL per backbone (task/sseg/model.py:69-80);
+    # the engine exposes the same choice as a flag whose default 'auto' resolves to exactly those URLs
+    assert te.pop('pretrained_backbone') == ('auto', 'str', None)
+    assert table(pr) == te
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree only exists in the build container')
@@ -455,3 +459,39 @@ def test_optimizer_wrappers_build_the_reference_optimizer(name):
         ka = {k: v for k, v in ga.items() if k != 'params'}
         kb = {k: v for k, v in gb.items() if k != 'params'}
         assert ka == kb
+
+
+def test_pretrained_backbone_url_resolution_and_key_filtered_load(tmp_path, monkeypatch):
+    """--pretrained-backbone: 'auto' resolves to the URLs the reference hard-codes (task/sseg/model.py:69-80), 'none'
+    keeps the initialisers; a zoo checkpoint found in the local cache is loaded key-filtered like resnet.py:145-156
+    (torchvision layout: extra ``fc.*`` entries are dropped, backbone entries overwrite the initialisers)."""
+    import argparse
+    import torch
+    from pixelssl_b200.task.sseg import model as M
+    from pixelssl_b200.task.sseg.module import resnet as R
+    ns = argparse.Namespace(backbone='resnet101', pretrained_backbone='auto')
+    assert M.pretrained_backbone_url(ns) == 'https://download.pytorch.org/models/resnet101-5d3b4d8f.pth'
+    ns.backbone = 'resnet101-coco'
+    assert M.pretrained_backbone_url(ns).endswith('resnet101COCO-41f33a49.pth')
+    ns.pretrained_backbone = 'none'
+    assert M.pretrained_backbone_url(ns) is None
+    ns.pretrained_backbone = '/some/file.pth'
+    assert M.pretrained_backbone_url(ns) == '/some/file.pth'
+    # synthetic torchvision-layout checkpoint for a ResNet-50 in the cache directory
+    net = R.ResNet([3, 4, 6, 3], 16)
+    g = torch.Generator().manual_seed(0)
+    fake = {k: torch.randn(v.shape, generator=g) if v.is_floating_point() else v.clone() for k, v in net.state_dict().items()}
+    fake['fc.weight'] = torch.randn(1000, 2048, generator=g)
+    fake['fc.bias'] = torch.randn(1000, generator=g)
+    torch.save(fake, tmp_path / 'resnet50-19c8e357.pth')
+    monkeypatch.setenv('PXL_PRETRAINED_DIR', str(tmp_path))
+    net2 = R.ResNet([3, 4, 6, 3], 16, pretrained_url=M.PRETRAINED_BACKBONE_URLS['resnet50'])
+    for k, v in net2.state_dict().items():
+        assert torch.equal(v, fake[k]), k
+    assert net2.conv1.weight.is_contiguous(memory_format=torch.channels_last)
+    # requested but unobtainable: an error, not a silent random init
+    monkeypatch.setenv('PXL_PRETRAINED_DIR', str(tmp_path / 'nowhere'))
+    monkeypatch.setattr(torch.hub, 'get_dir', lambda: str(tmp_path / 'nohub'))
+    monkeypatch.setattr(torch.hub, 'load_state_dict_from_url', lambda *a, **k: (_ for _ in ()).throw(OSError('offline')))
+    with pytest.raises(BaseException):
+        R.ResNet([3, 4, 6, 3], 16, pretrained_url=M.PRETRAINED_BACKBONE_URLS['resnet50'])

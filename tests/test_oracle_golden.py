@@ -162,6 +162,33 @@ def test_mt_steps_match_reference_train_body():
 
 
 @pytest.mark.slow
+def test_mt_step_257_matches_reference_train_body():
+    """The mid-size fixture (257x257, batch 2+2, one step) pins the oracle on the feature-map sizes the 513x513
+    benchmark configuration produces modulo scale (odd edges on every pyramid level)."""
+    g = load('mt_steps_257.npz')
+    size, lbs, ubs = int(g['size']), int(g['lbs']), int(g['ubs'])
+    assert (size, lbs, ubs, int(g['steps'])) == (257, 2, 2, 1)
+    s = O.randomize_bn_affine(O.init_deeplabv2(int(g['s_seed'][0]), cls_bias_std=0.01), int(g['s_seed'][1]))
+    t = O.randomize_bn_affine(O.init_deeplabv2(int(g['t_seed'][0]), cls_bias_std=0.01), int(g['t_seed'][1]))
+    mt = O.MTOracle(s, t, lr=0.00025, momentum=0.9, weight_decay=0.0005, max_iters=10,
+                    cons_scale=1.0, rampup_steps=1, ema_decay=0.99, cons_for_labeled=False)
+    img, lab = O.synthetic_batch(int(g['data_seed']), lbs + ubs, lbs, size, size)
+    out = mt.step(img, lab, lbs)
+    for key in ('s_task_loss', 't_task_loss', 'cons_loss'):
+        ref = float(g['%s_0' % key])
+        assert abs(float(out[key]) - ref) <= 2e-5 * max(1.0, abs(ref)), (key, float(out[key]), ref)
+    gc = _checks([out['grads'][n] for n in mt.names])
+    rel = np.abs(gc[:, 1] - g['grad_checksum_0'][:, 1]) / np.maximum(g['grad_checksum_0'][:, 1], 1e-30)
+    assert rel.max() < 1e-3 and np.median(rel) < 2e-4, (mt.names[int(rel.argmax())], rel.max(), np.median(rel))
+    np.testing.assert_allclose(_checks([mt.s[n] for n in mt.names])[:, 1], g['s_param_checksum_0'][:, 1], rtol=1e-5)
+    np.testing.assert_allclose(_checks([mt.t[n] for n in mt.names])[:, 1], g['t_param_checksum_0'][:, 1], rtol=1e-5)
+    # and the fp32 noise floor at this size is recorded next to it
+    t64 = load('fp64_truth_257.npz')
+    noise = np.abs(g['grad_checksum_0'][:, 1] - t64['mt_grad_checksum_0'][:, 1]) / t64['mt_grad_checksum_0'][:, 1]
+    assert 1e-5 < np.median(noise) < 1e-2, np.median(noise)
+
+
+@pytest.mark.slow
 def test_null_and_cutmix_steps_match_reference_train_bodies():
     """ssl_null.py:78-144 and ssl_cutmix.py:140-251 (masks from the same numpy seed)."""
     names = [n for n, _, _ in O.deeplabv2_param_shapes()]
