@@ -494,6 +494,56 @@ def golden_fp64_mid(size=257):
     print('fp64 truth (mid-size) written')
 
 
+def golden_fp64_algs():
+    """fp64 oracle evaluation of the Adv / GCT / CCT golden steps (adv_step_65, gct_step_129, cct_step_65): the
+    yardstick of the reference's own fp32 noise for the quantities tests/test_gpu_{adv,gct,cct}.py compare."""
+    import random
+    from oracle import adv_oracle as A, gct_oracle as Gc, cct_oracle as C
+    D = torch.float64
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    rec = {}
+
+    def td(st):
+        return {k: (v.to(D) if v.is_floating_point() else v) for k, v in st.items()}
+    # AdvSSL
+    s = O.to_dtype(O.randomize_bn_affine(O.init_deeplabv2(81, cls_bias_std=0.01), 82), D)
+    adv = A.AdvOracle(s, td(A.init_fcd(83)), labeled_adv_scale=0.01, unlabeled_adv_scale=0.001, adv_for_labeled=True,
+                      discriminator_lr=1e-4, unlabeled_for_discriminator=True, lr=0.00025, momentum=0.9,
+                      weight_decay=0.0005, max_iters=10)
+    img, lab = O.synthetic_batch(600, 4, 2, 65, 65)
+    out = adv.step(img.to(D), lab.to(D), 2)
+    for k in ('task_loss', 'labeled_adv_loss', 'unlabeled_adv_loss', 'fake_d_loss', 'real_d_loss'):
+        rec['adv_' + k] = float(out[k])
+    rec['adv_grad_checksum'] = checksums([(n, out['grads'][n]) for n in names])
+    rec['adv_d_grad_checksum'] = checksums([(n, out['d_grads'][n]) for n in adv.d_names])
+    print('adv fp64 done')
+    # GCT
+    lst = O.to_dtype(O.randomize_bn_affine(O.init_deeplabv2(91, cls_bias_std=0.01), 92), D)
+    rst = O.to_dtype(O.randomize_bn_affine(O.init_deeplabv2(93, cls_bias_std=0.01), 94), D)
+    gct = Gc.GctOracle(lst, rst, td(Gc.init_fd(95)), 129, fc_ssl_scale=1.0, dc_ssl_scale=100.0, dc_threshold=0.45,
+                       rampup_steps=0, fd_lr=1e-4, fd_scale=10.0, mu=0.5, nu=1)
+    img, lab = O.synthetic_batch(700, 4, 2, 129, 129)
+    out = gct.step(img.to(D), lab.to(D), 2)
+    for k in ('l_task_loss', 'l_fc_loss', 'l_dc_loss', 'r_task_loss', 'r_fc_loss', 'r_dc_loss', 'l_fd_loss', 'r_fd_loss'):
+        rec['gct_' + k] = float(out[k])
+    for mid in ('l', 'r'):
+        rec['gct_%s_grad_checksum' % mid] = checksums([(n, out[mid + '_grads'][n]) for n in names])
+    rec['gct_fd_grad_checksum'] = checksums([(n, out['fd_grads'][n]) for n in gct.fd_names])
+    print('gct fp64 done')
+    # CCT
+    st = O.to_dtype(O.randomize_bn_affine(O.init_deeplabv2(101, cls_bias_std=0.01), 102), D)
+    cct = C.CctOracle(st, td(C.init_decoders(103, 7)), C.KINDS, cons_scale=30.0, rampup_steps=0, ad_lr_scale=10.0,
+                      lr=0.00025, momentum=0.9, weight_decay=0.0005, max_iters=10)
+    img, lab = O.synthetic_batch(800, 4, 2, 65, 65)
+    random.seed(7); np.random.seed(8); torch.manual_seed(9)
+    out = cct.step(img.to(D), lab.to(D), 2)
+    rec['cct_task_loss'], rec['cct_cons_loss'] = float(out['task_loss']), float(out['cons_loss'])
+    rec['cct_grad_checksum'] = checksums([(n, out['grads'][n]) for n in names])
+    rec['cct_dec_grad_checksum'] = checksums([(n, out['dec_grads'][n]) for n in cct.dec_names])
+    np.savez_compressed(os.path.join(OUT, 'fp64_truth_algs.npz'), **rec)
+    print('fp64 truth (adv / gct / cct) written')
+
+
 def golden_fp64():
     """Exact-arithmetic (fp64) evaluation of the SAME steps with the oracle, to measure the
     reference's own fp32 rounding noise on these (ill-conditioned, random-init) networks.  The GPU
@@ -553,6 +603,9 @@ if __name__ == '__main__':
     which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 'gct', 'cct', 'pspnet', 'val', 'input', 'fp64']
     if which == ['fp64']:
         golden_fp64()
+        sys.exit(0)
+    if which == ['fp64algs']:
+        golden_fp64_algs()
         sys.exit(0)
     if which == ['fp64mid']:
         golden_fp64_mid()

@@ -537,7 +537,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128 * (p.a_inkernel ? 1 : 2)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(&tmem_base_slot, tmem_cols);
@@ -611,11 +611,17 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                 if (ok) umma_commit(&acc_full[set]);
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 6 || !p.a_inkernel) {
         // ================= epilogue =================
+        // Without an operand transform (every mode but 3xTF32 on raw activations) warps 6..9 form a second epilogue
+        // group: the two groups take alternate 32-column slabs of the tile (TMEM lane quarter = warp % 4 either
+        // way), each with its own staging slab and named barrier.
+        const int grp = warp >= 6 ? 1 : 0;
+        const int ngrp = p.a_inkernel ? 1 : 2;
         const int q = warp & 3;
         const int r = q * 32 + lane;
-        const int et = threadIdx.x - 64;                 // 0..127
+        const int et = threadIdx.x - 64 - 128 * grp;     // 0..127 within the group
+        const int barid = 1 + grp;
         uint32_t tcount = 0, sc = 0;
         const float osc = p.out_scale * (oscale_ptr ? __ldg(oscale_ptr) : 1.f);
         bool ok = true;
@@ -632,7 +638,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             float* orow = out + ((int64_t)(n * p.outH + oy * p.out_mul + p.out_offy) * p.outW + ox * p.out_mul + p.out_offx) * p.ldo;
             const int used = iters < p.nacc ? iters : p.nacc;
             const uint32_t tbase = tmem_d + set * set_cols + ((uint32_t)(q * 32) << 16);
-            for (int j = 0; j < p.BN; j += 32) {
+            for (int j = 32 * grp; j < p.BN; j += 32 * ngrp) {
                 const int cb = n0 + j;
                 if (cb >= p.Cout) break;                  // uniform: nothing left to store for this tile
                 float v[32];
@@ -673,16 +679,20 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                     }
                 }
                 if (p.tma_store) {
-                    const uint32_t b = sc & 1u;
-                    // slab b was last stored two slabs ago: its TMA read must be over before it is rewritten
-                    if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    // one group: two staging slabs used alternately (slab b was last stored two slabs ago);
+                    // two groups: one slab each, its previous TMA read must be over before it is rewritten
+                    const uint32_t b = ngrp == 1 ? (sc & 1u) : (uint32_t)grp;
+                    if (et == 0) {
+                        if (ngrp == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
                     float4* dst = reinterpret_cast<float4*>(staging + (size_t)b * TC_A_BYTES + (size_t)r * 128);
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
                         dst[c ^ (r & 7)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
                     if (et == 0) {
                         tma_store_4d(staging + (size_t)b * TC_A_BYTES, &mapOut, cb, w0, h0, n);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -1197,7 +1207,7 @@ static int conv_tc_launch_core(const pxl_conv_geom* g, const int* taps, const px
     // tuning knobs (environment, read once): shared-memory budget per CTA in KB (<= ~100 lets two CTAs share
     // an SM so one CTA's epilogue overlaps the other's main loop), N-tile cap, accumulator count
     static int cfg_budget_kb = -1, cfg_bn_max1 = 256, cfg_bn_max3 = 128, cfg_nacc3 = 4;
-    static int cfg_bn_max_h3 = 128, cfg_bn_max_h1 = 256, cfg_nacc_h3 = 2, cfg_nacc_h1 = 1;
+    static int cfg_bn_max_h3 = 256, cfg_bn_max_h1 = 256, cfg_nacc_h3 = 4, cfg_nacc_h1 = 1;   // measured: tools/sweep_h16.sh
     if (cfg_budget_kb < 0) {
         const char* e = getenv("PXL_TC_SMEM_KB"); cfg_budget_kb = e ? atoi(e) : 200;
         if ((e = getenv("PXL_TC_BN_MAX_TF32"))) cfg_bn_max1 = atoi(e);
@@ -1653,7 +1663,7 @@ static int conv_wgrad_tc_core(const pxl_conv_geom* g, const int* taps, const voi
     } else {
         p.N = g->N; p.OH = g->OH; p.OW = g->OW; mapW = g->OW; mapH = g->OH; mapN = g->N; inW = g->W; inH = g->H;
     }
-    static int cfg_wg_bn_max = -1, cfg_wg_bn_max_h3 = 128, cfg_wg_bn_max_h1 = 256, cfg_wg_rows_h3 = 64, cfg_wg_rows_h1 = 64;
+    static int cfg_wg_bn_max = -1, cfg_wg_bn_max_h3 = 256, cfg_wg_bn_max_h1 = 256, cfg_wg_rows_h3 = 64, cfg_wg_rows_h1 = 128;
     if (cfg_wg_bn_max < 0) {
         const char* e = getenv("PXL_WG_BN_MAX"); cfg_wg_bn_max = e ? atoi(e) : 128;
         if ((e = getenv("PXL_WG_BN_MAX_F16X3"))) cfg_wg_bn_max_h3 = atoi(e);

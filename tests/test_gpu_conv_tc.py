@@ -81,7 +81,8 @@ def test_conv_tc_forward_and_dgrad(ops, case, precision, tol):
 
 
 @pytest.mark.parametrize('precision,tol', PRECS)
-@pytest.mark.parametrize('case', [(2, 128, 33, 35, 128, 3), (2, 256, 17, 17, 512, 1), (1, 64, 65, 65, 64, 3)])
+@pytest.mark.parametrize('case', [(2, 128, 33, 35, 128, 3), (2, 256, 17, 17, 512, 1), (1, 64, 65, 65, 64, 3),
+                                  (2, 128, 32, 36, 128, 3), (1, 64, 64, 64, 128, 1)])      # even input sizes too
 def test_conv_tc_stride2(ops, case, precision, tol):
     """stride-2 convolutions: forward and wgrad use the TMA traversal stride, dgrad is decomposed by
     output parity into four stride-1 launches."""
@@ -105,7 +106,9 @@ def test_conv_tc_stride2(ops, case, precision, tol):
 
 
 @pytest.mark.parametrize('precision,tol', PRECS)
-@pytest.mark.parametrize('case', [(2, 64, 65, 65, 128, 2), (3, 128, 33, 33, 128, 1), (2, 256, 17, 19, 512, 2), (2, 512, 9, 9, 512, 1)])
+@pytest.mark.parametrize('case', [(2, 64, 65, 65, 128, 2), (3, 128, 33, 33, 128, 1), (2, 256, 17, 19, 512, 2), (2, 512, 9, 9, 512, 1),
+                                  (3, 64, 64, 64, 128, 2), (3, 128, 32, 32, 128, 1), (3, 128, 31, 31, 256, 2), (3, 256, 14, 14, 512, 2),
+                                  (3, 512, 7, 7, 512, 1)])        # the FlawDetector's sizes at 129x129 (even and odd)
 def test_conv_tc_4x4_pad1(ops, case, precision, tol):
     """The 4x4 / padding 1 convolutions (stride 2 and 1, with bias) of the FlawDetector (ssl_gct.py:539-585) and the
     FC discriminator (ssl_adv.py:466-503): even kernel, so the stride-2 dgrad parity classes are asymmetric."""

@@ -10,7 +10,7 @@ import torch.nn.functional as F
 from oracle import sseg_oracle as O
 from oracle import gct_oracle as Gc
 
-from conftest import TEST_PRECISIONS
+from conftest import TEST_PRECISIONS, assert_loss_yardstick, assert_energy_yardstick
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), 'golden')
@@ -107,7 +107,13 @@ def test_flaw_detector_forward_backward(ops):
     (out * w.cuda()).sum().backward()
     e_out, e_in = rel(out, ref), rel_q(pg.grad, pc.grad)
     print('flaw detector: out %.2e  d/dprob %.2e' % (e_out, e_in))
-    assert e_out <= 1e-4 and e_in <= 2e-3
+    # The 99.8 % quantile of the input-gradient error counts LeakyReLU kink flips: the CPU oracle's own fp32
+    # evaluation is 4.6e-4 (max 1.1e-3) away from its fp64 evaluation, and a 1e-5 relative input perturbation moves it
+    # by the same amount (measured, oracle/gct_oracle.py).  The exact-fp32 FFMA path stays at the 2e-3 it was written
+    # for; the tensor-core modes carry ~2e-5 forward error on these K = 4x4x512 reductions (fp32 TMEM accumulation
+    # truncates, see tests/test_gpu_conv_tc.py) and flip a few more kinks: 2e-2 on the quantile, median still tight.
+    med = float(((pg.grad.cpu().double() - pc.grad.double()).abs() / pc.grad.double().abs().max()).median())
+    assert e_out <= 1e-4 and e_in <= (2e-3 if ops.get_conv_precision() == 0 else 2e-2) and med <= 2e-5, (e_out, e_in, med)
     for n, p in fd.named_parameters():
         if n.endswith('.bias') and 'bnorm' not in n and not n.startswith('classifier'):
             continue      # a conv bias in front of a normalisation has an exactly-zero true gradient: both sides are noise
@@ -133,18 +139,23 @@ def test_gct_step_golden(ops):
     alg.fd_model.load_state_dict({'module.' + k: v for k, v in Gc.init_fd(95).items()})
     img, lab = O.synthetic_batch(700, 4, 2, size, size)
     alg._train([((img,), (lab,))], 0)
-    for k in ('l_task_loss', 'r_task_loss'):
-        assert abs(float(alg.meters[k].val) - float(g[k])) <= 2e-3 * abs(float(g[k])), k
-    # SSL terms and the FD loss sit downstream of softmax maps that carry the task nets' fp32 noise
-    for k in ('l_fc_loss', 'l_dc_loss', 'r_fc_loss', 'r_dc_loss', 'l_fd_loss', 'r_fd_loss'):
-        got, ref = float(alg.meters[k].val), float(g[k])
-        print(k, got, ref)
-        assert abs(got - ref) <= 3e-2 * abs(ref), (k, got, ref)
+    t64 = np.load(os.path.join(G, 'fp64_truth_algs.npz'))        # the oracle in fp64 on the same step (make_golden.py)
+    # task losses, the SSL terms (downstream of softmax maps that carry the task nets' noise) and the FD losses:
+    # within 1e-3 of the exact value or 3x the reference's own fp32 deviation from it
+    for k in ('l_task_loss', 'r_task_loss', 'l_fc_loss', 'l_dc_loss', 'r_fc_loss', 'r_dc_loss', 'l_fd_loss', 'r_fd_loss'):
+        got = float(alg.meters[k].val)
+        print(k, got, float(g[k]), float(t64['gct_' + k]))
+        assert_loss_yardstick(got, float(g[k]), float(t64['gct_' + k]), k)
     fn = [n for n, _ in Gc.fd_param_shapes()]
     fp = dict(alg.fd_model.module.named_parameters())
+    # conv biases feeding IBNorm have an exactly-zero true gradient (the norm removes them): not comparable
     keep = np.array([not (n.endswith('.bias') and 'bnorm' not in n and not n.startswith('classifier')) for n in fn])
-    cs = np.array([float((fp[n].grad.double() ** 2).sum()) for n in fn])
-    relg = (np.abs(cs - g['fd_grad_checksum'][:, 1]) / np.maximum(g['fd_grad_checksum'][:, 1], 1e-30))[keep]
-    print('fd grad energy rel: median %.2e max %.2e' % (np.median(relg), relg.max()))
-    assert np.median(relg) <= 5e-2 and relg.max() <= 3e-1
+    sq = np.array([float((fp[n].grad.double() ** 2).sum()) for n in fn])
+    print(assert_energy_yardstick(sq, g['fd_grad_checksum'], t64['gct_fd_grad_checksum'], 'flaw-detector grads', keep=keep,
+                                  floor_med=1e-3, floor_max=1e-2))
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    for mid, model in (('l', alg.l_model), ('r', alg.r_model)):
+        sp = dict(model.module.model.named_parameters())
+        sq = np.array([float((sp[n].grad.double() ** 2).sum()) for n in names])
+        print(assert_energy_yardstick(sq, g[mid + '_grad_checksum'], t64['gct_%s_grad_checksum' % mid], mid + ' task-model grads'))
     assert abs(alg.fd_optimizer.param_groups[0]['lr'] - float(g['fd_lr'])) <= 1e-12

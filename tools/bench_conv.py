@@ -40,18 +40,22 @@ def taps_of(k, dil):
     return t
 
 
-def time_fn(fn, iters=12, warmup=3):
+def time_fn(fn, iters=8, warmup=3, reps=12):
+    """Median device time of one launch: `reps` back-to-back launches between two events (a single launch between
+    events would mostly measure the host-side launch latency of these 30-100 us kernels)."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(200000)           # ~100 us of GPU idle spin so the queue fills behind it
         a.record()
-        fn()
+        for _ in range(reps):
+            fn()
         b.record()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b) * 1e3)
+        ts.append(a.elapsed_time(b) * 1e3 / reps)
     ts.sort()
     return ts[len(ts) // 2]
 
