@@ -11,6 +11,11 @@ import torch.nn as nn
 from .. import ops
 
 
+# False: models built now stay single-process even when torch.distributed is initialised (no BN statistics exchange,
+# no gradient all-reduce) - used by bench.py's ddp_check to run the big-batch yardstick on one rank
+DISTRIBUTED = True
+
+
 class ParamArena:
     def __init__(self, module):
         params = [p for p in module.parameters()]
@@ -51,6 +56,7 @@ class ParamArena:
         self._conv_tiles = tiles
         self._derived = {}            # name -> flat tensor; valid for self._derived_key
         self._derived_key = None
+        self.distributed = DISTRIBUTED
         ops.register_param_arena(self)
 
     def derived(self, name):
@@ -131,9 +137,12 @@ class ParamArena:
 
     def all_reduce_grads(self, group=None):
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.grad, group=group)
-            self.grad.div_(dist.get_world_size(group))
+        if self.distributed and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            if dist.get_backend(group) == 'nccl':
+                dist.all_reduce(self.grad, op=dist.ReduceOp.AVG, group=group)     # the 1/world scaling rides in the reduction
+            else:
+                dist.all_reduce(self.grad, group=group)
+                self.grad.div_(dist.get_world_size(group))
 
     def sgd_step(self, optimizer, teacher=None, ema_d=0.0):
         """torch.optim.SGD.step() semantics (momentum, weight decay, dampening 0, no nesterov) read
@@ -244,7 +253,7 @@ class EngineParallel(nn.Module):
 
     def _setup_distributed(self):
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if DISTRIBUTED and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.broadcast(self.arena.data, src=0)
             for b in self.module.buffers():
                 dist.broadcast(b, src=0)
