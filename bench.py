@@ -307,10 +307,13 @@ def run_engine(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    sat_log = {}
     ms_dev, ktimes, launches = timed(dev)
+    sat_log['after_value'] = ops.h16_status_sites()
     clocks = sampler.stop() if sampler else None
     a.log_freq = 1                    # every step's losses are read back for its log line (one step late, see ssl_base)
     ms_e2e, _, _ = timed(host, api=True)
+    sat_log['after_e2e'] = ops.h16_status_sites()
     a.log_freq = 10 ** 9
 
     # instrumented pass: CUDA events around every convolution launch (outside the timed region on purpose)
@@ -332,6 +335,7 @@ def run_engine(args):
         # cuDNN's TF32 default gives the reference on a GPU); not the headline because it is outside the 1e-3
         # tolerance against the CPU reference
         ops.set_conv_precision(alt_name)
+        sat_log['before_alt'] = ops.h16_status_sites()
         ms_alt, _, _ = timed(dev)
         ops.set_conv_precision(args.precision)
         alt = {'conv_precision': alt_name, 'value': (lbs + ubs) * world * args.steps / (ms_alt / 1e3), 'unit': 'images/s',
@@ -386,7 +390,8 @@ def run_engine(args):
         'roofline': roof if roof else roof_hbm,
         'roofline_wgrad': roof_wg,
         'roofline_hbm': roof_hbm,
-        'pipeline_status': {'tcgen05_watchdog': status[0], 'fp16_pair_saturations': status[1]},
+        'pipeline_status': {'tcgen05_watchdog': status[0], 'fp16_pair_saturations': status[1],
+                            'saturations_by_site_split_fixed_dyn_bnapply_bndx': ops.h16_status_sites(), 'phases': sat_log},
     }
     if args.config == 'mt':
         ach = MT_FLOP_PER_IMG * (lbs + ubs) / (ms_dev / args.steps / 1e3) / 1e12

@@ -247,8 +247,9 @@ int pxl_conv_wgrad_h16_launch(const pxl_conv_geom* geom_host, const int* taps_dy
 int pxl_h16_split(const float* x, void* hi, void* lo, int64_t n, float scale, float* slot, int target_log2,
                   void* stream);
 int pxl_h16_absmax(const float* x, int64_t n, float* slot, void* stream);
-int* pxl_h16_sat_counter(void);      /* DEVICE int the producers of fp16 pairs add saturation events to */
-int pxl_h16_status(void);            /* number of kernels that saturated since the last reset (synchronises) */
+int* pxl_h16_sat_counter(void);      /* DEVICE int[4] the producers of fp16 pairs add saturation events to */
+int pxl_h16_status(void);            /* number of threads that clipped a value since the last reset (synchronises) */
+int pxl_h16_status_sites(int* out4_host);   /* the same per producer: split fixed / split dynamic / BN apply / BN dx */
 int pxl_h16_reset_status(void);
 /* hi = round-to-nearest tf32 of x (low 13 mantissa bits zero), lo = x - hi (exact); n % 4 == 0 */
 int pxl_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
@@ -379,6 +380,20 @@ int pxl_peer_allreduce_bn(double* sums, int n, void* const* mailboxes, int rank,
                           float* invstd, float* scale, float* shift, float* dgamma_acc, float* dbeta_acc,
                           void* stream);
 int pxl_peer_status(void);
+
+/* ---- input pipeline on the GPU (csrc/input_pipeline.cu) ------------------------------------------------------
+ * Replaces the per-sample PIL / numpy work of PascalVocDataset._train_prehandle / _val_prehandle
+ * (task/sseg/data.py:90-123): RandomScaleCrop (:223-256) = Pillow BILINEAR resize of the 8-bit image (22-bit
+ * fixed-point separable antialiased resampling, 8-bit intermediate) + NEAREST resize of the label + zero padding +
+ * crop, RandomHorizontalFlip (:184-192), Normalize (:142-161) and ToTensor (:164-181): HWC uint8 -> CHW float32,
+ * bit for bit.  The host draws the random numbers and builds the per-axis tables (window start / tap count, 22-bit
+ * weights, NEAREST indices) exactly as Pillow does; all table pointers are DEVICE int32.  lab_hw NULL = unlabeled
+ * sample (label output = label_const).  no_resize != 0: plain normalise (+crop / flip) of the source. */
+int pxl_input_prehandle(const uint8_t* img_hwc, const uint8_t* lab_hw, int H, int W, int ow, int oh, int no_resize,
+                        const int* xb, const int* xk, int kmax_x, const int* yb, const int* yk, int kmax_y,
+                        const int* lx, const int* ly, int x1, int y1, int crop_w, int crop_h, int flip,
+                        float label_fill, float label_const, const double* mean3_host, const double* std3_host,
+                        float* out_img_chw, float* out_lab_hw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -70,6 +70,7 @@ SIGNATURES = {
     'pxl_h16_absmax': (c_int, [P, c_int64, P, P]),
     'pxl_h16_sat_counter': (c_void_p, []),
     'pxl_h16_status': (c_int, []),
+    'pxl_h16_status_sites': (c_int, [P]),
     'pxl_h16_reset_status': (c_int, []),
     'pxl_split_tf32': (c_int, [P, P, P, c_int64, P]),
     'pxl_conv_tc_status': (c_int, []),
@@ -110,6 +111,8 @@ SIGNATURES = {
     'pxl_peer_allreduce_bn': (c_int, [P, c_int, P, c_int, c_int, c_int64, c_double, c_int, P, P, P, P, c_float, c_float,
                                       c_int, P, P, P, P, P, P, P]),
     'pxl_peer_status': (c_int, []),
+    'pxl_input_prehandle': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, c_int, P, P, c_int, c_int, c_int, c_int,
+                                    c_int, c_float, c_float, P, P, P, P, P]),
     'pxl_sgd_ema': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, P]),
     'pxl_ema': (c_int, [P, P, c_int64, c_float, P]),
 }

@@ -13,25 +13,33 @@
 #include "common.cuh"
 #include <cuda_fp16.h>
 
+// saturation events per producer site: [0] pxl_h16_split fixed scale, [1] pxl_h16_split dynamic scale,
+// [2] BatchNorm apply (activations), [3] BatchNorm backward dx (gradients)
 static int* g_sat_counter = nullptr;
 
 extern "C" int* pxl_h16_sat_counter(void) {
     if (!g_sat_counter) {
-        if (cudaMalloc(&g_sat_counter, sizeof(int)) != cudaSuccess) return nullptr;
-        cudaMemset(g_sat_counter, 0, sizeof(int));
+        if (cudaMalloc(&g_sat_counter, 4 * sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(g_sat_counter, 0, 4 * sizeof(int));
     }
     return g_sat_counter;
 }
 
-extern "C" int pxl_h16_status(void) {
+extern "C" int pxl_h16_status_sites(int* out4_host) {
+    for (int i = 0; i < 4; ++i) out4_host[i] = 0;
     if (!g_sat_counter) return 0;
-    int v = 0;
-    if (cudaMemcpy(&v, g_sat_counter, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    return v;
+    return cudaMemcpy(out4_host, g_sat_counter, 4 * sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int pxl_h16_status(void) {
+    int v[4];
+    if (pxl_h16_status_sites(v) != 0) return -1;
+    long long t = (long long)v[0] + v[1] + v[2] + v[3];
+    return t > 0x7fffffff ? 0x7fffffff : (int)t;
 }
 
 extern "C" int pxl_h16_reset_status(void) {
-    if (g_sat_counter) cudaMemset(g_sat_counter, 0, sizeof(int));
+    if (g_sat_counter) cudaMemset(g_sat_counter, 0, 4 * sizeof(int));
     return 0;
 }
 
@@ -81,7 +89,7 @@ extern "C" int pxl_h16_split(const float* x, void* hi, void* lo, int64_t n, floa
     const int64_t n4 = n / 4;
     int blocks = (int)(pxl_cdiv(n4, 256 * 2) < PXL_NUM_SMS * 8 ? pxl_cdiv(n4, 256 * 2) : PXL_NUM_SMS * 8);
     int* sat = pxl_h16_sat_counter();
-    if (slot) h16_split_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)hi, (uint2*)lo, n4, 1.f, slot, target_log2, sat);
+    if (slot) h16_split_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)hi, (uint2*)lo, n4, 1.f, slot, target_log2, sat ? sat + 1 : sat);
     else h16_split_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)hi, (uint2*)lo, n4, scale, nullptr, 0, sat);
     PXL_CHECK_LAUNCH();
     return 0;

@@ -212,6 +212,7 @@ extern "C" int pxl_bn_apply_h16(const float* x, const float* scale, const float*
     const float4 *x4 = (const float4*)x, *s4 = (const float4*)scale, *h4 = (const float4*)shift, *r4 = (const float4*)residual;
     float4* y4 = (float4*)y;
     int* sat = hi ? pxl_h16_sat_counter() : nullptr;
+    if (sat) sat += 2;
 #define PXL_AP_ARGS x4, s4, h4, r4, y4, n4, C / 4, (uint2*)hi, (uint2*)lo, hscale, sat
     if (residual && relu) bn_apply_kernel<true, true><<<blocks, 256, 0, st>>>(PXL_AP_ARGS);
     else if (residual) bn_apply_kernel<true, false><<<blocks, 256, 0, st>>>(PXL_AP_ARGS);
@@ -322,6 +323,7 @@ extern "C" int pxl_bn_finalize_apply_h16(const float* x, const double* sums, dou
     if (!x || !sums || !gamma || !beta || !mean || !invstd || !scale || !shift || (!y && !hi) || rows <= 0 || C <= 0 || (C & 3) || count <= 0)
         return PXL_ERR_BAD_ARG;
     int* sat = hi ? pxl_h16_sat_counter() : nullptr;
+    if (sat) sat += 2;
     const RedLayout L = stream_layout(rows, C);
     dim3 grid(L.rowBlocks, L.colBlocks);
     cudaStream_t st = (cudaStream_t)stream;
@@ -524,6 +526,7 @@ extern "C" int pxl_bn_bwd_dx_h16(const float* x, const float* y, const float* dy
                                  void* dhi, void* dlo, float* slot, int target_log2, void* stream) {
     if ((!dx && !dhi) || (dhi && !slot)) return PXL_ERR_BAD_ARG;
     int* sat = dhi ? pxl_h16_sat_counter() : nullptr;
+    if (sat) sat += 3;
     if (!x || !dy || !mean || !invstd || !gamma || !dsums || rows <= 0 || C <= 0 || (C & 3) || (relu && !y && !(scale && shift))) return PXL_ERR_BAD_ARG;
     const RedLayout L = stream_layout(rows, C);     // the reductions' decomposition without their atomics
     dim3 grid(L.rowBlocks, L.colBlocks);

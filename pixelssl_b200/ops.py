@@ -483,6 +483,13 @@ def h16_status():
     return int(_lib.load().pxl_h16_status())
 
 
+def h16_status_sites():
+    """Saturation events per producer: (split fixed, split dynamic, BN apply, BN backward dx)."""
+    out = (ctypes.c_int * 4)()
+    _lib.load().pxl_h16_status_sites(out)
+    return tuple(int(v) for v in out)
+
+
 def h16_cached(x, scale, want_lo=True):
     """h16_split memoised on the tensor object for one step (a weight used by several launches)."""
     ent = getattr(x, '_pxl_h16', None)

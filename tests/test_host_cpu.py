@@ -495,3 +495,38 @@ def test_pretrained_backbone_url_resolution_and_key_filtered_load(tmp_path, monk
     monkeypatch.setattr(torch.hub, 'load_state_dict_from_url', lambda *a, **k: (_ for _ in ()).throw(OSError('offline')))
     with pytest.raises(BaseException):
         R.ResNet([3, 4, 6, 3], 16, pretrained_url=M.PRETRAINED_BACKBONE_URLS['resnet50'])
+
+
+def test_gpu_input_pipeline_host_tables_and_draws_match_the_oracle():
+    """Host side of the GPU input pipeline (pixelssl_b200/task/sseg/gpu_input.py): Pillow's resampling tables and the
+    reference's random-draw order, against oracle/input_oracle.py (itself pinned bit for bit to Pillow and to the
+    reference's transform classes)."""
+    import random
+    from oracle import input_oracle as I
+    from pixelssl_b200.task.sseg import gpu_input as G
+    for n_in, n_out in [(53, 40), (37, 80), (64, 64), (90, 33), (500, 513), (375, 1026), (333, 257)]:
+        bounds, taps = I._coefficients(n_in, n_out)
+        b, w = G.bilinear_tables(n_in, n_out)
+        assert b.shape == (n_out, 2) and w.shape[0] == n_out
+        for i, ((x0, n), k) in enumerate(zip(bounds, taps)):
+            assert (int(b[i, 0]), int(b[i, 1])) == (x0, n)
+            assert np.array_equal(w[i, :n], k) and not w[i, n:].any()
+        ramp = np.arange(n_in, dtype=np.int64)[None, :].repeat(2, 0)
+        assert np.array_equal(G.nearest_table(n_in, n_out), I.resize_nearest(ramp, n_out, 2)[0])
+    # the draws: composing the oracle's pixel functions with the product's geometry reproduces the oracle's pipeline
+    rs = np.random.RandomState(5)
+    for k, (h, w, base, crop) in enumerate([(37, 53, 40, 33), (64, 41, 40, 33), (50, 50, 24, 40), (33, 90, 60, 33)]):
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        lab = rs.randint(0, 21, (h, w)).astype(np.uint8)
+        random.seed(900 + k)
+        x_ref, y_ref = I.train_prehandle(img, lab, base, crop)
+        random.seed(900 + k)
+        ow, oh, x1, y1, flip = G.draw_train_geometry(h, w, base, crop)
+        a, m = I.resize_bilinear_u8(img, ow, oh), I.resize_nearest(lab, ow, oh)
+        a = np.pad(a, ((0, max(crop - oh, 0)), (0, max(crop - ow, 0)), (0, 0)))
+        m = np.pad(m, ((0, max(crop - oh, 0)), (0, max(crop - ow, 0))))
+        a, m = a[y1:y1 + crop, x1:x1 + crop], m[y1:y1 + crop, x1:x1 + crop]
+        if flip:
+            a, m = a[:, ::-1], m[:, ::-1]
+        x, y = I.normalize_to_chw(a, m)
+        assert np.array_equal(x, x_ref) and np.array_equal(y, y_ref)
