@@ -97,7 +97,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -179,7 +179,7 @@ def ddp_check(world, rank, precision):
     from pixelssl_b200.nn import arena as arena_mod
     from pixelssl_b200.nn.modules import BatchNorm2d
     size = 65
-    prev = ops.get_conv_precision()
+    prev = {v: k for k, v in ops.PRECISION.items()}[ops.get_conv_precision()]
     ops.set_conv_precision(precision)
 
     def cfg(bs, ubs):
@@ -261,20 +261,29 @@ def run_engine(args):
     ddp = ddp_check(world, rank, 'fp32') if (world > 1 and not args.no_ddp_check) else None
     torch.manual_seed(0); random.seed(0); np.random.seed(0)
     make_cfg, lbs, ubs, size, workload = CONFIGS[args.config]
-    a = runner.build_args(make_cfg(), iters_per_epoch=662)
-    import logging
-    logging.getLogger('PixelSSL').setLevel(logging.ERROR)
-    alg = runner.build_algorithm(a)
     nb = 4
     host = synthetic_host_batches(nb, rank, True, lbs, ubs, size)
     dev = [(i.cuda(), l.cuda()) for i, l in host]
-    epoch = [0]
+    st = {'alg': None, 'a': None, 'epoch': 0}
+
+    def fresh_algorithm():
+        """Every timed phase starts from the same freshly initialised models / optimiser state: on random-label
+        synthetic batches the reference algorithm itself drifts upwards in loss within tens of steps (the CPU oracle
+        does the same), so phases run back to back would not time the same regime."""
+        if st['alg'] is not None:
+            st['alg'] = None
+            torch.cuda.empty_cache()
+        torch.manual_seed(0); random.seed(0); np.random.seed(0)
+        st['a'] = runner.build_args(make_cfg(), iters_per_epoch=662)
+        st['alg'] = runner.build_algorithm(st['a'])
+        st['epoch'] = 0
 
     def run_steps(batches, count, api):
         """``count`` iterations through the algorithm's own loop (``_train`` / the public ``train``)."""
+        alg = st['alg']
         loader = [((batches[i % nb][0],), (batches[i % nb][1],)) for i in range(count)]
-        (alg.train if api else alg._train)(loader, epoch[0])
-        epoch[0] += 1
+        (alg.train if api else alg._train)(loader, st['epoch'])
+        st['epoch'] += 1
 
     def barrier():
         if world > 1:
@@ -287,34 +296,43 @@ def run_engine(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    def timed(batches, api=False):
+    losses = {}
+    clock_rec = []
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    def first_loss():
+        vals = st['alg'].meters.values()
+        return float(next(v for k, v in sorted(vals.items()) if 'task_loss' in k))
+
+    def timed(batches, api=False, tag=None):
+        fresh_algorithm()
+        st['a'].log_freq = 1 if api else 10 ** 9   # api: every step's losses are read back for its log line
         run_steps(batches, args.warmup, api)
         barrier()
+        if tag == 'value' and sampler:
+            sampler.start()                   # clocks / throttle reasons DURING the timed region
         ops.reset_launch_count()
         ops.kernel_timer_start('pxl_mse_consistency')
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         run_steps(batches, args.steps, api)
-        if api:
-            vals = alg.meters.values()
-            float(next(v for k, v in vals.items() if 'loss' in k))        # the last step's loss is on the host
+        last = first_loss() if api else None                             # the last step's loss is on the host
         e1.record()
         barrier()
+        if tag == 'value' and sampler:
+            clock_rec.append(sampler.stop())
         ms = e0.elapsed_time(e1)
         ktimes = ops.kernel_timer_stop('pxl_mse_consistency')
+        if tag:
+            losses[tag] = {'task_loss_after_%d_steps' % (args.warmup + args.steps): last if last is not None else first_loss()}
         return max_over_ranks(ms), ktimes, ops.launch_count()
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
     sat_log = {}
-    ms_dev, ktimes, launches = timed(dev)
+    ms_dev, ktimes, launches = timed(dev, tag='value')
     sat_log['after_value'] = ops.h16_status_sites()
-    clocks = sampler.stop() if sampler else None
-    a.log_freq = 1                    # every step's losses are read back for its log line (one step late, see ssl_base)
-    ms_e2e, _, _ = timed(host, api=True)
+    clocks = clock_rec[0] if clock_rec else None
+    ms_e2e, _, _ = timed(host, api=True, tag='e2e')
     sat_log['after_e2e'] = ops.h16_status_sites()
-    a.log_freq = 10 ** 9
 
     # instrumented pass: CUDA events around every convolution launch (outside the timed region on purpose)
     h16 = args.precision in ('f16x3', 'f16')
@@ -322,6 +340,9 @@ def run_engine(args):
     wg_name = 'pxl_conv_wgrad_h16_launch' if h16 else 'pxl_conv_wgrad_tc_launch'
     conv_rec = wg_rec = []
     if args.precision != 'fp32':
+        fresh_algorithm()
+        st['a'].log_freq = 10 ** 9
+        run_steps(dev, 1, False)
         barrier()
         ops.kernel_timer_start(fwd_name); ops.kernel_timer_start(wg_name)
         run_steps(dev, min(args.steps, 3), False)
@@ -336,7 +357,7 @@ def run_engine(args):
         # tolerance against the CPU reference
         ops.set_conv_precision(alt_name)
         sat_log['before_alt'] = ops.h16_status_sites()
-        ms_alt, _, _ = timed(dev)
+        ms_alt, _, _ = timed(dev, tag='alt')
         ops.set_conv_precision(args.precision)
         alt = {'conv_precision': alt_name, 'value': (lbs + ubs) * world * args.steps / (ms_alt / 1e3), 'unit': 'images/s',
                'ms_per_step': ms_alt / args.steps}
@@ -390,6 +411,7 @@ def run_engine(args):
         'roofline': roof if roof else roof_hbm,
         'roofline_wgrad': roof_wg,
         'roofline_hbm': roof_hbm,
+        'losses': losses,
         'pipeline_status': {'tcgen05_watchdog': status[0], 'fp16_pair_saturations': status[1],
                             'saturations_by_site_split_fixed_dyn_bnapply_bndx': ops.h16_status_sites(), 'phases': sat_log},
     }
@@ -404,7 +426,8 @@ def run_engine(args):
         out['ddp_check'] = ddp
     if rank == 0:
         if world == 1 and args.config == 'mt':
-            del alg, dev
+            st['alg'] = None
+            del dev
             torch.cuda.empty_cache()
             if not args.no_gpu_torch_baseline:
                 r = stock_torch_gpu_reference(steps=50, warmup=10, lbs=LBS, ubs=UBS)

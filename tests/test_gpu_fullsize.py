@@ -49,6 +49,42 @@ def test_c2_mean_teacher_full_size(ops):
     assert 1.0 < v['s_task_loss'] < 20.0         # ln(21) = 3.04 plus random-init spread
 
 
+def test_c2_full_size_step_matches_the_cpu_oracle(ops):
+    """Parity at the benchmark's image size (513x513, the tile-edge cases 513 -> 257 -> 129 -> 65 -> 33 of every
+    kernel): one Mean-Teacher step at batch 2+2 on the fp16-pair tensor-core path against the CPU oracle (the
+    restatement of ssl_mt.py:124-224 pinned to the reference at 97x97 and 257x257).  Losses within the north_star's
+    1e-3; per-tensor gradient energies within the reference's own fp32 noise level measured at the smaller sizes
+    (median 1.5e-3, tail 3e-2; tests/test_gpu_model.py) times a small factor."""
+    from pixelssl_b200 import runner
+    size, lbs, ubs = 513, 2, 2
+    cfg = dict(BASE, ssl_algorithm='ssl_mt', cons_for_labeled=False, cons_scale=1.0, cons_rampup_epochs=1, ema_decay=0.99,
+               batch_size=lbs + ubs, unlabeled_batch_size=ubs, epochs=2)
+    alg = runner.build_algorithm(runner.build_args(cfg, iters_per_epoch=5))
+    s0 = O.randomize_bn_affine(O.init_deeplabv2(11, cls_bias_std=0.01), 12)
+    t0 = O.randomize_bn_affine(O.init_deeplabv2(21, cls_bias_std=0.01), 22)
+    alg.s_model.load_state_dict({'module.model.' + k: v for k, v in s0.items()})
+    alg.t_model.load_state_dict({'module.model.' + k: v for k, v in t0.items()})
+    img, lab = O.synthetic_batch(100, lbs + ubs, lbs, size, size)
+    alg._train([((img,), (lab,))], 0)
+    torch.cuda.synchronize()
+    assert ops.conv_tc_status() == 0 and ops.h16_status() == 0
+    mt = O.MTOracle(s0, t0, lr=0.00025, momentum=0.9, weight_decay=0.0005, max_iters=10, cons_scale=1.0,
+                    rampup_steps=1, ema_decay=0.99, cons_for_labeled=False)
+    ref = mt.step(img, lab, lbs)
+    for key in ('s_task_loss', 't_task_loss', 'cons_loss'):
+        got, want = float(alg.meters[key].val), float(ref[key])
+        assert abs(got - want) <= 1e-3 * max(abs(want), 1e-2), (key, got, want)
+    names = mt.names
+    sp = dict(alg.s_model.module.model.named_parameters())
+    e = np.array([abs(float((sp[n].grad.double() ** 2).sum()) - float((ref['grads'][n].double() ** 2).sum())) /
+                  max(float((ref['grads'][n].double() ** 2).sum()), 1e-300) for n in names])
+    print('513x513 step vs CPU oracle: grad energy rel median %.2e p95 %.2e max %.2e (%s)' % (
+        np.median(e), np.percentile(e, 95), e.max(), names[int(e.argmax())]))
+    assert np.median(e) <= 1e-2 and np.percentile(e, 95) <= 5e-2 and e.max() <= 2e-1
+    del alg
+    torch.cuda.empty_cache()
+
+
 def test_c3_cutmix_full_size(ops):
     v = _step(ops, {'ssl_algorithm': 'ssl_cutmix', 'cons_scale': 20.0, 'cons_rampup_epochs': 0, 'cons_threshold': 0.97,
                     'ema_decay': 0.99, 'mask_prop_range': (0.5, 0.5)}, 8, 8, 513)
