@@ -211,25 +211,32 @@ def ddp_check(world, rank, precision):
     equal = all(torch.equal(allsums[0], t) for t in allsums)
     res = {'ranks_hold_identical_params_and_bn_buffers': bool(equal)}
     if rank == 0:
-        arena_mod.DISTRIBUTED = False
-        try:
-            big = runner.build_algorithm(runner.build_args(cfg(2 * world, world), iters_per_epoch=5))
-        finally:
-            arena_mod.DISTRIBUTED = True
-        big.s_model.load_state_dict(state)
-        big.t_model.load_state_dict(state)
-        for m in list(big.s_model.modules()) + list(big.t_model.modules()):
-            if isinstance(m, BatchNorm2d):
-                m.multi_replica_formula = True       # batchnorm.py:125: the multi-replica path clamps var instead of adding eps
-        big._train([((img.cuda(),), (lab.cuda(),))], 0)
-        g1, p1, b1 = flat(big)
+        def big_batch(perm):
+            arena_mod.DISTRIBUTED = False
+            try:
+                big = runner.build_algorithm(runner.build_args(cfg(2 * world, world), iters_per_epoch=5))
+            finally:
+                arena_mod.DISTRIBUTED = True
+            big.s_model.load_state_dict(state)
+            big.t_model.load_state_dict(state)
+            for m in list(big.s_model.modules()) + list(big.t_model.modules()):
+                if isinstance(m, BatchNorm2d):
+                    m.multi_replica_formula = True       # batchnorm.py:125: the multi-replica path clamps var instead of adding eps
+            big._train([((img[perm].cuda(),), (lab[perm].cuda(),))], 0)
+            return flat(big)
+        ident = list(range(2 * world))
+        g1, p1, b1 = big_batch(ident)
+        # yardstick: the SAME big batch with its labeled and its unlabeled samples reversed - identical loss, different
+        # order of the fp32 partial sums; what a data-parallel run may differ by (tests/test_gpu_ddp.py)
+        gp, pp, bp = big_batch(ident[:world][::-1] + ident[world:][::-1])
         rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+        noise = {'grad': rel(gp, g1), 'param': rel(pp, p1), 'bn_buffer': rel(bp, b1)}
         res.update({'size': size, 'per_rank_batch': '1 labeled + 1 unlabeled', 'conv_precision': precision,
                     'grad_max_rel_vs_big_batch': rel(gd, g1), 'param_max_rel_vs_big_batch': rel(pd, p1),
-                    'bn_buffer_max_rel_vs_big_batch': rel(bd, b1)})
-        res['ok'] = bool(equal and res['bn_buffer_max_rel_vs_big_batch'] <= 1e-4 and res['param_max_rel_vs_big_batch'] <= 5e-4
-                         and res['grad_max_rel_vs_big_batch'] <= 5e-2)
-        del big
+                    'bn_buffer_max_rel_vs_big_batch': rel(bd, b1), 'batch_permutation_noise_of_the_big_batch': noise})
+        res['ok'] = bool(equal and res['grad_max_rel_vs_big_batch'] <= 3 * noise['grad'] + 1e-3
+                         and res['param_max_rel_vs_big_batch'] <= 3 * noise['param'] + 1e-5
+                         and res['bn_buffer_max_rel_vs_big_batch'] <= 3 * noise['bn_buffer'] + 1e-5)
     dist.barrier()
     del alg
     torch.cuda.empty_cache()

@@ -164,6 +164,14 @@ __device__ __forceinline__ void tma_store_4d(const void* src, const CUtensorMap*
         ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// TMA reduce-add: global[box] += shared[box] (fp32), performed by the L2 - the split-K accumulation of the wgrad
+// kernel without one RED instruction per element
+__device__ __forceinline__ void tma_reduce_add_3d(const void* src, const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+        ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_commit_and_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1384,6 +1392,7 @@ struct WgParams {
     int f16;           // fp16 operands (kind::f16): 64-channel slabs, 16 pixel rows per MMA, plain SWIZZLE_128B
     int slab_ch;       // channels per 128-byte slab row: 32 (tf32) or 64 (fp16)
     float out_scale;   // the tile is multiplied by this (and by *oscale_ptr) before it is added into dW
+    int tma_red;       // epilogue: stage 32-column slabs in the drained ring and add them into dW with TMA reduce
     int tiles_ci, ktiles_per_cta, ktiles_total;
     short dy[PXL_MAX_TAPS], dx[PXL_MAX_TAPS];
 };
@@ -1418,6 +1427,7 @@ __device__ __forceinline__ uint64_t mnmajor_sw128_f16_desc(uint32_t smem_addr, u
 __global__ void __launch_bounds__(320, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapDyLo,
                      const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapXLo,
+                     const __grid_constant__ CUtensorMap mapDw,
                      const WgParams p, float* __restrict__ dw, int* __restrict__ err_flag,
                      const float* __restrict__ oscale_ptr) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1565,7 +1575,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
                 const int used = iters < p.nacc ? iters : p.nacc;
                 const float osc = p.out_scale * (oscale_ptr ? __ldg(oscale_ptr) : 1.f);
                 float* drow = dw + ((int64_t)co * p.ntaps + tap) * p.Cin;
+                const int r = q * 32 + lane;
+                const int et = threadIdx.x - 64;
+                uint32_t sc = 0;
                 for (int j = 0; j < p.BN; j += 32) {
+                    if (p.tma_red && ci0 + j >= p.Cin) break;          // uniform
                     float v[32];
                     tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)j, v);
                     for (int a = 1; a < used; ++a) {
@@ -1574,6 +1588,25 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
 #pragma unroll
                         for (int c = 0; c < 32; ++c) v[c] += u[c];
                     }
+                    if (p.tma_red) {
+                        // the operand ring is drained (acc_bar): two 16 KB slabs of it stage the tile, 128 rows (co) x
+                        // 32 floats (ci) in the 128B-swizzled layout, and the TMA unit adds them into dW
+                        const uint32_t b = sc & 1u;
+                        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        float4* dst = reinterpret_cast<float4*>(smem + (size_t)b * 16384 + (size_t)r * 128);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            dst[c ^ (r & 7)] = make_float4(v[4 * c] * osc, v[4 * c + 1] * osc, v[4 * c + 2] * osc, v[4 * c + 3] * osc);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (et == 0) {
+                            tma_reduce_add_3d(smem + (size_t)b * 16384, &mapDw, ci0 + j, tap, co0);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        ++sc;
+                        continue;
+                    }
                     if (co >= p.Cout) continue;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
@@ -1581,6 +1614,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
                         if (ci < p.Cin) atomicAdd(drow + ci, v[c] * osc);
                     }
                 }
+                if (p.tma_red && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             }
         }
     }
@@ -1741,8 +1775,23 @@ static int conv_wgrad_tc_core(const pxl_conv_geom* g, const int* taps, const voi
         attr = true;
     }
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    // dW [Cout][taps][Cin] as a 3-D tensor (Cin, taps, Cout): box {32, 1, 128}, 128-byte swizzle, fp32 reduce-add target
+    static int cfg_wg_red = -1;
+    if (cfg_wg_red < 0) { const char* e = getenv("PXL_WG_TMA_REDUCE"); cfg_wg_red = e ? atoi(e) : 1; }
+    CUtensorMap mDw = mDy;
+    p.tma_red = 0;
+    if (cfg_wg_red && (g->Cin % 4) == 0 && ((uintptr_t)dw % 16) == 0 && (size_t)p.stages * stage_bytes >= 32768) {
+        EncodeTiledFn enc = get_encode();
+        cuuint64_t dims[3] = {(cuuint64_t)g->Cin, (cuuint64_t)g->ntaps, (cuuint64_t)g->Cout};
+        cuuint64_t strides[2] = {(cuuint64_t)g->Cin * 4, (cuuint64_t)g->ntaps * g->Cin * 4};
+        cuuint32_t box[3] = {32, 1, 128};
+        cuuint32_t es[3] = {1, 1, 1};
+        if (enc && enc(&mDw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)dw, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            p.tma_red = 1;
+    }
     dim3 grid((unsigned)(tiles_co * p.tiles_ci), (unsigned)g->ntaps, (unsigned)split);
-    conv_wgrad_tc_kernel<<<grid, inkernel ? 320 : 192, smem, (cudaStream_t)stream>>>(mDy, mDyLo, mX, mXLo, p, dw, g_err_flag, oscale_ptr);
+    conv_wgrad_tc_kernel<<<grid, inkernel ? 320 : 192, smem, (cudaStream_t)stream>>>(mDy, mDyLo, mX, mXLo, mDw, p, dw, g_err_flag, oscale_ptr);
     PXL_CHECK_LAUNCH();
     return 0;
 }
