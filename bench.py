@@ -154,7 +154,7 @@ def synthetic_host_batches(count, rank, pin, lbs=None, ubs=None, size=None):
 
 def _roofline_from(records, peak, src, kernel, bound='tensor', traffic=None):
     """records: [(ms, flop)] of one entry point's launches -> roofline block (TFLOP/s against the measured 16-bit peak)."""
-    records = [(ms, fl) for ms, fl in records if fl]
+    records = [(ms, fl[0] if isinstance(fl, tuple) else fl) for ms, fl in records if fl]
     if not records:
         return None
     ms, fl = sum(r[0] for r in records), sum(r[1] for r in records)

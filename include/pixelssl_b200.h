@@ -381,6 +381,21 @@ int pxl_peer_allreduce_bn(double* sums, int n, void* const* mailboxes, int rank,
                           void* stream);
 int pxl_peer_status(void);
 
+/* stem im2col written directly as the fp16 pair [pixels][192] of the kind::f16 path (hi, lo nullable; value*scale) */
+int pxl_stem_im2col_h16(const float* img_planar, void* hi, void* lo, float scale, int N, int H, int W, int OH, int OW,
+                        void* stream);
+
+/* ---- ASPP head as one GEMM + gather (csrc/aspp_gather.cu) ----------------------------------------------------
+ * Classifier_Module.forward (task/sseg/module/deeplab_v2.py:81-85) = sum of four dilated 3x3 convolutions 2048 -> C.
+ * On the fp16-pair path the channel contraction runs first as one 1x1 GEMM with N = ntaps*C outputs
+ * (Z[p,t,co] = W_t x[p]); pxl_aspp_gather adds the taps: out[p,co] = bias[co] + sum_t Z[p + off_t, t, co] (zero
+ * padding).  Backward: pxl_aspp_scatter_h16 builds the fp16 pair of dZ[q,t,co] = dy[q - off_t, co] (scale from the
+ * absmax in slot[2], like pxl_h16_split) for the dgrad / wgrad GEMMs. */
+int pxl_aspp_gather(const float* Z, const float* bias, float* out, int N, int H, int W, int C, int ldz, int ldo,
+                    const int* taps_dydx_host, int ntaps, void* stream);
+int pxl_aspp_scatter_h16(const float* dy, void* hi, void* lo, float* slot, int target_log2, int N, int H, int W, int C,
+                         int ldy, int ldz, const int* taps_dydx_host, int ntaps, void* stream);
+
 /* ---- input pipeline on the GPU (csrc/input_pipeline.cu) ------------------------------------------------------
  * Replaces the per-sample PIL / numpy work of PascalVocDataset._train_prehandle / _val_prehandle
  * (task/sseg/data.py:90-123): RandomScaleCrop (:223-256) = Pillow BILINEAR resize of the 8-bit image (22-bit

@@ -631,3 +631,54 @@ extern "C" int pxl_stem_im2col(const float* img, float* cols, int N, int H, int 
     PXL_CHECK_LAUNCH();
     return 0;
 }
+
+// fp16-pair variant for the kind::f16 tensor-core path (csrc/h16_prep.cu): the unfolded stem matrix is written directly
+// as hi / lo planes [pixels][192] (147 taps*channels + 45 zero lanes: K must be a multiple of the 64-element operand
+// row), value * scale = hi + lo.  768 B per output pixel instead of 640 B of fp32, and no separate split pass.
+#include <cuda_fp16.h>
+#define ST_KH 192
+__global__ void __launch_bounds__(256)
+stem_im2col_h16_kernel(const float* __restrict__ img, uint2* __restrict__ hi, uint2* __restrict__ lo, float scale,
+                       int N, int H, int W, int OH, int OW, int* __restrict__ sat) {
+    const int64_t total4 = (int64_t)N * OH * OW * (ST_KH / 4);
+    bool clipped = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k4 = (int)(i % (ST_KH / 4));
+        const int64_t pix = i / (ST_KH / 4);
+        const int ox = (int)(pix % OW), oy = (int)((pix / OW) % OH), n = (int)(pix / ((int64_t)OW * OH));
+        unsigned short h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k4 * 4 + e;
+            float x = 0.f;
+            if (k < ST_K) {
+                const int c = k % 3, rs = k / 3, r = rs / 7, sx = rs - r * 7;
+                const int iy = oy * 2 - 3 + r, ix = ox * 2 - 3 + sx;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) x = __ldg(img + ((int64_t)(n * 3 + c) * H + iy) * W + ix);
+            }
+            const float t = x * scale;
+            const float cl = fminf(fmaxf(t, -65504.f), 65504.f);
+            clipped |= (cl != t) && (t == t);
+            const __half hh = __float2half_rn(cl);
+            h[e] = __half_as_ushort(hh);
+            l[e] = __half_as_ushort(__float2half_rn(cl - __half2float(hh)));
+        }
+        hi[i] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+        if (lo) lo[i] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+    }
+    if (clipped && sat) atomicAdd(sat, 1);
+}
+
+extern "C" int* pxl_h16_sat_counter(void);
+
+extern "C" int pxl_stem_im2col_h16(const float* img, void* hi, void* lo, float scale, int N, int H, int W, int OH, int OW,
+                                   void* stream) {
+    if (!img || !hi || !(scale > 0.f) || N <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0) return PXL_ERR_BAD_ARG;
+    const int64_t total4 = (int64_t)N * OH * OW * (ST_KH / 4);
+    int64_t blocks = pxl_cdiv(total4, 256 * 4);
+    if (blocks > PXL_NUM_SMS * 16) blocks = PXL_NUM_SMS * 16;
+    stem_im2col_h16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(img, (uint2*)hi, (uint2*)lo, scale, N, H, W, OH, OW,
+                                                                              pxl_h16_sat_counter());
+    PXL_CHECK_LAUNCH();
+    return 0;
+}

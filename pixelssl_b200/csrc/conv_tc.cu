@@ -1649,7 +1649,11 @@ static void pick_ktile(int OH, int OW, bool flat, int maxrows, int& BW, int& BH,
         if (bh > 256) bh = 256;
         const int alloc = (bw * bh + unit - 1) / unit * unit;
         const int64_t tiles = (int64_t)((OW + bw - 1) / bw) * ((OH + bh - 1) / bh);
-        const double eff = (double)OH * OW / ((double)tiles * alloc);
+        // useful rows per allocated row, discounted for narrow boxes: a TMA box is fetched as bh separate runs of
+        // bw pixels, and short runs stream poorly (PXL_WG_WIDE_BIAS, measured with tools/bench_conv.py)
+        static double bias = -1.0;
+        if (bias < 0.0) { const char* e = getenv("PXL_WG_WIDE_BIAS"); bias = e ? atof(e) : 0.0; }
+        const double eff = (double)OH * OW / ((double)tiles * alloc) * (1.0 - bias / (bias + bw));
         if (eff > best + 1e-9) { best = eff; BW = bw; BH = bh; }
     }
 }

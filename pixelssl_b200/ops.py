@@ -542,7 +542,8 @@ def _stride2_dgrad_classes(taps, ntaps):
 def _tc_launch(geom, taps, ext, x_parts, w_parts, bias, out):
     _timed_call('pxl_conv_tc_launch_ex', ctypes.byref(geom), _ctaps(taps), ctypes.byref(ext) if ext is not None else None,
                 _p(x_parts[0]), _p(x_parts[1]), _p(w_parts[0]), _p(w_parts[1]), _p(bias), _p(out), _stream(),
-                meta=2.0 * geom.N * geom.OH * geom.OW * geom.Cin * geom.Cout * geom.ntaps)
+                meta=(2.0 * geom.N * geom.OH * geom.OW * geom.Cin * geom.Cout * geom.ntaps,
+                      'fwd/dgrad(tf32) N%d %dx%d Cin%d Cout%d taps%d' % (geom.N, geom.OH, geom.OW, geom.Cin, geom.Cout, geom.ntaps)))
 
 
 def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, out=None, precision=None, bn_stats=None):
@@ -578,7 +579,8 @@ def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div,
             ext.out_scale, ext.out_scale_dev = oscale, (odev.data_ptr() if odev is not None else None)
             _timed_call('pxl_conv_h16_launch', ctypes.byref(geom), _ctaps(tp), ctypes.byref(ext), _p(xh.hi), _p(xh.lo),
                         _p(wh.hi), _p(wh.lo if want_lo else None), _p(bias), _p(out), _stream(),
-                        meta=2.0 * geom.N * geom.OH * geom.OW * geom.Cin * min(geom.Cout, Cout) * geom.ntaps)
+                        meta=(2.0 * geom.N * geom.OH * geom.OW * geom.Cin * min(geom.Cout, Cout) * geom.ntaps,
+                              'fwd/dgrad N%d %dx%d Cin%d Cout%d taps%d mul%d' % (geom.N, geom.OH, geom.OW, geom.Cin, geom.Cout, geom.ntaps, geom.mul)))
         if div == 1:
             ext = ConvTcExt(0, None, 0, 0, 0, 0, 0, None)
             if bn_stats is not None:
@@ -656,7 +658,7 @@ def conv_wgrad_raw(x, dy, dw, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, p
         geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
         _timed_call('pxl_conv_wgrad_h16_launch', ctypes.byref(geom), _ctaps(taps), _p(xh.hi), _p(xh.lo), _p(dh.hi), _p(dh.lo),
                     _p(dw), float(fx * fd), _p(pd if pd is not None else px), _stream(),
-                    meta=2.0 * N * OH * OW * Cin * Cout * ntaps)
+                    meta=(2.0 * N * OH * OW * Cin * Cout * ntaps, 'wgrad N%d %dx%d Cin%d Cout%d taps%d mul%d' % (N, OH, OW, Cin, Cout, ntaps, mul)))
         return dw
     if prec != 0 and div == 1 and mul in _WGRAD_TC_STRIDES and Cin % 32 == 0 and ldo % 32 == 0:
         geom = ConvGeom(N, H, W, Cin, OH, OW, Cout, ldo, mul, div, ntaps, prec)
@@ -667,10 +669,10 @@ def conv_wgrad_raw(x, dy, dw, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, p
             x_hi, x_lo = x if isinstance(x, tuple) else (x, None)     # raw operands: split inside the kernel
             d_hi, d_lo = dy if isinstance(dy, tuple) else (dy, None)
             _timed_call('pxl_conv_wgrad_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x_hi), _p(x_lo), _p(d_hi), _p(d_lo),
-                        _p(dw), _stream(), meta=2.0 * N * OH * OW * Cin * Cout * ntaps)
+                        _p(dw), _stream(), meta=(2.0 * N * OH * OW * Cin * Cout * ntaps, 'wgrad(tf32) N%d %dx%d Cin%d Cout%d taps%d' % (N, OH, OW, Cin, Cout, ntaps)))
         else:
             _timed_call('pxl_conv_wgrad_tc_launch', ctypes.byref(geom), _ctaps(taps), _p(x), _p(None), _p(dy), _p(None),
-                        _p(dw), _stream(), meta=2.0 * N * OH * OW * Cin * Cout * ntaps)
+                        _p(dw), _stream(), meta=(2.0 * N * OH * OW * Cin * Cout * ntaps, 'wgrad(tf32) N%d %dx%d Cin%d Cout%d taps%d' % (N, OH, OW, Cin, Cout, ntaps)))
         return dw
     if isinstance(x, tuple):
         x = x[0] + x[1]
@@ -873,7 +875,75 @@ class _Aspp(torch.autograd.Function):
         return (dx, None) + tuple(dws) + tuple(db for _ in range(nb))
 
 
+class _AsppGemm(torch.autograd.Function):
+    """Classifier_Module.forward (deeplab_v2.py:81-85) on the fp16-pair tensor-core path: the channel contraction of
+    all taps as ONE 1x1 GEMM (N = taps*C, the latent is read once), then a gather that adds the taps
+    (csrc/aspp_gather.cu).  Backward: dZ = scatter(dY) as an fp16 pair, dX = dZ * W'^T and dW' = dZ^T * X are plain
+    1x1 dgrad / wgrad GEMMs with K = taps*C and N = taps*C.  Same output layout as _Aspp."""
+    LDO = 32
+
+    @staticmethod
+    def forward(ctx, x, dilations, *wb):
+        nb = len(dilations)
+        weights, biases = wb[:nb], wb[nb:]
+        N, Cin, H, W = x.shape
+        C = weights[0].shape[0]
+        prec = _conv_precision
+        want_lo = prec == 3
+        ldo = max(_AsppGemm.LDO, (C + 3) // 4 * 4)
+        taps = []
+        for d in dilations:
+            taps += _taps(3, 3, d, d)
+        T = 9 * nb
+        ldz = (T * C + 63) // 64 * 64                      # 36*21 = 756 -> 768
+        # W' [ldz][Cin]: row t*C + co = W_t[co, :]
+        wq = torch.zeros((ldz, Cin), dtype=torch.float32, device=x.device)
+        for i, wgt in enumerate(weights):
+            _chk(wgt, 'aspp weight', cl=True)
+            wq[9 * i * C:9 * (i + 1) * C] = wgt.detach().permute(2, 3, 0, 1).reshape(9 * C, Cin)    # (kh,kw,co,ci)
+        wh = h16_split(wq, H16_W_SCALE, want_lo)
+        bsum = biases[0]
+        for b in biases[1:]:
+            bsum = bsum + b
+        xh = _pair_of(x, want_lo)
+        z = conv_raw(xh, wh, None, [0, 0], N, H, W, Cin, H, W, ldz, ldz, 1, 1, precision=prec)
+        out = torch.empty((N, ldo, H, W), dtype=torch.float32, device=x.device, memory_format=CL)
+        call('pxl_aspp_gather', _p(z), _p(bsum.detach().contiguous()), _p(out), N, H, W, C, ldz, ldo, _ctaps(taps), T, _stream())
+        ctx.save_for_backward(xh.buf, wq)
+        ctx.meta = (taps, N, H, W, Cin, C, ldo, ldz, nb, xh.scale, want_lo, prec)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        xbuf, wq = ctx.saved_tensors
+        taps, N, H, W, Cin, C, ldo, ldz, nb, xscale, want_lo, prec = ctx.meta
+        dy = as_cl(dy)          # [N, ldo, H, W]; lanes >= C are zero (bilinear backward zero-fills)
+        dev = dy.device
+        T = 9 * nb
+        n = N * H * W * ldz
+        slot = _scale_slot(dev)
+        call('pxl_h16_absmax', _p(dy), dy.numel(), _p(slot), _stream())
+        dz = torch.empty((2, n), dtype=torch.float16, device=dev)
+        call('pxl_aspp_scatter_h16', _p(dy), _p(dz[0]), _p(dz[1] if want_lo else None), _p(slot), H16_GRAD_TARGET_LOG2,
+             N, H, W, C, ldo, ldz, _ctaps(taps), T, _stream())
+        dzh = H16(dz, n, None, slot, want_lo)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wt = h16_split(wq.t().contiguous(), H16_W_SCALE, want_lo)            # [Cin][ldz]
+            dx = conv_raw(dzh, wt, None, [0, 0], N, H, W, ldz, H, W, Cin, Cin, 1, 1, precision=prec)
+        dwq = torch.zeros((ldz, Cin), dtype=torch.float32, device=dev)
+        conv_wgrad_raw(H16(xbuf, xbuf.shape[1], xscale, None, want_lo), dzh, dwq, [0, 0], N, H, W, Cin, H, W, ldz, ldz, 1, 1,
+                       precision=prec)
+        db = torch.empty(C, dtype=torch.float32, device=dev)
+        call('pxl_bias_grad', _p(dy), N * H * W, C, ldo, _p(db), 0, _stream())
+        g = dwq[:T * C].view(nb, 3, 3, C, Cin)                                   # (branch, kh, kw, co, ci)
+        dws = [g[i].permute(2, 3, 0, 1) for i in range(nb)]                      # logical [C, Cin, 3, 3], CL strides
+        return (dx, None) + tuple(dws) + tuple(db for _ in range(nb))
+
+
 def aspp(x, weights, biases, dilations=(6, 12, 18, 24)):
+    if _conv_precision >= 3 and x.shape[1] % 64 == 0:
+        return _AsppGemm.apply(x, tuple(dilations), *(tuple(weights) + tuple(biases)))
     return _Aspp.apply(x, tuple(dilations), *(tuple(weights) + tuple(biases)))
 
 
@@ -898,6 +968,21 @@ class _Stem(torch.autograd.Function):
             call('pxl_stem_conv7x7s2', _p(img), _p(weight), _p(out), N, H, W, OH, OW, _stream())
             ctx.save_for_backward(img)
             return out
+        if prec >= 3:
+            # fp16-pair path: the unfolded matrix is written directly as the hi / lo planes [pixels][192]
+            want_lo = prec == 3
+            n = N * OH * OW * 192
+            buf = torch.empty((2, n), dtype=torch.float16, device=img.device)
+            call('pxl_stem_im2col_h16', _p(img), _p(buf[0]), _p(buf[1] if want_lo else None), float(H16_ACT_SCALE),
+                 N, H, W, OH, OW, _stream())
+            colsh = H16(buf, n, H16_ACT_SCALE, None, want_lo)
+            wp = torch.zeros((64, 192), dtype=torch.float32, device=img.device)
+            wp[:, :147] = weight.detach().permute(0, 2, 3, 1).reshape(64, 147)
+            conv_raw(colsh, h16_split(wp, H16_W_SCALE, want_lo), None, [0, 0], N, OH, OW, 192, OH, OW, 64, 64, 1, 1, out=out,
+                     precision=prec, bn_stats=sums)
+            ctx.save_for_backward(buf if ctx.needs_input_grad[1] else None)
+            ctx.h16 = want_lo
+            return out
         cols = torch.empty((N, 160, OH, OW), dtype=torch.float32, device=img.device, memory_format=CL)
         call('pxl_stem_im2col', _p(img), _p(cols), N, H, W, OH, OW, _stream())
         wp = torch.zeros((64, 160), dtype=torch.float32, device=img.device)
@@ -914,6 +999,12 @@ class _Stem(torch.autograd.Function):
         if prec == 0:
             dw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=dy.device, memory_format=CL).zero_()
             call('pxl_stem_conv7x7s2_wgrad', _p(saved), _p(dy), _p(dw), N, H, W, OH, OW, _stream())
+            return None, dw, None
+        if prec >= 3:
+            dwp = torch.zeros((64, 192), dtype=torch.float32, device=dy.device)
+            conv_wgrad_raw(H16(saved, saved.shape[1], H16_ACT_SCALE, None, ctx.h16), dy, dwp, [0, 0], N, OH, OW, 192, OH, OW, 64, 64,
+                           1, 1, precision=prec)
+            dw = dwp[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2)
             return None, dw, None
         dwp = torch.zeros((64, 160), dtype=torch.float32, device=dy.device)
         conv_wgrad_raw(saved, dy, dwp, [0, 0], N, OH, OW, 160, OH, OW, 64, 64, 1, 1, precision=prec)
