@@ -122,7 +122,9 @@ def test_flaw_detector_forward_backward(ops):
         assert e <= 2e-2, n
     for n, b in fd.named_buffers():
         if 'num_batches' not in n:
-            assert rel(b, stc[n]) <= 1e-5, n
+            # running statistics follow the forward activations: fp32-exact on the FFMA path, the tensor-core modes'
+            # ~2e-5 forward error on the K = 8192 reductions otherwise
+            assert rel(b, stc[n]) <= (1e-5 if ops.get_conv_precision() == 0 else 2e-4), (n, rel(b, stc[n]))
 
 
 def test_gct_step_golden(ops):
