@@ -396,6 +396,12 @@ int pxl_aspp_gather(const float* Z, const float* bias, float* out, int N, int H,
 int pxl_aspp_scatter_h16(const float* dy, void* hi, void* lo, float* slot, int target_log2, int N, int H, int W, int C,
                          int ldy, int ldz, const int* taps_dydx_host, int ntaps, void* stream);
 
+/* ---- S4L (pixelssl/ssl_algorithm/ssl_s4l.py) --------------------------------------------------------------
+ * SSLS4L._batch_prehandle (:296-350): out [2*bs,C,H,W] = the batch followed by its rotated copies
+ * (_rotate_tensor :352-360, angle in {1,2,3} quarter turns per sample; angles = DEVICE int32 [bs]). */
+int pxl_s4l_rotate_batch(const float* in, float* out, const int* angles_dev, int bs, int C, int H, int W,
+                         int any_quarter_turn, void* stream);
+
 /* ---- input pipeline on the GPU (csrc/input_pipeline.cu) ------------------------------------------------------
  * Replaces the per-sample PIL / numpy work of PascalVocDataset._train_prehandle / _val_prehandle
  * (task/sseg/data.py:90-123): RandomScaleCrop (:223-256) = Pillow BILINEAR resize of the 8-bit image (22-bit

@@ -324,6 +324,43 @@ def golden_adv(pixelssl, sseg_proxy, size=65):
     print('adv golden:', {k: rec[k] for k in rec if 'loss' in k})
 
 
+def golden_s4l(pixelssl, sseg_proxy, size=65):
+    """One SSLS4L._train step (ssl_s4l.py:113-200): lbs 2 + ubs 2 doubled by the rotated copies."""
+    from oracle import s4l_oracle as S
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    args = make_args(pixelssl, sseg_proxy, 'ssl_s4l', {'rotated_sup_scale': 0.5, 'rotation_scale': 1.0}, 4, 2)
+    alg = build_algorithm(pixelssl, args, 'ssl_s4l')
+    st = O.randomize_bn_affine(O.init_deeplabv2(121, cls_bias_std=0.01), 122)
+    sd = {'module.task_model.model.' + k: v.clone() for k, v in st.items()}
+    sd.update({'module.rotation_classifier.' + k: v.clone() for k, v in S.init_rc(123).items()})
+    missing = alg.model.load_state_dict(sd, strict=False)
+    assert not [k for k in missing.missing_keys if 'num_batches' not in k and 'running' not in k], missing
+    img, lab = O.synthetic_batch(1000, 4, 2, size, size)
+    np.random.seed(77)
+    alg._train([((img.clone(),), (lab.clone(),))], 0)
+    sp = dict(alg.model.module.task_model.model.named_parameters())
+    rp = dict(alg.model.module.rotation_classifier.named_parameters())
+    rnames = [n for n, _ in S.rc_shapes()]
+    rec = {'size': size, 'np_seed': 77}
+    for k in ('unrotated_task_loss', 'rotated_task_loss', 'rotation_loss', 'rotation_acc'):
+        rec[k] = float(alg.meters[k].val)
+    rec['grad_checksum'] = checksums([(n, sp[n].grad) for n in names])
+    rec['param_checksum'] = checksums([(n, sp[n]) for n in names])
+    rec['rc_grad_checksum'] = checksums([(n, rp[n].grad) for n in rnames])
+    rec['rc_param_checksum'] = checksums([(n, rp[n]) for n in rnames])
+    rb = dict(alg.model.module.rotation_classifier.named_buffers())
+    rec['rc_buffer_checksum'] = checksums([(n, b.float()) for n, b in rb.items()])
+    rec['rc_buffer_names'] = np.array(list(rb.keys()))
+    rec['lrs'] = np.array([g['lr'] for g in alg.optimizer.param_groups])
+    # the rotated batch itself (bit-exact target of the rotate kernel)
+    np.random.seed(77)
+    angles = np.random.randint(low=1, high=4, size=4)
+    rec['angles'] = angles
+    rec['rot_img_sample'] = alg._rotate_tensor(img[1], int(angles[1])).numpy()
+    np.savez_compressed(os.path.join(OUT, 's4l_step_%d.npz' % size), **rec)
+    print('s4l golden:', {k: rec[k] for k in rec if 'loss' in k or 'acc' in k}, 'angles', angles)
+
+
 def golden_gct(pixelssl, sseg_proxy, size=129):
     """One SSLGCT._train step (ssl_gct.py:176-298): two DeepLabV2 task models + FlawDetector, lbs 2 + ubs 2."""
     from oracle import gct_oracle as Gc
@@ -600,7 +637,7 @@ if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     pixelssl, sseg_proxy = patch_and_import()
-    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 'gct', 'cct', 'pspnet', 'val', 'input', 'fp64']
+    which = sys.argv[1:] or ['ops', 'forward', 'mt', 'nullcutmix', 'adv', 's4l', 'gct', 'cct', 'pspnet', 'val', 'input', 'fp64']
     if which == ['fp64']:
         golden_fp64()
         sys.exit(0)
@@ -624,6 +661,8 @@ if __name__ == '__main__':
         golden_null_cutmix(pixelssl, sseg_proxy)
     if 'adv' in which:
         golden_adv(pixelssl, sseg_proxy)
+    if 's4l' in which:
+        golden_s4l(pixelssl, sseg_proxy)
     if 'gct' in which:
         golden_gct(pixelssl, sseg_proxy)
     if 'cct' in which:

@@ -9,7 +9,7 @@ Importing the package does not need a GPU; the first kernel call loads lib/libpi
 from .version import __version__
 from .utils import log_info, log_warn, log_err, str2bool, str2intlist, REGRESSION, CLASSIFICATION
 from . import nn, ssl_algorithm
-from .ssl_algorithm import SSL_NULL, SSL_MT, SSL_ADV, SSL_GCT, SSL_CCT, SSL_CUTMIX, SSL_ALGORITHMS
+from .ssl_algorithm import SSL_NULL, SSL_MT, SSL_ADV, SSL_S4L, SSL_GCT, SSL_CCT, SSL_CUTMIX, SSL_ALGORITHMS
 from .runner import create_parser, build_args, run_script
 
 

@@ -1242,10 +1242,14 @@ static int conv_tc_launch_core(const pxl_conv_geom* g, const int* taps, const px
         if (tiles > PXL_NUM_SMS) use_persist = 0;
     }
     // CTA pairs (cta_group::2): 256 pixels x BN per step, each CTA stages half of the weight tile
+    // PXL_TC_PAIR: 0 never, 1 whenever possible, 2 (default) = the fp16 modes on layers with >= 256 output channels and
+    // a reduction of >= 256 (ResNet layer3 / layer4): there the halved weight traffic per SM pays (measured per
+    // shape, tools/bench_conv.py: -6..-10 %); narrower layers are epilogue / L2 bound and lose with M = 256 tiles
     static int cfg_pair = -1;
-    if (cfg_pair < 0) { const char* e = getenv("PXL_TC_PAIR"); cfg_pair = e ? atoi(e) : 0; }
+    if (cfg_pair < 0) { const char* e = getenv("PXL_TC_PAIR"); cfg_pair = e ? atoi(e) : 2; }
     int use_pair = 0;
-    if (cfg_pair && cfg_persist && p.BN >= 128) {
+    const bool pair_wanted = cfg_pair == 1 || (cfg_pair == 2 && f16 && g->Cout >= 256 && (int64_t)g->Cin * g->ntaps >= 256);
+    if (pair_wanted && cfg_persist && p.BN >= 128) {
         int bw, bh;
         pick_tile(p.OH, p.OW, flat, bw, bh);
         const int64_t pix_tiles = (int64_t)p.N * ((p.OW + bw - 1) / bw) * ((p.OH + bh - 1) / bh);

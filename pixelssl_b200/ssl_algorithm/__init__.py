@@ -1,5 +1,5 @@
 """Algorithm registry with the reference's names (pixelssl/ssl_algorithm/__init__.py:10-27)."""
-from . import ssl_base, ssl_null, ssl_mt, ssl_cutmix, ssl_adv, ssl_gct, ssl_cct
+from . import ssl_base, ssl_null, ssl_mt, ssl_cutmix, ssl_adv, ssl_gct, ssl_cct, ssl_s4l
 
 SSL_NULL = ssl_null.SSLNULL.NAME
 SSL_MT = ssl_mt.SSLMT.NAME
@@ -7,5 +7,6 @@ SSL_CUTMIX = ssl_cutmix.SSLCUTMIX.NAME
 SSL_ADV = ssl_adv.SSLADV.NAME
 SSL_GCT = ssl_gct.SSLGCT.NAME
 SSL_CCT = ssl_cct.SSLCCT.NAME
+SSL_S4L = ssl_s4l.SSLS4L.NAME
 
-SSL_ALGORITHMS = [SSL_NULL, SSL_MT, SSL_ADV, SSL_GCT, SSL_CCT, SSL_CUTMIX]
+SSL_ALGORITHMS = [SSL_NULL, SSL_MT, SSL_ADV, SSL_S4L, SSL_GCT, SSL_CCT, SSL_CUTMIX]

@@ -381,3 +381,34 @@ def test_validation_input_pipeline_matches_reference_transforms(h, w, size, resc
     x_ref, y_ref = sseg_data.PascalVocDataset._val_prehandle(fake, Image.fromarray(img), Image.fromarray(lab))
     x, y = I.val_prehandle(img, lab, size, rescaling)
     assert np.array_equal(x, x_ref.numpy()) and np.array_equal(y, y_ref.numpy())
+
+
+@pytest.mark.slow
+def test_s4l_step_matches_reference_train_body():
+    """SSLS4L._train (ssl_s4l.py:113-200): batch doubled by rotated copies (np.random quarter turns), rotation
+    classifier with plain nn.BatchNorm2d, three loss terms, one SGD step over the task model + classifier groups."""
+    from oracle import s4l_oracle as S
+    g = load('s4l_step_65.npz')
+    names = [n for n, _, _ in O.deeplabv2_param_shapes()]
+    st = O.randomize_bn_affine(O.init_deeplabv2(121, cls_bias_std=0.01), 122)
+    orc = S.S4LOracle(st, S.init_rc(123), rotated_sup_scale=0.5, rotation_scale=1.0, lr=0.00025, momentum=0.9,
+                      weight_decay=0.0005, max_iters=10)
+    img, lab = O.synthetic_batch(1000, 4, 2, 65, 65)
+    np.random.seed(int(g['np_seed']))
+    angles = np.random.randint(low=1, high=4, size=4)
+    assert np.array_equal(angles, g['angles'])
+    assert np.array_equal(S.rotate_tensor(img[1], int(angles[1])).numpy(), g['rot_img_sample'])
+    out = orc.step(img, lab, 2, angles)
+    for k in ('unrotated_task_loss', 'rotated_task_loss', 'rotation_loss'):
+        assert abs(float(out[k]) - float(g[k])) <= 2e-5 * abs(float(g[k])), (k, float(out[k]), float(g[k]))
+    assert abs(float(out['rotation_acc']) - float(g['rotation_acc'])) <= 1e-4
+    rel = np.abs(_checks([out['grads'][n] for n in names])[:, 1] - g['grad_checksum'][:, 1]) / g['grad_checksum'][:, 1]
+    assert rel.max() < 5e-3 and np.median(rel) < 5e-4, (rel.max(), np.median(rel))
+    rn = orc.rc_names
+    rel = np.abs(_checks([out['rc_grads'][n] for n in rn])[:, 1] - g['rc_grad_checksum'][:, 1]) / np.maximum(g['rc_grad_checksum'][:, 1], 1e-30)
+    keep = np.array([not (n.startswith('conv') and n.endswith('.bias')) for n in rn])      # biases in front of a BN: zero true gradient
+    assert rel[keep].max() < 2e-3, rel
+    np.testing.assert_allclose(_checks([orc.rc[n] for n in rn])[:, 1], g['rc_param_checksum'][:, 1], rtol=1e-5)
+    np.testing.assert_allclose(_checks([orc.s[n] for n in names])[:, 1], g['param_checksum'][:, 1], rtol=1e-5)
+    bn = [str(n) for n in g['rc_buffer_names']]
+    np.testing.assert_allclose(_checks([orc.rc[n].float() for n in bn])[:, 1], g['rc_buffer_checksum'][:, 1], rtol=1e-5)
