@@ -217,6 +217,7 @@ typedef struct {
                               * sync_batchnorm/batchnorm.py:60-62) */
     float out_scale;         /* 0 is read as 1: the accumulator is multiplied by out_scale * (*out_scale_dev) before */
     const float* out_scale_dev;   /* bias / statistics / store (undoes the power-of-two scales of fp16 pairs); nullable */
+    int out_accumulate;      /* != 0: out += result (TMA reduce-add epilogue; PXL_ERR_UNSUPPORTED where that epilogue is not used) */
 } pxl_conv_tc_ext;
 int pxl_conv_tc_launch_ex(const pxl_conv_geom* geom_host, const int* taps_dydx_host, const pxl_conv_tc_ext* ext_host,
                           const float* in_hi, const float* in_lo, const float* w_hi, const float* w_lo,

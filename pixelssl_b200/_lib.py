@@ -23,7 +23,7 @@ class ConvTcExt(ctypes.Structure):
     """mirror of pxl_conv_tc_ext"""
     _fields_ = [('w_ntaps', c_int), ('widx_host', ctypes.POINTER(c_int)), ('out_mul', c_int),
                 ('out_offy', c_int), ('out_offx', c_int), ('out_H', c_int), ('out_W', c_int),
-                ('bn_stats', c_void_p), ('out_scale', c_float), ('out_scale_dev', c_void_p)]
+                ('bn_stats', c_void_p), ('out_scale', c_float), ('out_scale_dev', c_void_p), ('out_accumulate', c_int)]
 
 
 P = c_void_p

@@ -172,6 +172,14 @@ __device__ __forceinline__ void tma_reduce_add_3d(const void* src, const CUtenso
         ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// out[box] += shared[box] (fp32): lets a dgrad launch add its result into a tensor that already holds another
+// gradient (the residual branch of a bottleneck), instead of a separate elementwise add over both tensors
+__device__ __forceinline__ void tma_reduce_add_4d(const void* src, const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_commit_and_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -263,6 +271,7 @@ struct TcParams {
     int f16;        // operands are fp16 (kind::f16); nsplit == 3 then means the fp16 pair hi/lo of both operands
     int kc;         // K elements per 128-byte operand row: 32 (tf32) or 64 (fp16)
     float out_scale;   // the accumulator is multiplied by this (and by *oscale_ptr) before bias / statistics / store
+    int out_acc;       // TMA-store epilogue adds into `out` (cp.reduce.async.bulk .add) instead of overwriting it
     short dy[PXL_MAX_TAPS], dx[PXL_MAX_TAPS], widx[PXL_MAX_TAPS];
 };
 
@@ -702,7 +711,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
                     if (et == 0) {
-                        tma_store_4d(staging + (size_t)b * TC_A_BYTES, &mapOut, cb, w0, h0, n);
+                        if (p.out_acc) tma_reduce_add_4d(staging + (size_t)b * TC_A_BYTES, &mapOut, cb, w0, h0, n);
+                        else tma_store_4d(staging + (size_t)b * TC_A_BYTES, &mapOut, cb, w0, h0, n);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     ++sc;
@@ -1028,7 +1038,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     if (et == 0) {
-                        tma_store_4d(staging + (size_t)b * TC_A_BYTES, &mapOut, cb, w0, h0, n);
+                        if (p.out_acc) tma_reduce_add_4d(staging + (size_t)b * TC_A_BYTES, &mapOut, cb, w0, h0, n);
+                        else tma_store_4d(staging + (size_t)b * TC_A_BYTES, &mapOut, cb, w0, h0, n);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     ++sc;
@@ -1304,6 +1315,8 @@ static int conv_tc_launch_core(const pxl_conv_geom* g, const int* taps, const px
         rc = make_out_map(&mO, out, g->Cout, g->ldo, p.outW, p.outH, p.N, p.BW, p.BH);
         if (rc) p.tma_store = 0;
     }
+    p.out_acc = (ext && ext->out_accumulate) ? 1 : 0;
+    if (p.out_acc && !(p.tma_store && use_persist)) return PXL_ERR_UNSUPPORTED;      // accumulation exists in the TMA-store epilogues only
     cudaStream_t st = (cudaStream_t)stream;
     if (!g_err_flag) {
         cudaError_t e = cudaMalloc(&g_err_flag, sizeof(int));

@@ -344,6 +344,7 @@ def new_step():
     global _epoch
     _epoch += 1
     _stat_pool_reset()
+    _residual_stash.clear()
 
 
 # Per-channel fp64 accumulators (BN sums, their gradients) are tiny and short-lived (consumed by the next
@@ -546,7 +547,8 @@ def _tc_launch(geom, taps, ext, x_parts, w_parts, bias, out):
                       'fwd/dgrad(tf32) N%d %dx%d Cin%d Cout%d taps%d' % (geom.N, geom.OH, geom.OW, geom.Cin, geom.Cout, geom.ntaps)))
 
 
-def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, out=None, precision=None, bn_stats=None):
+def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div, out=None, precision=None, bn_stats=None,
+             accumulate=False):
     """Launch the NHWC tap-table convolution on raw buffers.  w_packed: [Cout][ntaps][Cin] contiguous.
     precision 0: FFMA kernel; 1: tcgen05 single-pass TF32; 2: tcgen05 3xTF32 (operands split on the
     fly).  Shapes the tensor-core kernel does not cover (Cin % 32 != 0, other strides) use the FFMA kernel."""
@@ -577,6 +579,7 @@ def conv_raw(x, w_packed, bias, taps, N, H, W, Cin, OH, OW, Cout, ldo, mul, div,
 
         def launch(geom, tp, ext):
             ext.out_scale, ext.out_scale_dev = oscale, (odev.data_ptr() if odev is not None else None)
+            ext.out_accumulate = 1 if accumulate else 0
             _timed_call('pxl_conv_h16_launch', ctypes.byref(geom), _ctaps(tp), ctypes.byref(ext), _p(xh.hi), _p(xh.lo),
                         _p(wh.hi), _p(wh.lo if want_lo else None), _p(bias), _p(out), _stream(),
                         meta=(2.0 * geom.N * geom.OH * geom.OW * geom.Cin * min(geom.Cout, Cout) * geom.ntaps,
@@ -1166,6 +1169,7 @@ def bn_act(x, gamma, beta, running_mean, running_var, training=True, momentum=0.
 # conv -> BN -> (+residual) -> (ReLU) as one node on the fp16-pair path
 # ------------------------------------------------------------------------------------------------
 
+_residual_stash = {}            # block key -> gradient of the residual branch waiting for the block's first dgrad (one step)
 H16_DX_TARGET_LOG2 = 12         # bn_bwd_dx: max|gamma*invstd| * absmax(dz) -> <= 2^12, 3 bits of headroom for the mean terms
 _unit_out_pair = None           # H16 of the last _ConvBnAct.forward output (picked up by conv_bn_act right after apply)
 
@@ -1206,8 +1210,9 @@ class _ConvBnAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, running_mean, running_var, residual, stride, padding, dilation,
-                momentum, eps, relu, group, clamp_var, out_mode):
+                momentum, eps, relu, group, clamp_var, out_mode, stash_key=None, stash_role=None):
         global _unit_out_pair
+        ctx.stash = (stash_key, stash_role)
         prec = _conv_precision
         want_lo = prec == 3
         N, Cin, H, W = x.shape
@@ -1305,6 +1310,12 @@ class _ConvBnAct(torch.autograd.Function):
              _p(dpair[0]), _p(dpair[1] if want_lo else None), _p(slot), H16_DX_TARGET_LOG2, _stream())
         dh = H16(dpair, n, None, slot, want_lo)
         dx = dw = None
+        stash_key, stash_role = ctx.stash
+        if stash_role == 'give' and dres is not None:
+            # the residual branch of this block is the block input itself: its gradient is handed to the block's first
+            # unit, whose dgrad epilogue adds into it (TMA reduce-add) - no elementwise add of the two branch gradients
+            _residual_stash[stash_key] = dres
+            dres = None
         if ctx.needs_input_grad[0]:
             arena, off = _arena_of(weight) if BATCH_WEIGHT_PREP else (None, None)
             if arena is not None and arena._conv_at.get(off) == (Cout, T, Cin):
@@ -1312,14 +1323,27 @@ class _ConvBnAct(torch.autograd.Function):
                 wt = H16(arena.derived('h16_t')[:, off:off + nw], nw, H16_W_SCALE, None, True)
             else:
                 wt = h16_split(transpose_weights(weight, Cout, T, Cin), H16_W_SCALE, want_lo)
-            dx = conv_raw(dh, wt, None, [-v for v in taps], N, OH, OW, Cout, H, W, Cin, Cin, 1, stride, precision=prec)
+            held = _residual_stash.pop(stash_key, None) if stash_role == 'take' else None
+            if held is not None:
+                try:
+                    dx = conv_raw(dh, wt, None, [-v for v in taps], N, OH, OW, Cout, H, W, Cin, Cin, 1, stride, out=held,
+                                  precision=prec, accumulate=True)
+                except _lib.PxlError as e:
+                    if e.code != _lib.PXL_ERR_UNSUPPORTED:
+                        raise
+                    dx = conv_raw(dh, wt, None, [-v for v in taps], N, OH, OW, Cout, H, W, Cin, Cin, 1, stride, precision=prec)
+                    dx += held
+            else:
+                dx = conv_raw(dh, wt, None, [-v for v in taps], N, OH, OW, Cout, H, W, Cin, Cin, 1, stride, precision=prec)
+        elif stash_role == 'take':
+            _residual_stash.pop(stash_key, None)
         if ctx.needs_input_grad[1]:
             inplace = ACCUM_WGRAD_INPLACE and weight.grad is not None and weight.grad.is_contiguous(memory_format=CL)
             dwbuf = weight.grad if inplace else torch.zeros_like(weight, memory_format=torch.preserve_format)
             conv_wgrad_raw(H16(xbuf, xbuf.shape[1], xscale, None, want_lo), dh, dwbuf, taps, N, H, W, Cin, OH, OW, Cout, Cout,
                            stride, 1, precision=prec)
             dw = None if inplace else dwbuf
-        return (dx, dw, dgamma, dbeta, None, None, dres) + (None,) * 9
+        return (dx, dw, dgamma, dbeta, None, None, dres) + (None,) * 11
 
 
 def conv_bn_unit_ok(conv, bn):
@@ -1329,14 +1353,17 @@ def conv_bn_unit_ok(conv, bn):
             and conv.in_channels % 64 == 0 and conv.out_channels % 64 == 0 and conv.stride in (1, 2))
 
 
-def conv_bn_act(x, conv, bn, relu=False, residual=None, out_mode='both'):
-    """conv (nn.modules.Conv2d) -> bn (nn.modules.BatchNorm2d) -> (+residual) -> (ReLU); see _ConvBnAct."""
+def conv_bn_act(x, conv, bn, relu=False, residual=None, out_mode='both', stash_key=None, stash_role=None):
+    """conv (nn.modules.Conv2d) -> bn (nn.modules.BatchNorm2d) -> (+residual) -> (ReLU); see _ConvBnAct.
+    stash_key / stash_role: a bottleneck whose residual branch is its own input marks its last unit 'give' and its
+    first unit 'take' with a common key - the residual gradient then reaches the block input through the first
+    unit's dgrad epilogue (out += ...) instead of through autograd's add."""
     global _unit_out_pair
     if not is_carrier(x):
         x = as_cl(x)
     out = _ConvBnAct.apply(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
                            int(conv.stride), int(conv.padding), int(conv.dilation), float(bn.momentum), float(bn.eps),
-                           bool(relu), bn.sync_group, bool(bn.multi_replica_formula), out_mode)
+                           bool(relu), bn.sync_group, bool(bn.multi_replica_formula), out_mode, stash_key, stash_role)
     pair, _unit_out_pair = _unit_out_pair, None
     if pair is not None:
         _attach_pair(out, pair, carrier=(out_mode == 'pair'))
