@@ -641,6 +641,26 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         const int barid = 1 + grp;
         uint32_t tcount = 0, sc = 0;
         const float osc = p.out_scale * (oscale_ptr ? __ldg(oscale_ptr) : 1.f);
+        // BatchNorm statistics are accumulated per lane across the tiles this CTA processes for one channel block
+        // and flushed with ONE pair of fp64 atomics per channel when the channel block changes / at the end: the
+        // stem and layer1 convolutions run ~50 tiles per CTA onto 64..256 channels, and per-tile atomics serialise on
+        // those few addresses (33 K atomics per address for the stem).  fp32 partials over <= a few thousand rows.
+        float st_s0 = 0.f, st_s1 = 0.f, st_s2 = 0.f, st_s3 = 0.f, st_q0 = 0.f, st_q1 = 0.f, st_q2 = 0.f, st_q3 = 0.f;
+        int st_n0 = -1;
+        auto flush_stats = [&]() {
+            if (stats && st_n0 >= 0) {
+                const float ss[4] = {st_s0, st_s1, st_s2, st_s3}, qq[4] = {st_q0, st_q1, st_q2, st_q3};
+#pragma unroll
+                for (int si = 0; si < 4; ++si) {
+                    const int cbf = st_n0 + 32 * (grp + si * ngrp) + lane;
+                    if (32 * (grp + si * ngrp) < p.BN && cbf < p.Cout && (ss[si] != 0.f || qq[si] != 0.f)) {
+                        atomicAdd(stats + cbf, (double)ss[si]);
+                        atomicAdd(stats + p.Cout + cbf, (double)qq[si]);
+                    }
+                }
+            }
+            st_s0 = st_s1 = st_s2 = st_s3 = st_q0 = st_q1 = st_q2 = st_q3 = 0.f;
+        };
         bool ok = true;
         for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++tcount) {
             const uint32_t set = tcount & 1u, aph = (tcount >> 1) & 1u;
@@ -649,6 +669,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             tc_fence_after();
             int n0, w0, h0, n;
             tc_tile_coords(p, tile, n0, w0, h0, n);
+            if (n0 != st_n0) { flush_stats(); st_n0 = n0; }
             const int hy = r / p.BW, wx = r - hy * p.BW;
             const int oy = h0 + hy, ox = w0 + wx;
             const bool valid = hy < p.BH && oy < p.OH && ox < p.OW;
@@ -690,7 +711,15 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                             sq[i] = (up ? sq[i + off] : sq[i]) + q_recv;
                         }
                     }
-                    if (cb + lane < p.Cout) {
+                    const int si = (j / 32 - grp) / ngrp;
+                    if (si < 4) {
+                        switch (si) {
+                            case 0: st_s0 += sv[0]; st_q0 += sq[0]; break;
+                            case 1: st_s1 += sv[0]; st_q1 += sq[0]; break;
+                            case 2: st_s2 += sv[0]; st_q2 += sq[0]; break;
+                            default: st_s3 += sv[0]; st_q3 += sq[0]; break;
+                        }
+                    } else if (cb + lane < p.Cout) {          // BN = 256 with one epilogue group: slabs 4..7 go out per tile
                         atomicAdd(stats + cb + lane, (double)sv[0]);
                         atomicAdd(stats + p.Cout + cb + lane, (double)sq[0]);
                     }
@@ -732,6 +761,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             tc_fence_before();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[set])) : "memory");
         }
+        flush_stats();
         if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     } else {
         // ================= operand transform (3xTF32, raw activations) =================

@@ -284,30 +284,43 @@ extern "C" int pxl_dilate3x3_reflect(const float* in, float* out, int n, int H, 
 
 // per-sample min-max normalisation (x - min) / (max - min + eps); zero_below: if the sample's max
 // is <= zero_below the whole map is zeroed first (FlawmapHandler, ssl_gct.py:641-657; < 0 disables)
-__global__ void __launch_bounds__(512)
-minmax_norm_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t HW, float eps, float zero_below,
-                   float clamp_min) {
-    const int b = blockIdx.x;
+// Two launches: (1) per-sample min / max over many CTAs (order-independent, so still deterministic) through ordered-uint
+// atomics into a small workspace, (2) the normalisation itself.  A single 512-thread CTA per sample, as in round 1, is
+// latency bound on 713x713 maps (0.36 ms per call).
+__device__ __forceinline__ unsigned f2ord(float f) { const unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(unsigned o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
+
+__global__ void minmax_init_kernel(unsigned* ws, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { ws[2 * i] = 0xffffffffu; ws[2 * i + 1] = 0u; }
+}
+
+__global__ void __launch_bounds__(256)
+minmax_reduce_kernel(const float* __restrict__ in, int64_t HW, float clamp_min, unsigned* __restrict__ ws) {
+    const int b = blockIdx.y;
     const float* ip = in + (int64_t)b * HW;
-    float* op = out + (int64_t)b * HW;
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-    for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
         float v = __ldg(ip + i);
         if (v < clamp_min) v = clamp_min;
         mn = fminf(mn, v); mx = fmaxf(mx, v);
     }
-    __shared__ float smn[16], smx[16];
     mn = -warp_max(-mn); mx = warp_max(mx);
-    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
-    __syncthreads();
-    mn = smn[0]; mx = smx[0];
-#pragma unroll
-    for (int i = 1; i < 16; ++i) { mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(ws + 2 * b, f2ord(mn)); atomicMax(ws + 2 * b + 1, f2ord(mx)); }
+}
+
+__global__ void __launch_bounds__(256)
+minmax_apply_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t HW, float eps, float zero_below,
+                    float clamp_min, const unsigned* __restrict__ ws) {
+    const int b = blockIdx.y;
+    const float mn = ord2f(ws[2 * b]), mx = ord2f(ws[2 * b + 1]);
     // reference quirk kept: min/max are taken BEFORE the map is zeroed (ssl_gct.py:648-654), so a
     // zeroed map becomes the constant -min / (max - min + eps), not 0
     const bool zero = (zero_below >= 0.f) && (mx <= zero_below);
     const float denom = mx - mn + eps;
-    for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float* ip = in + (int64_t)b * HW;
+    float* op = out + (int64_t)b * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
         float v = __ldg(ip + i);
         if (v < clamp_min) v = clamp_min;
         if (zero) v = 0.f;
@@ -319,8 +332,22 @@ minmax_norm_kernel(const float* __restrict__ in, float* __restrict__ out, int64_
 // -inf to disable).  in == out allowed.
 extern "C" int pxl_minmax_norm(const float* in, float* out, int n, int64_t HW, float eps, float zero_below,
                                float clamp_min, void* stream) {
-    if (!in || !out || n <= 0 || HW <= 0) return PXL_ERR_BAD_ARG;
-    minmax_norm_kernel<<<n, 512, 0, (cudaStream_t)stream>>>(in, out, HW, eps, zero_below, clamp_min);
+    if (!in || !out || n <= 0 || HW <= 0 || n > 65535) return PXL_ERR_BAD_ARG;
+    static unsigned* ws = nullptr;
+    static int ws_n = 0;
+    if (ws_n < n) {
+        if (ws) cudaFree(ws);
+        if (cudaMalloc(&ws, (size_t)2 * n * sizeof(unsigned)) != cudaSuccess) { ws = nullptr; ws_n = 0; return PXL_ERR_BAD_ARG; }
+        ws_n = n;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int bx = (int)pxl_cdiv(HW, 256 * 8);
+    if (bx > PXL_NUM_SMS * 2) bx = PXL_NUM_SMS * 2;
+    if (bx < 1) bx = 1;
+    minmax_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(ws, n);
+    minmax_reduce_kernel<<<dim3(bx, n), 256, 0, st>>>(in, HW, clamp_min, ws);
+    minmax_apply_kernel<<<dim3(bx, n), 256, 0, st>>>(in, out, HW, eps, zero_below, clamp_min, ws);
+    pxl_count_launch_(2);
     PXL_CHECK_LAUNCH();
     return 0;
 }
@@ -508,27 +535,32 @@ extern "C" int pxl_argmax_nonzero_mask(const float* logits, float* mask, int n, 
 // ------------------------------------------------------------------------------------------
 // PSPNet pyramid pooling pieces on NHWC (task/sseg/module/_pspnet.py:57-102)
 // ------------------------------------------------------------------------------------------
-// nn.AdaptiveAvgPool2d(bin): window [floor(i*H/bin), ceil((i+1)*H/bin))
+// nn.AdaptiveAvgPool2d(bin): window [floor(i*H/bin), ceil((i+1)*H/bin)).  One thread per (bin cell, channel quad,
+// window row): it sums its row and adds it into the (zeroed) output - with one thread per cell, as in round 1, the
+// 1x1 / 2x2 pyramids summed up to 8100 pixels serially (0.13 ms per call on the 90x90 PSPNet latent).
 __global__ void __launch_bounds__(256)
-adaptive_pool_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H, int W, int c4, int bin) {
-    const int64_t total = (int64_t)N * bin * bin * c4;
+adaptive_pool_fwd_kernel(const float4* __restrict__ x, float* __restrict__ y, int N, int H, int W, int c4, int bin, int maxwin) {
+    const int64_t total = (int64_t)N * bin * bin * c4 * maxwin;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const int c = (int)(i % c4);
         int64_t p = i / c4;
+        const int r = (int)(p % maxwin); p /= maxwin;
         const int bx = (int)(p % bin); p /= bin;
         const int by = (int)(p % bin);
         const int n = (int)(p / bin);
         const int y0 = (by * H) / bin, y1 = ((by + 1) * H + bin - 1) / bin;
         const int x0 = (bx * W) / bin, x1 = ((bx + 1) * W + bin - 1) / bin;
+        const int yy = y0 + r;
+        if (yy >= y1) continue;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int yy = y0; yy < y1; ++yy)
-            for (int xx = x0; xx < x1; ++xx) {
-                const float4 v = __ldg(x + ((int64_t)(n * H + yy) * W + xx) * c4 + c);
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-            }
+        for (int xx = x0; xx < x1; ++xx) {
+            const float4 v = __ldg(x + ((int64_t)(n * H + yy) * W + xx) * c4 + c);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
         const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
-        y[i] = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+        float* o = y + ((((int64_t)n * bin + by) * bin + bx) * c4 + c) * 4;
+        atomicAdd(o, s.x * inv); atomicAdd(o + 1, s.y * inv); atomicAdd(o + 2, s.z * inv); atomicAdd(o + 3, s.w * inv);
     }
 }
 
@@ -565,7 +597,13 @@ extern "C" int pxl_adaptive_avgpool_nhwc(const float* x, float* y, int N, int H,
     int blocks = (int)(pxl_cdiv(total, 256) < PXL_NUM_SMS * 8 ? pxl_cdiv(total, 256) : PXL_NUM_SMS * 8);
     // backward: x = dy [N,bin,bin,C], y = dx [N,H,W,C]
     if (backward) adaptive_pool_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C / 4, bin);
-    else adaptive_pool_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C / 4, bin);
+    else {
+        const int maxwin = (H + bin - 1) / bin + 1;
+        const int64_t tot = (int64_t)N * bin * bin * (C / 4) * maxwin;
+        int fb = (int)(pxl_cdiv(tot, 256) < PXL_NUM_SMS * 16 ? pxl_cdiv(tot, 256) : PXL_NUM_SMS * 16);
+        cudaMemsetAsync(y, 0, (size_t)N * bin * bin * C * sizeof(float), (cudaStream_t)stream);
+        adaptive_pool_fwd_kernel<<<fb, 256, 0, (cudaStream_t)stream>>>((const float4*)x, y, N, H, W, C / 4, bin, maxwin);
+    }
     PXL_CHECK_LAUNCH();
     return 0;
 }
@@ -604,41 +642,42 @@ bilinear_nhwc_fwd_kernel(const float4* __restrict__ in, float* __restrict__ out,
     }
 }
 
-// backward: one thread per (input pixel, channel quad) gathers every output pixel in its support
+// backward: one thread per (input pixel, channel quad, OUTPUT ROW): rows outside the pixel's support exit at once, the
+// others walk the output row and add their weighted sum into the (zeroed) input gradient.  Round 1 had one thread per
+// input pixel scanning all H*W outputs (0.6 ms per call for the PSPNet pyramid at 90x90).
 __global__ void __launch_bounds__(256)
-bilinear_nhwc_bwd_kernel(const float* __restrict__ gout, float4* __restrict__ gin, int N, int h, int w, int c4, int H, int W,
+bilinear_nhwc_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int N, int h, int w, int c4, int H, int W,
                          int ldo, int coff, float sh, float sw, bool ac) {
-    const int64_t total = (int64_t)N * h * w * c4;
+    const int64_t total = (int64_t)N * h * w * c4 * H;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const int c = (int)(i % c4);
         int64_t p = i / c4;
+        const int Y = (int)(p % H); p /= H;
         const int xi = (int)(p % w); p /= w;
         const int yi = (int)(p % h);
         const int n = (int)(p / h);
+        const float fy = src_idx(sh, Y, ac);
+        const int y0 = (int)fy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
+        if (y0 != yi && y1 != yi) continue;
+        const float ly1 = fy - (float)y0;
+        float wy = 0.f;
+        if (y0 == yi) wy += 1.f - ly1;
+        if (y1 == yi) wy += ly1;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int Y = 0; Y < H; ++Y) {
-            const float fy = src_idx(sh, Y, ac);
-            const int y0 = (int)fy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
-            const float ly1 = fy - (float)y0;
-            float wy = 0.f;
-            if (y0 == yi) wy += 1.f - ly1;
-            if (y1 == yi) wy += ly1;
-            if (y0 != yi && y1 != yi) continue;
-            for (int X = 0; X < W; ++X) {
-                const float fx = src_idx(sw, X, ac);
-                const int x0 = (int)fx, x1 = x0 + (x0 < w - 1 ? 1 : 0);
-                if (x0 != xi && x1 != xi) continue;
-                const float lx1 = fx - (float)x0;
-                float wx = 0.f;
-                if (x0 == xi) wx += 1.f - lx1;
-                if (x1 == xi) wx += lx1;
-                const float4 g = __ldg(reinterpret_cast<const float4*>(gout + ((int64_t)(n * H + Y) * W + X) * ldo + coff + 4 * c));
-                const float ww = wy * wx;
-                s.x += g.x * ww; s.y += g.y * ww; s.z += g.z * ww; s.w += g.w * ww;
-            }
+        for (int X = 0; X < W; ++X) {
+            const float fx = src_idx(sw, X, ac);
+            const int x0 = (int)fx, x1 = x0 + (x0 < w - 1 ? 1 : 0);
+            if (x0 != xi && x1 != xi) continue;
+            const float lx1 = fx - (float)x0;
+            float wx = 0.f;
+            if (x0 == xi) wx += 1.f - lx1;
+            if (x1 == xi) wx += lx1;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gout + ((int64_t)(n * H + Y) * W + X) * ldo + coff + 4 * c));
+            s.x += g.x * wx; s.y += g.y * wx; s.z += g.z * wx; s.w += g.w * wx;
         }
-        gin[i] = s;
+        float* o = gin + ((((int64_t)n * h + yi) * w + xi) * c4 + c) * 4;
+        atomicAdd(o, s.x * wy); atomicAdd(o + 1, s.y * wy); atomicAdd(o + 2, s.z * wy); atomicAdd(o + 3, s.w * wy);
     }
 }
 
@@ -658,9 +697,10 @@ extern "C" int pxl_bilinear_nhwc(const float* in, float* out, int N, int h, int 
         int blocks = (int)(pxl_cdiv(total, 256) < PXL_NUM_SMS * 8 ? pxl_cdiv(total, 256) : PXL_NUM_SMS * 8);
         bilinear_nhwc_fwd_kernel<<<blocks, 256, 0, st>>>((const float4*)in, out, N, h, w, C / 4, H, W, ldo, coff, sh, sw, align_corners != 0);
     } else {      // in = grad of the wide output [N,H,W,ldo], out = grad of the small input [N,h,w,C]
-        const int64_t total = (int64_t)N * h * w * (C / 4);
-        int blocks = (int)(pxl_cdiv(total, 256) < PXL_NUM_SMS * 8 ? pxl_cdiv(total, 256) : PXL_NUM_SMS * 8);
-        bilinear_nhwc_bwd_kernel<<<blocks, 256, 0, st>>>(in, (float4*)out, N, h, w, C / 4, H, W, ldo, coff, sh, sw, align_corners != 0);
+        const int64_t total = (int64_t)N * h * w * (C / 4) * H;
+        int blocks = (int)(pxl_cdiv(total, 256) < PXL_NUM_SMS * 16 ? pxl_cdiv(total, 256) : PXL_NUM_SMS * 16);
+        cudaMemsetAsync(out, 0, (size_t)N * h * w * C * sizeof(float), st);
+        bilinear_nhwc_bwd_kernel<<<blocks, 256, 0, st>>>(in, out, N, h, w, C / 4, H, W, ldo, coff, sh, sw, align_corners != 0);
     }
     PXL_CHECK_LAUNCH();
     return 0;

@@ -111,5 +111,7 @@ def test_pspnet_supervised_step_vs_oracle(ops):
     head = np.array([not n.startswith('backbone.') for n in names])
     print('pspnet grad energy rel: head median %.2e max %.2e | backbone median %.2e' % (
         np.median(relg[head]), relg[head].max(), np.median(relg[~head])))
-    assert np.median(relg[head]) <= 1e-3 and relg[head].max() <= 5e-2
+    # measured over repeated runs (the pyramid's pooling / resize backward use fp32 atomics, and a few ReLU kinks take
+    # either branch): head median 3.5e-4 .. 9.4e-4, max 2e-3 .. 3e-2 in every precision mode
+    assert np.median(relg[head]) <= 3e-3 and relg[head].max() <= 5e-2
     assert np.median(relg[~head]) <= 2e-2
