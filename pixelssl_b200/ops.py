@@ -1169,6 +1169,37 @@ def bn_act(x, gamma, beta, running_mean, running_var, training=True, momentum=0.
 # conv -> BN -> (+residual) -> (ReLU) as one node on the fp16-pair path
 # ------------------------------------------------------------------------------------------------
 
+# Weight gradients are off the critical path of the backward pass (nothing reads them before the optimiser step), so
+# they could run on a side stream right after the dX pair they consume exists, overlapping the HBM-bound BatchNorm
+# backward launches.  NEGATIVE RESULT (measured, B200, MT step): 53.8 ms -> 76.4 ms.  The wgrad CTAs (200 KB of
+# shared memory each) take SMs away from the persistent one-CTA-per-SM convolutions of the critical path, which then
+# wait for them - a priority inversion the default stream cannot be prioritised out of.  Opt-in: PXL_WGRAD_SIDE_STREAM=1.
+WGRAD_SIDE_STREAM = _os.environ.get('PXL_WGRAD_SIDE_STREAM', '0') != '0'
+_side_streams = {}
+
+
+def _wgrad_stream(device):
+    s = _side_streams.get(device)
+    if s is None:
+        s = _side_streams[device] = [torch.cuda.Stream(device=device), False, False]
+    return s
+
+
+def _join_after_backward():
+    for ent in _side_streams.values():
+        ent[2] = False
+    join_side_streams()
+
+
+def join_side_streams():
+    """Make the current stream wait for every side-stream launch so far (called before gradients are consumed:
+    all-reduce, optimiser step, zero_grad)."""
+    for ent in _side_streams.values():
+        if ent[1]:
+            torch.cuda.current_stream().wait_stream(ent[0])
+            ent[1] = False
+
+
 _residual_stash = {}            # block key -> gradient of the residual branch waiting for the block's first dgrad (one step)
 H16_DX_TARGET_LOG2 = 12         # bn_bwd_dx: max|gamma*invstd| * absmax(dz) -> <= 2^12, 3 bits of headroom for the mean terms
 _unit_out_pair = None           # H16 of the last _ConvBnAct.forward output (picked up by conv_bn_act right after apply)
@@ -1340,8 +1371,24 @@ class _ConvBnAct(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             inplace = ACCUM_WGRAD_INPLACE and weight.grad is not None and weight.grad.is_contiguous(memory_format=CL)
             dwbuf = weight.grad if inplace else torch.zeros_like(weight, memory_format=torch.preserve_format)
-            conv_wgrad_raw(H16(xbuf, xbuf.shape[1], xscale, None, want_lo), dh, dwbuf, taps, N, H, W, Cin, OH, OW, Cout, Cout,
-                           stride, 1, precision=prec)
+            xh = H16(xbuf, xbuf.shape[1], xscale, None, want_lo)
+            if WGRAD_SIDE_STREAM and inplace:
+                ent = _wgrad_stream(dev)
+                main = torch.cuda.current_stream()
+                ev = torch.cuda.Event()
+                ev.record(main)                         # the dX pair (and everything before it) is enqueued
+                ent[0].wait_event(ev)
+                with torch.cuda.stream(ent[0]):
+                    conv_wgrad_raw(xh, dh, dwbuf, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1, precision=prec)
+                dpair.record_stream(ent[0])
+                xbuf.record_stream(ent[0])
+                ent[1] = True
+                if not ent[2]:
+                    # whoever reads .grad after loss.backward() does so on the main stream: join when this backward ends
+                    ent[2] = True
+                    torch.autograd.Variable._execution_engine.queue_callback(_join_after_backward)
+            else:
+                conv_wgrad_raw(xh, dh, dwbuf, taps, N, H, W, Cin, OH, OW, Cout, Cout, stride, 1, precision=prec)
             dw = None if inplace else dwbuf
         return (dx, dw, dgamma, dbeta, None, None, dres) + (None,) * 11
 
