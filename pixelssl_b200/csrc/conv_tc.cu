@@ -272,6 +272,7 @@ struct TcParams {
     int kc;         // K elements per 128-byte operand row: 32 (tf32) or 64 (fp16)
     float out_scale;   // the accumulator is multiplied by this (and by *oscale_ptr) before bias / statistics / store
     int out_acc;       // TMA-store epilogue adds into `out` (cp.reduce.async.bulk .add) instead of overwriting it
+    int stats_smem;    // BN statistics: column walk over the staged slab instead of the register butterfly
     short dy[PXL_MAX_TAPS], dx[PXL_MAX_TAPS], widx[PXL_MAX_TAPS];
 };
 
@@ -695,7 +696,9 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 #pragma unroll
                     for (int c = 0; c < 32; ++c) if (cb + c < p.Cout) v[c] += __ldg(bias + cb + c);
                 }
-                if (stats) {
+                const bool walk = stats && p.stats_smem && p.tma_store;
+                float col_s = 0.f, col_q = 0.f;              // this lane's column over this warp's 32 rows
+                if (stats && !walk) {
                     float sv[32], sq[32];
 #pragma unroll
                     for (int c = 0; c < 32; ++c) { const float o = valid ? v[c] : 0.f; sv[c] = o; sq[c] = o * o; }
@@ -711,18 +714,11 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                             sq[i] = (up ? sq[i + off] : sq[i]) + q_recv;
                         }
                     }
-                    const int si = (j / 32 - grp) / ngrp;
-                    if (si < 4) {
-                        switch (si) {
-                            case 0: st_s0 += sv[0]; st_q0 += sq[0]; break;
-                            case 1: st_s1 += sv[0]; st_q1 += sq[0]; break;
-                            case 2: st_s2 += sv[0]; st_q2 += sq[0]; break;
-                            default: st_s3 += sv[0]; st_q3 += sq[0]; break;
-                        }
-                    } else if (cb + lane < p.Cout) {          // BN = 256 with one epilogue group: slabs 4..7 go out per tile
-                        atomicAdd(stats + cb + lane, (double)sv[0]);
-                        atomicAdd(stats + p.Cout + cb + lane, (double)sq[0]);
-                    }
+                    col_s = sv[0]; col_q = sq[0];
+                }
+                if (walk && !valid) {                        // rows outside the image are clipped by the TMA store; zero them for the sums
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = 0.f;
                 }
                 if (p.tma_store) {
                     // one group: two staging slabs used alternately (slab b was last stored two slabs ago);
@@ -744,6 +740,17 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                         else tma_store_4d(staging + (size_t)b * TC_A_BYTES, &mapOut, cb, w0, h0, n);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                    if (walk) {
+                        // column `lane` of rows 32q .. 32q+31 of the staged slab: one 128-byte row per step, the 32 lanes
+                        // read its 32 words (16-byte chunks XOR-swizzled by row & 7), conflict-free
+                        const float* srow = reinterpret_cast<const float*>(staging + (size_t)b * TC_A_BYTES + (size_t)(q * 32) * 128);
+                        const int cq = lane >> 2, cw = lane & 3;
+#pragma unroll 8
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const float o = srow[rr * 32 + (((cq ^ (rr & 7)) << 2) | cw)];
+                            col_s += o; col_q = fmaf(o, o, col_q);
+                        }
+                    }
                     ++sc;
                 } else if (valid) {
                     if (cb + 31 < p.Cout && (p.ldo & 3) == 0) {
@@ -754,6 +761,20 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 #pragma unroll
                         for (int c = 0; c < 32; ++c)
                             if (cb + c < p.Cout) orow[cb + c] = v[c];
+                    }
+                }
+                if (stats) {
+                    const int si = (j / 32 - grp) / ngrp;
+                    if (si < 4) {
+                        switch (si) {
+                            case 0: st_s0 += col_s; st_q0 += col_q; break;
+                            case 1: st_s1 += col_s; st_q1 += col_q; break;
+                            case 2: st_s2 += col_s; st_q2 += col_q; break;
+                            default: st_s3 += col_s; st_q3 += col_q; break;
+                        }
+                    } else if (cb + lane < p.Cout) {          // BN = 256 with one epilogue group: slabs 4..7 go out per tile
+                        atomicAdd(stats + cb + lane, (double)col_s);
+                        atomicAdd(stats + p.Cout + cb + lane, (double)col_q);
                     }
                 }
             }
@@ -818,7 +839,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 //             leader's barrier).  3xTF32 in-kernel split: per CTA, local loads.
 //   ready[s]  3xTF32: leader's only, count 256 = transform threads of both CTAs (peer arrives remotely)
 //   empty[s]  per CTA, count 1, arrival = multicast tcgen05.commit of the leader's MMA thread
-//   acc_full[2]  per CTA, count 1, multicast commit;   acc_empty[2]  leader's only, count 256
+//   acc_full[2]  per CTA, count 1, multicast commit;   acc_empty[2]  leader's only, count 256 per epilogue group
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -910,7 +931,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 256); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 256); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 256 * (p.a_inkernel ? 1 : 2)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc2(&tmem_base_slot, tmem_cols);
@@ -996,13 +1017,33 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 if (ok) umma2_commit_mc(&acc_full[set]);
             }
         }
-    } else if (warp < 6) {
-        // ================= epilogue (both CTAs, own 128 rows) =================
+    } else if (warp < 6 || !p.a_inkernel) {
+        // ================= epilogue (both CTAs, own 128 rows; two 4-warp groups on alternate slabs like the
+        // persistent kernel when there is no operand transform) =================
+        const int grp = warp >= 6 ? 1 : 0;
+        const int ngrp = p.a_inkernel ? 1 : 2;
         const int q = warp & 3;
         const int r = q * 32 + lane;
-        const int et = threadIdx.x - 64;
+        const int et = threadIdx.x - 64 - 128 * grp;
+        const int barid = 1 + grp;
         uint32_t tcount = 0, sc = 0;
         const float osc = p.out_scale * (oscale_ptr ? __ldg(oscale_ptr) : 1.f);
+        float st_s0 = 0.f, st_s1 = 0.f, st_s2 = 0.f, st_s3 = 0.f, st_q0 = 0.f, st_q1 = 0.f, st_q2 = 0.f, st_q3 = 0.f;
+        int st_n0 = -1;
+        auto flush_stats = [&]() {
+            if (stats && st_n0 >= 0) {
+                const float ss[4] = {st_s0, st_s1, st_s2, st_s3}, qq[4] = {st_q0, st_q1, st_q2, st_q3};
+#pragma unroll
+                for (int si = 0; si < 4; ++si) {
+                    const int cbf = st_n0 + 32 * (grp + si * ngrp) + lane;
+                    if (32 * (grp + si * ngrp) < p.BN && cbf < p.Cout && (ss[si] != 0.f || qq[si] != 0.f)) {
+                        atomicAdd(stats + cbf, (double)ss[si]);
+                        atomicAdd(stats + p.Cout + cbf, (double)qq[si]);
+                    }
+                }
+            }
+            st_s0 = st_s1 = st_s2 = st_s3 = st_q0 = st_q1 = st_q2 = st_q3 = 0.f;
+        };
         bool ok = true;
         for (int work = cid; work < p.total_tiles && ok; work += nclusters, ++tcount) {
             const uint32_t set = tcount & 1u, aph = (tcount >> 1) & 1u;
@@ -1011,13 +1052,14 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             tc_fence_after();
             int n0, w0, h0, n;
             tc_pair_coords(p, work, rank, n0, w0, h0, n);
+            if (n0 != st_n0) { flush_stats(); st_n0 = n0; }
             const int hy = r / p.BW, wx = r - hy * p.BW;
             const int oy = h0 + hy, ox = w0 + wx;
             const bool valid = n < p.N && hy < p.BH && oy < p.OH && ox < p.OW;
             float* orow = out + ((int64_t)(n * p.outH + oy * p.out_mul + p.out_offy) * p.outW + ox * p.out_mul + p.out_offx) * p.ldo;
             const int used = iters < p.nacc ? iters : p.nacc;
             const uint32_t tbase = tmem_d + set * set_cols + ((uint32_t)(q * 32) << 16);
-            for (int j = 0; j < p.BN; j += 32) {
+            for (int j = 32 * grp; j < p.BN; j += 32 * ngrp) {
                 const int cb = n0 + j;
                 if (cb >= p.Cout || n >= p.N) break;
                 float v[32];
@@ -1036,7 +1078,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
                     for (int c = 0; c < 32; ++c) if (cb + c < p.Cout) v[c] += __ldg(bias + cb + c);
                 }
-                if (stats) {
+                const bool walk = stats && p.stats_smem && p.tma_store;
+                float col_s = 0.f, col_q = 0.f;
+                if (stats && !walk) {
                     float sv[32], sq[32];
 #pragma unroll
                     for (int c = 0; c < 32; ++c) { const float o = valid ? v[c] : 0.f; sv[c] = o; sq[c] = o * o; }
@@ -1052,25 +1096,38 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                             sq[i] = (up ? sq[i + off] : sq[i]) + q_recv;
                         }
                     }
-                    if (cb + lane < p.Cout) {
-                        atomicAdd(stats + cb + lane, (double)sv[0]);
-                        atomicAdd(stats + p.Cout + cb + lane, (double)sq[0]);
-                    }
+                    col_s = sv[0]; col_q = sq[0];
+                }
+                if (walk && !valid) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = 0.f;
                 }
                 if (p.tma_store) {
-                    const uint32_t b = sc & 1u;
-                    if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const uint32_t b = ngrp == 1 ? (sc & 1u) : (uint32_t)grp;
+                    if (et == 0) {
+                        if (ngrp == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
                     float4* dst = reinterpret_cast<float4*>(staging + (size_t)b * TC_A_BYTES + (size_t)r * 128);
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
                         dst[c ^ (r & 7)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
                     if (et == 0) {
                         if (p.out_acc) tma_reduce_add_4d(staging + (size_t)b * TC_A_BYTES, &mapOut, cb, w0, h0, n);
                         else tma_store_4d(staging + (size_t)b * TC_A_BYTES, &mapOut, cb, w0, h0, n);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    if (walk) {
+                        const float* srow = reinterpret_cast<const float*>(staging + (size_t)b * TC_A_BYTES + (size_t)(q * 32) * 128);
+                        const int cq = lane >> 2, cw = lane & 3;
+#pragma unroll 8
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const float o = srow[rr * 32 + (((cq ^ (rr & 7)) << 2) | cw)];
+                            col_s += o; col_q = fmaf(o, o, col_q);
+                        }
                     }
                     ++sc;
                 } else if (valid) {
@@ -1084,11 +1141,26 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                             if (cb + c < p.Cout) orow[cb + c] = v[c];
                     }
                 }
+                if (stats) {
+                    const int si = (j / 32 - grp) / ngrp;
+                    if (si < 4) {
+                        switch (si) {
+                            case 0: st_s0 += col_s; st_q0 += col_q; break;
+                            case 1: st_s1 += col_s; st_q1 += col_q; break;
+                            case 2: st_s2 += col_s; st_q2 += col_q; break;
+                            default: st_s3 += col_s; st_q3 += col_q; break;
+                        }
+                    } else if (cb + lane < p.Cout) {
+                        atomicAdd(stats + cb + lane, (double)col_s);
+                        atomicAdd(stats + p.Cout + cb + lane, (double)col_q);
+                    }
+                }
             }
-            // release this accumulator set to the leader's MMA thread (256 arrivals: both CTAs)
+            // release this accumulator set to the leader's MMA thread (arrivals of both CTAs' epilogue threads)
             tc_fence_before();
             mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[set]), 0));
         }
+        flush_stats();
         if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     } else {
         // ================= operand transform (3xTF32 with raw activations; both CTAs) =================
@@ -1345,6 +1417,9 @@ static int conv_tc_launch_core(const pxl_conv_geom* g, const int* taps, const px
         rc = make_out_map(&mO, out, g->Cout, g->ldo, p.outW, p.outH, p.N, p.BW, p.BH);
         if (rc) p.tma_store = 0;
     }
+    static int cfg_stats_smem = -1;
+    if (cfg_stats_smem < 0) { const char* e = getenv("PXL_TC_STATS_SMEM"); cfg_stats_smem = e ? atoi(e) : 1; }
+    p.stats_smem = cfg_stats_smem;
     p.out_acc = (ext && ext->out_accumulate) ? 1 : 0;
     if (p.out_acc && !(p.tma_store && use_persist)) return PXL_ERR_UNSUPPORTED;      // accumulation exists in the TMA-store epilogues only
     cudaStream_t st = (cudaStream_t)stream;
