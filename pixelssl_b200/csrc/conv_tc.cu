@@ -212,8 +212,44 @@ __device__ __forceinline__ void umma_any(int f16, uint32_t tmem_d, uint64_t ades
     if (f16) umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
     else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
 }
+// One lane of a converged warp (deterministic for a given member mask).  The producer and MMA warps run their loops
+// with all 32 lanes in uniform control flow and predicate only the TMA / tcgen05 instructions with this: addresses
+// and descriptors then live in uniform registers.  A loop entered by `if (lane == 0)` instead costs ~40 SASS
+// instructions per tcgen05.mma (VOTEU / ELECT / R2UR per operand plus integer divisions for the ring indices) and
+// the issuing thread, not the tensor pipe, bounds the kernel (ncu source view, profiles/r02_ncu_l1.conv2_*).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the MMAs of one 128-byte K slice of a stage (4 steps of 32 bytes; hi*hi + lo*hi + hi*lo when the operands are split)
+template <int F16>
+__device__ __forceinline__ void umma_slice(uint32_t acc, uint64_t da, uint64_t db, uint64_t dal, uint64_t dbl,
+                                           uint32_t idesc, uint32_t acc0, bool split3) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (F16) umma_f16(acc, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc0);
+        else umma_tf32(acc, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc0);
+    }
+    if (split3) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (F16) umma_f16(acc, dal + 2 * k, db + 2 * k, idesc, 1u);
+            else umma_tf32(acc, dal + 2 * k, db + 2 * k, idesc, 1u);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (F16) umma_f16(acc, da + 2 * k, dbl + 2 * k, idesc, 1u);
+            else umma_tf32(acc, da + 2 * k, dbl + 2 * k, idesc, 1u);
+        }
+    }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -317,22 +353,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t tmem_d = tmem_base_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            // bytes the TMA unit will deliver per stage: full boxes, OOB parts are zero-filled but counted
-            uint32_t tx = (uint32_t)((p.BW * p.BH * 128 + b_bytes) * (p.nsplit == 3 ? 2 : 1));
-            if (p.a_inkernel) tx -= (uint32_t)(p.BW * p.BH * 128);      // no A_lo box: it is produced in shared memory
-            bool ok = true;
-            for (int it = 0; it < iters && ok; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                ok = mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 1);
-                if (!ok) break;
-                const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * p.kc;
-                uint8_t* sa = smem + (size_t)s * stage_bytes;
+        // ================= TMA producer (whole warp converged, TMA under elect.sync) =================
+        // bytes the TMA unit will deliver per stage: full boxes, OOB parts are zero-filled but counted
+        uint32_t tx = (uint32_t)((p.BW * p.BH * 128 + b_bytes) * (p.nsplit == 3 ? 2 : 1));
+        if (p.a_inkernel) tx -= (uint32_t)(p.BW * p.BH * 128);      // no A_lo box: it is produced in shared memory
+        uint32_t s = 0, ph = 0;
+        int tap = 0, c0 = 0;
+        for (int it = 0; it < iters; ++it) {
+            if (!__all_sync(0xffffffffu, mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 1))) break;
+            uint8_t* sa = smem + (size_t)s * stage_bytes;
+            const int ax = w0 * p.in_mul + p.dx[tap], ay = h0 * p.in_mul + p.dy[tap];
+            const int bk = p.widx[tap] * p.Cin + c0;
+            if (elect_one()) {
                 mbar_expect_tx(&full_bar[s], tx);
-                const int ax = w0 * p.in_mul + p.dx[tap], ay = h0 * p.in_mul + p.dy[tap];
-                const int bk = p.widx[tap] * p.Cin + c0;
                 tma_load_4d(sa, &mapA, &full_bar[s], c0, ax, ay, n);
                 tma_load_2d(sa + TC_A_BYTES, &mapB, &full_bar[s], bk, n0);
                 if (p.nsplit == 3) {
@@ -340,34 +373,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     tma_load_2d(sa + per_op + TC_A_BYTES, &mapBlo, &full_bar[s], bk, n0);
                 }
             }
+            __syncwarp();
+            c0 += p.kc; if (c0 >= p.Cin) { c0 = 0; ++tap; }
+            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
-            const uint32_t idesc = p.f16 ? f16_idesc(p.BN) : tf32_idesc(p.BN);
-            bool ok = true;
-            for (int it = 0; it < iters && ok; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                ok = mbar_wait(p.a_inkernel ? &ready_bar[s] : &full_bar[s], ph, err_flag, 2);
-                if (!ok) break;
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t da = kmajor_sw128_desc(sa), db = kmajor_sw128_desc(sa + TC_A_BYTES);
-                const uint32_t acc = tmem_d + (uint32_t)(it % p.nacc) * acc_cols;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)      // UMMA_K = 8 tf32 = 32 B: advance the start address by 2 x 16 B
-                    umma_any(p.f16, acc, da + 2 * k, db + 2 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
-                if (p.nsplit == 3) {
-                    const uint64_t dal = kmajor_sw128_desc(sa + per_op), dbl = kmajor_sw128_desc(sa + per_op + TC_A_BYTES);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_any(p.f16, acc, dal + 2 * k, db + 2 * k, idesc, 1);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_any(p.f16, acc, da + 2 * k, dbl + 2 * k, idesc, 1);
-                }
+        // ================= MMA issuer (whole warp converged, tcgen05 under elect.sync) =================
+        const uint32_t idesc = p.f16 ? f16_idesc(p.BN) : tf32_idesc(p.BN);
+        const uint32_t smem_base = smem_u32(smem);
+        uint32_t s = 0, ph = 0, a = 0;
+        for (int it = 0; it < iters; ++it) {
+            if (!__all_sync(0xffffffffu, mbar_wait(p.a_inkernel ? &ready_bar[s] : &full_bar[s], ph, err_flag, 2))) break;
+            tc_fence_after();
+            const uint32_t sa = smem_base + s * (uint32_t)stage_bytes;
+            const uint64_t da = kmajor_sw128_desc(sa), db = kmajor_sw128_desc(sa + TC_A_BYTES);
+            const uint64_t dal = kmajor_sw128_desc(sa + per_op), dbl = kmajor_sw128_desc(sa + per_op + TC_A_BYTES);
+            const uint32_t acc = tmem_d + a * acc_cols;
+            const uint32_t acc0 = it >= p.nacc ? 1u : 0u;
+            if (elect_one()) {
+                if (p.f16) umma_slice<1>(acc, da, db, dal, dbl, idesc, acc0, p.nsplit == 3);
+                else umma_slice<0>(acc, da, db, dal, dbl, idesc, acc0, p.nsplit == 3);
                 umma_commit(&empty_bar[s]);      // frees the smem slot once these MMAs have read it
+                if (it == iters - 1) umma_commit(&acc_bar);       // accumulator complete -> epilogue
             }
-            if (ok) umma_commit(&acc_bar);       // accumulator complete -> epilogue
+            __syncwarp();
+            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+            if (++a == (uint32_t)p.nacc) a = 0;
         }
     } else {
         // ================= epilogue: TMEM -> registers -> global (NHWC rows) =================
@@ -565,25 +596,23 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     const uint32_t tmem_d = tmem_base_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            uint32_t tx = (uint32_t)((p.BW * p.BH * 128 + b_bytes) * (p.nsplit == 3 ? 2 : 1));
-            if (p.a_inkernel) tx -= (uint32_t)(p.BW * p.BH * 128);
-            uint32_t gs = 0;
-            bool ok = true;
-            for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
-                int n0, w0, h0, n;
-                tc_tile_coords(p, tile, n0, w0, h0, n);
-                for (int it = 0; it < iters; ++it, ++gs) {
-                    const int s = gs % p.stages;
-                    const uint32_t ph = (gs / p.stages) & 1u;
-                    ok = mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 1);
-                    if (!ok) break;
-                    const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * p.kc;
-                    uint8_t* sa = smem + (size_t)s * stage_bytes;
+        // ================= TMA producer (whole warp converged, TMA under elect.sync) =================
+        uint32_t tx = (uint32_t)((p.BW * p.BH * 128 + b_bytes) * (p.nsplit == 3 ? 2 : 1));
+        if (p.a_inkernel) tx -= (uint32_t)(p.BW * p.BH * 128);
+        uint32_t s = 0, ph = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+            int n0, w0, h0, n;
+            tc_tile_coords(p, tile, n0, w0, h0, n);
+            int tap = 0, c0 = 0;
+            for (int it = 0; it < iters; ++it) {
+                ok = __all_sync(0xffffffffu, mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 1));
+                if (!ok) break;
+                uint8_t* sa = smem + (size_t)s * stage_bytes;
+                const int ax = w0 * p.in_mul + p.dx[tap], ay = h0 * p.in_mul + p.dy[tap];
+                const int bk = p.widx[tap] * p.Cin + c0;
+                if (elect_one()) {
                     mbar_expect_tx(&full_bar[s], tx);
-                    const int ax = w0 * p.in_mul + p.dx[tap], ay = h0 * p.in_mul + p.dy[tap];
-                    const int bk = p.widx[tap] * p.Cin + c0;
                     tma_load_4d(sa, &mapA, &full_bar[s], c0, ax, ay, n);
                     tma_load_2d(sa + TC_A_BYTES, &mapB, &full_bar[s], bk, n0);
                     if (p.nsplit == 3) {
@@ -591,42 +620,42 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                         tma_load_2d(sa + per_op + TC_A_BYTES, &mapBlo, &full_bar[s], bk, n0);
                     }
                 }
+                __syncwarp();
+                c0 += p.kc; if (c0 >= p.Cin) { c0 = 0; ++tap; }
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = p.f16 ? f16_idesc(p.BN) : tf32_idesc(p.BN);
-            uint32_t gs = 0, tcount = 0;
-            bool ok = true;
-            for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++tcount) {
-                const uint32_t set = tcount & 1u, aph = (tcount >> 1) & 1u;
-                ok = mbar_wait(&acc_empty[set], aph ^ 1u, err_flag, 5);       // epilogue drained this set
+        // ================= MMA issuer (whole warp converged, tcgen05 under elect.sync) =================
+        const uint32_t idesc = p.f16 ? f16_idesc(p.BN) : tf32_idesc(p.BN);
+        const uint32_t smem_base = smem_u32(smem);
+        uint32_t s = 0, ph = 0, tcount = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++tcount) {
+            const uint32_t set = tcount & 1u, aph = (tcount >> 1) & 1u;
+            ok = __all_sync(0xffffffffu, mbar_wait(&acc_empty[set], aph ^ 1u, err_flag, 5));       // epilogue drained this set
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t set_base = tmem_d + set * set_cols;
+            uint32_t a = 0;
+            for (int it = 0; it < iters; ++it) {
+                ok = __all_sync(0xffffffffu, mbar_wait(p.a_inkernel ? &ready_bar[s] : &full_bar[s], ph, err_flag, 2));
                 if (!ok) break;
                 tc_fence_after();
-                const uint32_t set_base = tmem_d + set * set_cols;
-                for (int it = 0; it < iters; ++it, ++gs) {
-                    const int s = gs % p.stages;
-                    const uint32_t ph = (gs / p.stages) & 1u;
-                    ok = mbar_wait(p.a_inkernel ? &ready_bar[s] : &full_bar[s], ph, err_flag, 2);
-                    if (!ok) break;
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint64_t da = kmajor_sw128_desc(sa), db = kmajor_sw128_desc(sa + TC_A_BYTES);
-                    const uint32_t acc = set_base + (uint32_t)(it % p.nacc) * acc_cols;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_any(p.f16, acc, da + 2 * k, db + 2 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
-                    if (p.nsplit == 3) {
-                        const uint64_t dal = kmajor_sw128_desc(sa + per_op), dbl = kmajor_sw128_desc(sa + per_op + TC_A_BYTES);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_any(p.f16, acc, dal + 2 * k, db + 2 * k, idesc, 1);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_any(p.f16, acc, da + 2 * k, dbl + 2 * k, idesc, 1);
-                    }
+                const uint32_t sa = smem_base + s * (uint32_t)stage_bytes;
+                const uint64_t da = kmajor_sw128_desc(sa), db = kmajor_sw128_desc(sa + TC_A_BYTES);
+                const uint64_t dal = kmajor_sw128_desc(sa + per_op), dbl = kmajor_sw128_desc(sa + per_op + TC_A_BYTES);
+                const uint32_t acc = set_base + a * acc_cols;
+                const uint32_t acc0 = it >= p.nacc ? 1u : 0u;
+                if (elect_one()) {
+                    if (p.f16) umma_slice<1>(acc, da, db, dal, dbl, idesc, acc0, p.nsplit == 3);
+                    else umma_slice<0>(acc, da, db, dal, dbl, idesc, acc0, p.nsplit == 3);
                     umma_commit(&empty_bar[s]);
+                    if (it == iters - 1) umma_commit(&acc_full[set]);
                 }
-                if (ok) umma_commit(&acc_full[set]);
+                __syncwarp();
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+                if (++a == (uint32_t)p.nacc) a = 0;
             }
         }
     } else if (warp < 6 || !p.a_inkernel) {
@@ -891,6 +920,27 @@ __device__ __forceinline__ void umma2_any(int f16, uint32_t tmem_d, uint64_t ade
     if (f16) umma2_f16(tmem_d, adesc, bdesc, idesc, accumulate);
     else umma2_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
 }
+template <int F16>
+__device__ __forceinline__ void umma2_slice(uint32_t acc, uint64_t da, uint64_t db, uint64_t dal, uint64_t dbl,
+                                            uint32_t idesc, uint32_t acc0, bool split3) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (F16) umma2_f16(acc, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc0);
+        else umma2_tf32(acc, da + 2 * k, db + 2 * k, idesc, k ? 1u : acc0);
+    }
+    if (split3) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (F16) umma2_f16(acc, dal + 2 * k, db + 2 * k, idesc, 1u);
+            else umma2_tf32(acc, dal + 2 * k, db + 2 * k, idesc, 1u);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (F16) umma2_f16(acc, da + 2 * k, dbl + 2 * k, idesc, 1u);
+            else umma2_tf32(acc, da + 2 * k, dbl + 2 * k, idesc, 1u);
+        }
+    }
+}
 __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
@@ -941,25 +991,24 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const uint32_t tmem_d = tmem_base_slot;
 
     if (warp == 0) {
-        // ================= TMA producer (both CTAs) =================
-        if (lane == 0) {
-            const uint32_t my_bytes = (uint32_t)((p.BW * p.BH * 128 + b_bytes) * (p.nsplit == 3 ? 2 : 1)) -
-                                      (p.a_inkernel ? (uint32_t)(p.BW * p.BH * 128) : 0u);
-            uint32_t gs = 0;
-            bool ok = true;
-            for (int work = cid; work < p.total_tiles && ok; work += nclusters) {
-                int n0, w0, h0, n;
-                tc_pair_coords(p, work, rank, n0, w0, h0, n);
-                const int brow = n0 + (int)rank * bh_rows;
-                for (int it = 0; it < iters; ++it, ++gs) {
-                    const int s = gs % p.stages;
-                    const uint32_t ph = (gs / p.stages) & 1u;
-                    ok = mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 1);
-                    if (!ok) break;
-                    const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * p.kc;
-                    uint8_t* sa = smem + (size_t)s * stage_bytes;
-                    const int ax = w0 * p.in_mul + p.dx[tap], ay = h0 * p.in_mul + p.dy[tap];
-                    const int bk = p.widx[tap] * p.Cin + c0;
+        // ================= TMA producer (both CTAs; whole warp converged, TMA under elect.sync) =================
+        const uint32_t my_bytes = (uint32_t)((p.BW * p.BH * 128 + b_bytes) * (p.nsplit == 3 ? 2 : 1)) -
+                                  (p.a_inkernel ? (uint32_t)(p.BW * p.BH * 128) : 0u);
+        uint32_t s = 0, ph = 0;
+        bool ok = true;
+        for (int work = cid; work < p.total_tiles && ok; work += nclusters) {
+            int n0, w0, h0, n;
+            tc_pair_coords(p, work, rank, n0, w0, h0, n);
+            const int brow = n0 + (int)rank * bh_rows;
+            int tap = 0, c0 = 0;
+            for (int it = 0; it < iters; ++it) {
+                ok = __all_sync(0xffffffffu, mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 1));
+                if (!ok) break;
+                uint8_t* sa = smem + (size_t)s * stage_bytes;
+                const int ax = w0 * p.in_mul + p.dx[tap], ay = h0 * p.in_mul + p.dy[tap];
+                const int bk = p.widx[tap] * p.Cin + c0;
+                const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+                if (elect_one()) {
                     if (p.a_inkernel) {
                         // local barrier: this CTA's transform warps wait for this CTA's bytes
                         mbar_expect_tx(&full_bar[s], my_bytes);
@@ -968,7 +1017,6 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         tma_load_2d(sa + per_op + TC_A_BYTES, &mapBlo, &full_bar[s], bk, brow);
                     } else {
                         // the leader's barrier collects the bytes of both CTAs
-                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
                         if (leader) mbar_expect_tx(&full_bar[s], 2u * my_bytes);
                         tma2_load_4d(sa, &mapA, fb, c0, ax, ay, n);
                         tma2_load_2d(sa + TC_A_BYTES, &mapB, fb, bk, brow);
@@ -978,43 +1026,45 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         }
                     }
                 }
+                __syncwarp();
+                c0 += p.kc; if (c0 >= p.Cin) { c0 = 0; ++tap; }
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (leader CTA, one thread) =================
-        if (leader && lane == 0) {
+        // ================= MMA issuer (leader CTA; whole warp converged, tcgen05 under elect.sync) =================
+        if (leader) {
             // M = 256 (bits 24..28 = M >> 4), N = BN
             const uint32_t idesc = (1u << 4) | (p.f16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-            uint32_t gs = 0, tcount = 0;
+            const uint32_t smem_base = smem_u32(smem);
+            uint32_t s = 0, ph = 0, tcount = 0;
             bool ok = true;
             for (int work = cid; work < p.total_tiles && ok; work += nclusters, ++tcount) {
                 const uint32_t set = tcount & 1u, aph = (tcount >> 1) & 1u;
-                ok = mbar_wait_cluster(&acc_empty[set], aph ^ 1u, err_flag, 5);
+                ok = __all_sync(0xffffffffu, mbar_wait_cluster(&acc_empty[set], aph ^ 1u, err_flag, 5));
                 if (!ok) break;
                 tc_fence_after();
                 const uint32_t set_base = tmem_d + set * set_cols;
-                for (int it = 0; it < iters; ++it, ++gs) {
-                    const int s = gs % p.stages;
-                    const uint32_t ph = (gs / p.stages) & 1u;
-                    ok = mbar_wait_cluster(p.a_inkernel ? &ready_bar[s] : &full_bar[s], ph, err_flag, 2);
+                uint32_t a = 0;
+                for (int it = 0; it < iters; ++it) {
+                    ok = __all_sync(0xffffffffu, mbar_wait_cluster(p.a_inkernel ? &ready_bar[s] : &full_bar[s], ph, err_flag, 2));
                     if (!ok) break;
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t sa = smem_base + s * (uint32_t)stage_bytes;
                     const uint64_t da = kmajor_sw128_desc(sa), db = kmajor_sw128_desc(sa + TC_A_BYTES);
-                    const uint32_t acc = set_base + (uint32_t)(it % p.nacc) * acc_cols;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma2_any(p.f16, acc, da + 2 * k, db + 2 * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
-                    if (p.nsplit == 3) {
-                        const uint64_t dal = kmajor_sw128_desc(sa + per_op), dbl = kmajor_sw128_desc(sa + per_op + TC_A_BYTES);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma2_any(p.f16, acc, dal + 2 * k, db + 2 * k, idesc, 1);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma2_any(p.f16, acc, da + 2 * k, dbl + 2 * k, idesc, 1);
+                    const uint64_t dal = kmajor_sw128_desc(sa + per_op), dbl = kmajor_sw128_desc(sa + per_op + TC_A_BYTES);
+                    const uint32_t acc = set_base + a * acc_cols;
+                    const uint32_t acc0 = it >= p.nacc ? 1u : 0u;
+                    if (elect_one()) {
+                        if (p.f16) umma2_slice<1>(acc, da, db, dal, dbl, idesc, acc0, p.nsplit == 3);
+                        else umma2_slice<0>(acc, da, db, dal, dbl, idesc, acc0, p.nsplit == 3);
+                        umma2_commit_mc(&empty_bar[s]);          // frees the slot in both CTAs
+                        if (it == iters - 1) umma2_commit_mc(&acc_full[set]);
                     }
-                    umma2_commit_mc(&empty_bar[s]);          // frees the slot in both CTAs
+                    __syncwarp();
+                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+                    if (++a == (uint32_t)p.nacc) a = 0;
                 }
-                if (ok) umma2_commit_mc(&acc_full[set]);
             }
         }
     } else if (warp < 6 || !p.a_inkernel) {
@@ -1596,22 +1646,20 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
 
     if (iters > 0) {
         if (warp == 0) {
-            if (lane == 0) {
-                const uint32_t box_bytes = (uint32_t)(p.rows * 128);
-                const uint32_t tx = box_bytes * (uint32_t)(nsA + nsB) * ((p.nsplit == 3 && !p.inkernel) ? 2u : 1u);
-                const int tdy = p.dy[tap], tdx = p.dx[tap];
-                bool ok = true;
-                for (int it = 0; it < iters && ok; ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                    ok = mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 11);
-                    if (!ok) break;
-                    const int kt = kt0 + it;
-                    const int tw = kt % p.tilesW, th = (kt / p.tilesW) % p.tilesH, n = kt / (p.tilesW * p.tilesH);
-                    const int w0 = tw * p.BW, h0 = th * p.BH;
-                    uint8_t* sa = smem + (size_t)s * stage_bytes;
+            // TMA producer: whole warp converged, TMA under elect.sync
+            const uint32_t box_bytes = (uint32_t)(p.rows * 128);
+            const int nparts = (p.nsplit == 3 && !p.inkernel) ? 2 : 1;
+            const uint32_t tx = box_bytes * (uint32_t)(nsA + nsB) * (uint32_t)nparts;
+            const int tdy = p.dy[tap], tdx = p.dx[tap];
+            int tw = kt0 % p.tilesW, th = (kt0 / p.tilesW) % p.tilesH, n = kt0 / (p.tilesW * p.tilesH);
+            uint32_t s = 0, ph = 0;
+            for (int it = 0; it < iters; ++it) {
+                if (!__all_sync(0xffffffffu, mbar_wait(&empty_bar[s], ph ^ 1u, err_flag, 11))) break;
+                const int w0 = tw * p.BW, h0 = th * p.BH;
+                uint8_t* sa = smem + (size_t)s * stage_bytes;
+                if (elect_one()) {
                     mbar_expect_tx(&full_bar[s], tx);
-                    for (int part = 0; part < ((p.nsplit == 3 && !p.inkernel) ? 2 : 1); ++part) {
+                    for (int part = 0; part < nparts; ++part) {
                         uint8_t* base = sa + (size_t)part * per_op;
                         const CUtensorMap* mdy = part ? &mapDyLo : &mapDy;
                         const CUtensorMap* mx = part ? &mapXLo : &mapX;
@@ -1622,37 +1670,55 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
                                         w0 * p.mul + tdx, h0 * p.mul + tdy, n);
                     }
                 }
+                __syncwarp();
+                if (++tw == p.tilesW) { tw = 0; if (++th == p.tilesH) { th = 0; ++n; } }
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
             }
         } else if (warp == 1) {
-            if (lane == 0) {
-                // D fp32, A/B tf32 or fp16, both MN-major (bits 15,16), M = 128, N = BN
-                const uint32_t idesc = (p.f16 ? f16_idesc(p.BN) : tf32_idesc(p.BN)) | (1u << 15) | (1u << 16);
-                const int krows = p.f16 ? 16 : 8;                 // pixel rows one MMA consumes
-                const int kmma = p.rows_alloc / krows;
-                const uint64_t kstep = (uint64_t)(krows * 128 / 16);   // descriptor start-address advance per MMA
-                bool ok = true;
-                for (int it = 0; it < iters && ok; ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                    ok = mbar_wait(p.inkernel ? &ready_bar[s] : &full_bar[s], ph, err_flag, 12);
-                    if (!ok) break;
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint32_t acc = tmem_d + (uint32_t)(it % p.nacc) * acc_cols;
-                    const uint32_t sb = sa + (uint32_t)(slabsA * slab_bytes);
-                    const uint64_t da = p.f16 ? mnmajor_sw128_f16_desc(sa, (uint32_t)slab_bytes) : mnmajor_sw128_desc(sa, (uint32_t)slab_bytes);
-                    const uint64_t db = p.f16 ? mnmajor_sw128_f16_desc(sb, (uint32_t)slab_bytes) : mnmajor_sw128_desc(sb, (uint32_t)slab_bytes);
-                    for (int k = 0; k < kmma; ++k)
-                        umma_any(p.f16, acc, da + kstep * k, db + kstep * k, idesc, (it >= p.nacc || k != 0) ? 1u : 0u);
-                    if (p.nsplit == 3) {
-                        const uint64_t dal = p.f16 ? mnmajor_sw128_f16_desc(sa + per_op, (uint32_t)slab_bytes) : mnmajor_sw128_desc(sa + per_op, (uint32_t)slab_bytes);
-                        const uint64_t dbl = p.f16 ? mnmajor_sw128_f16_desc(sb + per_op, (uint32_t)slab_bytes) : mnmajor_sw128_desc(sb + per_op, (uint32_t)slab_bytes);
-                        for (int k = 0; k < kmma; ++k) umma_any(p.f16, acc, dal + kstep * k, db + kstep * k, idesc, 1);
-                        for (int k = 0; k < kmma; ++k) umma_any(p.f16, acc, da + kstep * k, dbl + kstep * k, idesc, 1);
+            // MMA issuer: whole warp converged, tcgen05 under elect.sync
+            // D fp32, A/B tf32 or fp16, both MN-major (bits 15,16), M = 128, N = BN
+            const uint32_t idesc = (p.f16 ? f16_idesc(p.BN) : tf32_idesc(p.BN)) | (1u << 15) | (1u << 16);
+            const int krows = p.f16 ? 16 : 8;                 // pixel rows one MMA consumes
+            const int kmma = p.rows_alloc / krows;
+            const uint64_t kstep = (uint64_t)(krows * 128 / 16);   // descriptor start-address advance per MMA
+            const uint32_t smem_base = smem_u32(smem);
+            const uint32_t offB = (uint32_t)(slabsA * slab_bytes);
+            uint32_t s = 0, ph = 0, a = 0;
+            for (int it = 0; it < iters; ++it) {
+                if (!__all_sync(0xffffffffu, mbar_wait(p.inkernel ? &ready_bar[s] : &full_bar[s], ph, err_flag, 12))) break;
+                tc_fence_after();
+                const uint32_t sa = smem_base + s * (uint32_t)stage_bytes;
+                const uint32_t sb = sa + offB;
+                const uint32_t acc = tmem_d + a * acc_cols;
+                const uint32_t acc0 = it >= p.nacc ? 1u : 0u;
+                uint64_t da, db, dal, dbl;
+                if (p.f16) {
+                    da = mnmajor_sw128_f16_desc(sa, (uint32_t)slab_bytes); db = mnmajor_sw128_f16_desc(sb, (uint32_t)slab_bytes);
+                    dal = mnmajor_sw128_f16_desc(sa + per_op, (uint32_t)slab_bytes); dbl = mnmajor_sw128_f16_desc(sb + per_op, (uint32_t)slab_bytes);
+                } else {
+                    da = mnmajor_sw128_desc(sa, (uint32_t)slab_bytes); db = mnmajor_sw128_desc(sb, (uint32_t)slab_bytes);
+                    dal = mnmajor_sw128_desc(sa + per_op, (uint32_t)slab_bytes); dbl = mnmajor_sw128_desc(sb + per_op, (uint32_t)slab_bytes);
+                }
+                if (elect_one()) {
+                    if (p.f16) {
+                        for (int k = 0; k < kmma; ++k) umma_f16(acc, da + kstep * k, db + kstep * k, idesc, k ? 1u : acc0);
+                        if (p.nsplit == 3) {
+                            for (int k = 0; k < kmma; ++k) umma_f16(acc, dal + kstep * k, db + kstep * k, idesc, 1u);
+                            for (int k = 0; k < kmma; ++k) umma_f16(acc, da + kstep * k, dbl + kstep * k, idesc, 1u);
+                        }
+                    } else {
+                        for (int k = 0; k < kmma; ++k) umma_tf32(acc, da + kstep * k, db + kstep * k, idesc, k ? 1u : acc0);
+                        if (p.nsplit == 3) {
+                            for (int k = 0; k < kmma; ++k) umma_tf32(acc, dal + kstep * k, db + kstep * k, idesc, 1u);
+                            for (int k = 0; k < kmma; ++k) umma_tf32(acc, da + kstep * k, dbl + kstep * k, idesc, 1u);
+                        }
                     }
                     umma_commit(&empty_bar[s]);
+                    if (it == iters - 1) umma_commit(&acc_bar);
                 }
-                if (ok) umma_commit(&acc_bar);
+                __syncwarp();
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+                if (++a == (uint32_t)p.nacc) a = 0;
             }
         } else {
             const int q = warp & 3;

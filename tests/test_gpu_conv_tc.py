@@ -197,7 +197,8 @@ def test_tf32_operand_rounding_probe(ops):
 
 
 @pytest.mark.parametrize('precision', [1, 2, 3, 4])
-@pytest.mark.parametrize('shape', [(2, 64, 33, 33, 256, 1), (2, 128, 17, 19, 64, 3), (1, 64, 129, 129, 64, 3)])
+@pytest.mark.parametrize('shape', [(2, 64, 33, 33, 256, 1), (2, 128, 17, 19, 64, 3), (1, 64, 129, 129, 64, 3),
+                                   (4, 256, 40, 40, 512, 1), (16, 256, 33, 33, 256, 3)])
 def test_bn_statistics_fused_in_epilogue(ops, shape, precision):
     """The conv epilogue's per-channel sum / sum-of-squares equal those of the tensor it stored."""
     N, Cin, H, W, Cout, k = shape

@@ -77,12 +77,13 @@ def main():
             w = ops.h16_split(w, ops.H16_W_SCALE, prec == 3)
         flop = 2.0 * N * H * W * Cin * Cout * nt
         line = '%-30s' % name
-        if what in ('fwd', 'both'):
+        if what in ('fwd', 'both', 'fwdstats'):
             it = [0]
+            st = torch.zeros(2 * Cout, dtype=torch.float64, device='cuda') if what == 'fwdstats' else None
 
             def f():
                 it[0] += 1
-                ops.conv_raw(xs[it[0] % 3], w, None, taps, N, H, W, Cin, H, W, Cout, Cout, 1, 1, out=out, precision=prec)
+                ops.conv_raw(xs[it[0] % 3], w, None, taps, N, H, W, Cin, H, W, Cout, Cout, 1, 1, out=out, precision=prec, bn_stats=st)
             us = time_fn(f)
             tot_f += us * mult
             line += '  fwd %8.1f us %7.1f TF/s' % (us, flop / us / 1e6)

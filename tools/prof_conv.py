@@ -1,5 +1,5 @@
 """A few launches of one convolution shape for `ncu --set full -k regex:<kernel> -s <skip> -c 1`.
-    python tools/prof_conv.py f16x3 fwd|wgrad <shape index of tools/bench_conv.SHAPES>"""
+    python tools/prof_conv.py f16x3 fwd|fwdstats|wgrad <shape index of tools/bench_conv.SHAPES>"""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -22,8 +22,9 @@ if prec >= 3:
     w = ops.h16_split(w, ops.H16_W_SCALE, prec == 3)
     dy = ops.h16_split(dy, None, prec == 3)
 for _ in range(5):
-    if what == 'fwd':
-        ops.conv_raw(x, w, None, taps, N, H, W, Cin, H, W, Cout, Cout, 1, 1, out=out, precision=prec)
+    if what in ('fwd', 'fwdstats'):
+        st = torch.zeros(2 * Cout, dtype=torch.float64, device='cuda') if what == 'fwdstats' else None
+        ops.conv_raw(x, w, None, taps, N, H, W, Cin, H, W, Cout, Cout, 1, 1, out=out, precision=prec, bn_stats=st)
     else:
         ops.conv_wgrad_raw(x, dy, dw, taps, N, H, W, Cin, H, W, Cout, Cout, 1, 1, precision=prec)
 torch.cuda.synchronize()
