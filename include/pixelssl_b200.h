@@ -141,20 +141,24 @@ int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, const float* 
  * (y / dx NULL), writes it as the fp16 pair the next tcgen05 convolution reads, so the pair costs no extra trip
  * through HBM.  hi / lo: __half NHWC planes, lo nullable.  Forward: fixed scale `hscale`.  Backward: the reduce
  * launch leaves absmax(dz) in slot[2] (DEVICE float[4], zeroed), the dx launch derives the power-of-two scale from
- * it, max|gamma*invstd| and target_log2, and stores s / 1/s in slot[0] / slot[1]. */
+ * it, max|gamma*invstd| and target_log2, and stores s / 1/s in slot[0] / slot[1].
+ * relu_mask (nullable, rows*C/4 bytes): the forward launches store the sign bits of the result (bit k of byte i =
+ * element 4i+k > 0); the backward launches then take the ReLU mask from it instead of re-reading the fp32 result
+ * (0.25 B/element instead of 4). */
 int pxl_bn_apply_h16(const float* x, const float* scale, const float* shift, const float* residual, int relu, float* y,
-                     int64_t rows, int C, void* hi, void* lo, float hscale, void* stream);
+                     int64_t rows, int C, void* hi, void* lo, float hscale, void* relu_mask, void* stream);
 int pxl_bn_finalize_apply_h16(const float* x, const double* sums, double count, const float* gamma, const float* beta,
                               float* running_mean, float* running_var, float momentum, float eps, int clamp_mode,
                               float* mean, float* invstd, float* scale, float* shift, const float* residual, int relu,
-                              float* y, int64_t rows, int C, void* hi, void* lo, float hscale, void* stream);
+                              float* y, int64_t rows, int C, void* hi, void* lo, float hscale, void* relu_mask,
+                              void* stream);
 int pxl_bn_bwd_reduce_h16(const float* x, const float* y, const float* dy, const float* mean, const float* invstd,
                           int relu, int64_t rows, int C, double* dsums, const float* scale, const float* shift,
-                          float* amax_slot, void* stream);
+                          float* amax_slot, const void* relu_mask, void* stream);
 int pxl_bn_bwd_dx_h16(const float* x, const float* y, const float* dy, const float* mean, const float* invstd,
                       const float* gamma, const double* dsums, double count, int relu, float* dx, float* dres,
                       int64_t rows, int C, const float* scale, const float* shift, float* dgamma_acc, float* dbeta_acc,
-                      void* dhi, void* dlo, float* slot, int target_log2, void* stream);
+                      void* dhi, void* dlo, float* slot, int target_log2, const void* relu_mask, void* stream);
 int pxl_bn_bwd_params(const double* dsums, int C, float* dgamma, float* dbeta, int accumulate,
                       void* stream);
 

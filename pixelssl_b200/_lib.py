@@ -52,11 +52,11 @@ SIGNATURES = {
     'pxl_bn_finalize_apply': (c_int, [P, P, c_double, P, P, P, P, c_float, c_float, c_int, P, P, P, P, P, c_int, P, c_int64,
                                       c_int, P]),
     'pxl_bn_bwd_params': (c_int, [P, c_int, P, P, c_int, P]),
-    'pxl_bn_apply_h16': (c_int, [P, P, P, P, c_int, P, c_int64, c_int, P, P, c_float, P]),
+    'pxl_bn_apply_h16': (c_int, [P, P, P, P, c_int, P, c_int64, c_int, P, P, c_float, P, P]),
     'pxl_bn_finalize_apply_h16': (c_int, [P, P, c_double, P, P, P, P, c_float, c_float, c_int, P, P, P, P, P, c_int, P, c_int64,
-                                          c_int, P, P, c_float, P]),
-    'pxl_bn_bwd_reduce_h16': (c_int, [P, P, P, P, P, c_int, c_int64, c_int, P, P, P, P, P]),
-    'pxl_bn_bwd_dx_h16': (c_int, [P, P, P, P, P, P, P, c_double, c_int, P, P, c_int64, c_int, P, P, P, P, P, P, P, c_int, P]),
+                                          c_int, P, P, c_float, P, P]),
+    'pxl_bn_bwd_reduce_h16': (c_int, [P, P, P, P, P, c_int, c_int64, c_int, P, P, P, P, P, P]),
+    'pxl_bn_bwd_dx_h16': (c_int, [P, P, P, P, P, P, P, c_double, c_int, P, P, c_int64, c_int, P, P, P, P, P, P, P, c_int, P, P]),
     'pxl_maxpool3x3s2_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'pxl_maxpool3x3s2_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'pxl_conv_nhwc': (c_int, [ctypes.POINTER(ConvGeom), ctypes.POINTER(c_int), P, P, P, P, P]),
@@ -153,9 +153,15 @@ def load():
     return lib
 
 
+_bound = {}
+
+
 def call(name, *args):
     """Call an int-returning entry point and raise PxlError on a non-zero return."""
-    rc = getattr(load(), name)(*args)
+    fn = _bound.get(name)
+    if fn is None:
+        fn = _bound[name] = getattr(load(), name)
+    rc = fn(*args)
     if rc != 0:
         raise PxlError(name, rc)
     return rc

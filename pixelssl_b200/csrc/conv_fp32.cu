@@ -650,6 +650,9 @@ __global__ void __launch_bounds__(256)
 stem_im2col_h16_kernel(const float* __restrict__ img, uint2* __restrict__ hi, uint2* __restrict__ lo, float scale,
                        int N, int H, int W, int OH, int OW, int tilesX, int tilesY, int* __restrict__ sat) {
     __shared__ float patch[3 * IM_PH * IM_PW];
+    __shared__ short koff_s[ST_KH];          // the lanes of a warp index the table with 32 different k: from constant memory
+                                             // that serialises 32-fold (it bounded the kernel: 1.57 ms -> see profiles/)
+    for (int i = threadIdx.x; i < ST_KH; i += blockDim.x) koff_s[i] = (short)c_im_koff[i];
     const int t = blockIdx.x;
     const int tx = t % tilesX, ty = (t / tilesX) % tilesY, n = t / (tilesX * tilesY);
     const int ox0 = tx * IM_TOX, oy0 = ty * IM_TOY;
@@ -670,7 +673,7 @@ stem_im2col_h16_kernel(const float* __restrict__ img, uint2* __restrict__ hi, ui
         unsigned short h[4], l[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int off = c_im_koff[k4 * 4 + e];
+            const int off = koff_s[k4 * 4 + e];
             const float v = off >= 0 ? patch[off + base] : 0.f;
             const float cl = fminf(fmaxf(v, -65504.f), 65504.f);
             clipped |= (cl != v) && (v == v);

@@ -679,13 +679,26 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         int st_n0 = -1;
         auto flush_stats = [&]() {
             if (stats && st_n0 >= 0) {
-                const float ss[4] = {st_s0, st_s1, st_s2, st_s3}, qq[4] = {st_q0, st_q1, st_q2, st_q3};
-#pragma unroll
-                for (int si = 0; si < 4; ++si) {
-                    const int cbf = st_n0 + 32 * (grp + si * ngrp) + lane;
-                    if (32 * (grp + si * ngrp) < p.BN && cbf < p.Cout && (ss[si] != 0.f || qq[si] != 0.f)) {
-                        atomicAdd(stats + cbf, (double)ss[si]);
-                        atomicAdd(stats + p.Cout + cbf, (double)qq[si]);
+                // the four warps of a group hold the four row quarters of the same channels: combine them through the
+                // group's (idle) staging slab so that ONE thread per channel issues the fp64 atomics - a single-wave
+                // layer-3 launch otherwise sends 548 atomics to each of 512 addresses at the same moment (+8 us)
+                float* scratch = reinterpret_cast<float*>(staging + (size_t)(ngrp == 1 ? 0 : grp) * TC_A_BYTES);
+                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
+                scratch[0 * 128 + r] = st_s0; scratch[1 * 128 + r] = st_q0;
+                scratch[2 * 128 + r] = st_s1; scratch[3 * 128 + r] = st_q1;
+                scratch[4 * 128 + r] = st_s2; scratch[5 * 128 + r] = st_q2;
+                scratch[6 * 128 + r] = st_s3; scratch[7 * 128 + r] = st_q3;
+                asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
+                const int slab = grp + q * ngrp;              // warp q of the group reduces accumulator slot si = q
+                const int cbf = st_n0 + 32 * slab + lane;
+                if (32 * slab < p.BN && cbf < p.Cout) {
+                    const float* ps = scratch + (2 * q) * 128 + lane;
+                    const float sv = (ps[0] + ps[32]) + (ps[64] + ps[96]);
+                    const float qv = (ps[128] + ps[160]) + (ps[192] + ps[224]);
+                    if (sv != 0.f || qv != 0.f) {
+                        atomicAdd(stats + cbf, (double)sv);
+                        atomicAdd(stats + p.Cout + cbf, (double)qv);
                     }
                 }
             }
@@ -1082,13 +1095,26 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         int st_n0 = -1;
         auto flush_stats = [&]() {
             if (stats && st_n0 >= 0) {
-                const float ss[4] = {st_s0, st_s1, st_s2, st_s3}, qq[4] = {st_q0, st_q1, st_q2, st_q3};
-#pragma unroll
-                for (int si = 0; si < 4; ++si) {
-                    const int cbf = st_n0 + 32 * (grp + si * ngrp) + lane;
-                    if (32 * (grp + si * ngrp) < p.BN && cbf < p.Cout && (ss[si] != 0.f || qq[si] != 0.f)) {
-                        atomicAdd(stats + cbf, (double)ss[si]);
-                        atomicAdd(stats + p.Cout + cbf, (double)qq[si]);
+                // the four warps of a group hold the four row quarters of the same channels: combine them through the
+                // group's (idle) staging slab so that ONE thread per channel issues the fp64 atomics - a single-wave
+                // layer-3 launch otherwise sends 548 atomics to each of 512 addresses at the same moment (+8 us)
+                float* scratch = reinterpret_cast<float*>(staging + (size_t)(ngrp == 1 ? 0 : grp) * TC_A_BYTES);
+                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
+                scratch[0 * 128 + r] = st_s0; scratch[1 * 128 + r] = st_q0;
+                scratch[2 * 128 + r] = st_s1; scratch[3 * 128 + r] = st_q1;
+                scratch[4 * 128 + r] = st_s2; scratch[5 * 128 + r] = st_q2;
+                scratch[6 * 128 + r] = st_s3; scratch[7 * 128 + r] = st_q3;
+                asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
+                const int slab = grp + q * ngrp;              // warp q of the group reduces accumulator slot si = q
+                const int cbf = st_n0 + 32 * slab + lane;
+                if (32 * slab < p.BN && cbf < p.Cout) {
+                    const float* ps = scratch + (2 * q) * 128 + lane;
+                    const float sv = (ps[0] + ps[32]) + (ps[64] + ps[96]);
+                    const float qv = (ps[128] + ps[160]) + (ps[192] + ps[224]);
+                    if (sv != 0.f || qv != 0.f) {
+                        atomicAdd(stats + cbf, (double)sv);
+                        atomicAdd(stats + p.Cout + cbf, (double)qv);
                     }
                 }
             }

@@ -170,11 +170,21 @@ extern "C" int pxl_bn_eval_coeffs(int C, const float* gamma, const float* beta, 
 // ------------------------------------------------------------------------------------------
 // apply: y = x*scale + shift (+ residual) (ReLU)        8 B/elem (12 with residual)
 // ------------------------------------------------------------------------------------------
+// ReLU mask of a float4 (bit k: lane k of the result is > 0): 1 byte per 4 values, written by the forward apply of a
+// block output and read by its backward instead of the fp32 result (0.25 B/element instead of 4, twice per step)
+__device__ __forceinline__ uint8_t relu_mask4(const float4& v) {
+    return (uint8_t)((v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u));
+}
+__device__ __forceinline__ void apply_mask4(float4& d, unsigned m) {
+    d.x = (m & 1u) ? d.x : 0.f; d.y = (m & 2u) ? d.y : 0.f; d.z = (m & 4u) ? d.z : 0.f; d.w = (m & 8u) ? d.w : 0.f;
+}
+
 template <bool RES, bool RELU>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float4* __restrict__ x, const float4* __restrict__ scale, const float4* __restrict__ shift,
                 const float4* __restrict__ res, float4* __restrict__ y, int64_t n4, int c4max,
-                uint2* __restrict__ hi, uint2* __restrict__ lo, float hscale, int* __restrict__ sat) {
+                uint2* __restrict__ hi, uint2* __restrict__ lo, float hscale, int* __restrict__ sat,
+                uint8_t* __restrict__ mask) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     bool clipped = false;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -187,6 +197,7 @@ bn_apply_kernel(const float4* __restrict__ x, const float4* __restrict__ scale, 
         if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         if (y) y[i] = v;
         if (hi) clipped |= h16_store4(v, hscale, hi, lo, i);
+        if (mask) mask[i] = relu_mask4(v);
     }
     if (clipped && sat) atomicAdd(sat, 1);
 }
@@ -194,17 +205,20 @@ bn_apply_kernel(const float4* __restrict__ x, const float4* __restrict__ scale, 
 extern "C" int* pxl_h16_sat_counter(void);
 
 extern "C" int pxl_bn_apply_h16(const float* x, const float* scale, const float* shift, const float* residual,
-                                int relu, float* y, int64_t rows, int C, void* hi, void* lo, float hscale, void* stream);
+                                int relu, float* y, int64_t rows, int C, void* hi, void* lo, float hscale, void* relu_mask,
+                                void* stream);
 
 extern "C" int pxl_bn_apply(const float* x, const float* scale, const float* shift, const float* residual,
                             int relu, float* y, int64_t rows, int C, void* stream) {
     if (!y) return PXL_ERR_BAD_ARG;
-    return pxl_bn_apply_h16(x, scale, shift, residual, relu, y, rows, C, nullptr, nullptr, 1.f, stream);
+    return pxl_bn_apply_h16(x, scale, shift, residual, relu, y, rows, C, nullptr, nullptr, 1.f, nullptr, stream);
 }
 
-// y nullable when the fp16 pair (hi, lo nullable) is the only output wanted
+// y nullable when the fp16 pair (hi, lo nullable) is the only output wanted; relu_mask (nullable, rows*C/4 bytes)
+// receives the sign bits of the result for the backward (pxl_bn_bwd_*_h16)
 extern "C" int pxl_bn_apply_h16(const float* x, const float* scale, const float* shift, const float* residual,
-                                int relu, float* y, int64_t rows, int C, void* hi, void* lo, float hscale, void* stream) {
+                                int relu, float* y, int64_t rows, int C, void* hi, void* lo, float hscale, void* relu_mask,
+                                void* stream) {
     if (!x || !scale || !shift || (!y && !hi) || rows <= 0 || C <= 0 || (C & 3)) return PXL_ERR_BAD_ARG;
     const int64_t n4 = rows * (C / 4);
     int blocks = (int)(pxl_cdiv(n4, 256 * 2) < PXL_NUM_SMS * 8 ? pxl_cdiv(n4, 256 * 2) : PXL_NUM_SMS * 8);
@@ -213,7 +227,7 @@ extern "C" int pxl_bn_apply_h16(const float* x, const float* scale, const float*
     float4* y4 = (float4*)y;
     int* sat = hi ? pxl_h16_sat_counter() : nullptr;
     if (sat) sat += 2;
-#define PXL_AP_ARGS x4, s4, h4, r4, y4, n4, C / 4, (uint2*)hi, (uint2*)lo, hscale, sat
+#define PXL_AP_ARGS x4, s4, h4, r4, y4, n4, C / 4, (uint2*)hi, (uint2*)lo, hscale, sat, (uint8_t*)relu_mask
     if (residual && relu) bn_apply_kernel<true, true><<<blocks, 256, 0, st>>>(PXL_AP_ARGS);
     else if (residual) bn_apply_kernel<true, false><<<blocks, 256, 0, st>>>(PXL_AP_ARGS);
     else if (relu) bn_apply_kernel<false, true><<<blocks, 256, 0, st>>>(PXL_AP_ARGS);
@@ -236,7 +250,8 @@ bn_finalize_apply_kernel(const float4* __restrict__ x, const double* __restrict_
                          float* mean, float* invstd, float* scale, float* shift,
                          const float4* __restrict__ res, float4* __restrict__ y,
                          int64_t rows, int C, int TX, int TY, int64_t rowsPerBlock,
-                         uint2* __restrict__ hi, uint2* __restrict__ lo, float hscale, int* __restrict__ sat) {
+                         uint2* __restrict__ hi, uint2* __restrict__ lo, float hscale, int* __restrict__ sat,
+                         uint8_t* __restrict__ mask) {
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
     if (c4 >= c4max) return;
@@ -277,6 +292,7 @@ bn_finalize_apply_kernel(const float4* __restrict__ x, const double* __restrict_
         if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         if (y) y[i] = v;
         if (hi) clipped |= h16_store4(v, hscale, hi, lo, i);
+        if (mask) mask[i] = relu_mask4(v);
     }
     if (clipped && sat) atomicAdd(sat, 1);
 }
@@ -303,7 +319,7 @@ extern "C" int pxl_bn_finalize_apply_h16(const float* x, const double* sums, dou
                                          const float* beta, float* running_mean, float* running_var, float momentum,
                                          float eps, int clamp_mode, float* mean, float* invstd, float* scale, float* shift,
                                          const float* residual, int relu, float* y, int64_t rows, int C,
-                                         void* hi, void* lo, float hscale, void* stream);
+                                         void* hi, void* lo, float hscale, void* relu_mask, void* stream);
 
 extern "C" int pxl_bn_finalize_apply(const float* x, const double* sums, double count, const float* gamma,
                                      const float* beta, float* running_mean, float* running_var, float momentum,
@@ -311,7 +327,7 @@ extern "C" int pxl_bn_finalize_apply(const float* x, const double* sums, double 
                                      const float* residual, int relu, float* y, int64_t rows, int C, void* stream) {
     if (!y) return PXL_ERR_BAD_ARG;
     return pxl_bn_finalize_apply_h16(x, sums, count, gamma, beta, running_mean, running_var, momentum, eps, clamp_mode, mean,
-                                     invstd, scale, shift, residual, relu, y, rows, C, nullptr, nullptr, 1.f, stream);
+                                     invstd, scale, shift, residual, relu, y, rows, C, nullptr, nullptr, 1.f, nullptr, stream);
 }
 
 // the same launch also (or only: y nullable) writes the result as the fp16 pair the next convolution reads
@@ -319,7 +335,7 @@ extern "C" int pxl_bn_finalize_apply_h16(const float* x, const double* sums, dou
                                          const float* beta, float* running_mean, float* running_var, float momentum,
                                          float eps, int clamp_mode, float* mean, float* invstd, float* scale, float* shift,
                                          const float* residual, int relu, float* y, int64_t rows, int C,
-                                         void* hi, void* lo, float hscale, void* stream) {
+                                         void* hi, void* lo, float hscale, void* relu_mask, void* stream) {
     if (!x || !sums || !gamma || !beta || !mean || !invstd || !scale || !shift || (!y && !hi) || rows <= 0 || C <= 0 || (C & 3) || count <= 0)
         return PXL_ERR_BAD_ARG;
     int* sat = hi ? pxl_h16_sat_counter() : nullptr;
@@ -329,7 +345,7 @@ extern "C" int pxl_bn_finalize_apply_h16(const float* x, const double* sums, dou
     cudaStream_t st = (cudaStream_t)stream;
 #define PXL_FA_ARGS (const float4*)x, sums, count, 1.0 / count, gamma, beta, running_mean, running_var, momentum, eps, clamp_mode, mean, invstd, \
                     scale, shift, (const float4*)residual, (float4*)y, rows, C, L.TX, L.TY, L.rowsPerBlock, \
-                    (uint2*)hi, (uint2*)lo, hscale, sat
+                    (uint2*)hi, (uint2*)lo, hscale, sat, (uint8_t*)relu_mask
     if (residual && relu) bn_finalize_apply_kernel<true, true><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
     else if (residual) bn_finalize_apply_kernel<true, false><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
     else if (relu) bn_finalize_apply_kernel<false, true><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
@@ -350,7 +366,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
                      const float* __restrict__ mean, const float* __restrict__ invstd, int64_t rows, int C,
                      int TX, int TY, int64_t rowsPerBlock, double* __restrict__ dsums,
-                     const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ amax_slot) {
+                     const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ amax_slot,
+                     const uint8_t* __restrict__ mask) {
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
     const int64_t r0 = (int64_t)blockIdx.x * rowsPerBlock;
@@ -378,6 +395,8 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, c
             } else if (RELU == 2) {
                 d.x = fmaf(v.x, sc.x, sh.x) > 0.f ? d.x : 0.f; d.y = fmaf(v.y, sc.y, sh.y) > 0.f ? d.y : 0.f;
                 d.z = fmaf(v.z, sc.z, sh.z) > 0.f ? d.z : 0.f; d.w = fmaf(v.w, sc.w, sh.w) > 0.f ? d.w : 0.f;
+            } else if (RELU == 3) {
+                apply_mask4(d, __ldg(mask + r * c4max + c4));
             }
             float4 xh = make_float4((v.x - m.x) * is.x, (v.y - m.y) * is.y, (v.z - m.z) * is.z, (v.w - m.w) * is.w);
             s = f4add(s, d);
@@ -396,25 +415,31 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, c
 
 extern "C" int pxl_bn_bwd_reduce_h16(const float* x, const float* y, const float* dy, const float* mean,
                                      const float* invstd, int relu, int64_t rows, int C, double* dsums,
-                                     const float* scale, const float* shift, float* amax_slot, void* stream);
+                                     const float* scale, const float* shift, float* amax_slot, const void* relu_mask,
+                                     void* stream);
 
 extern "C" int pxl_bn_bwd_reduce(const float* x, const float* y, const float* dy, const float* mean,
                                  const float* invstd, int relu, int64_t rows, int C, double* dsums,
                                  const float* scale, const float* shift, void* stream) {
-    return pxl_bn_bwd_reduce_h16(x, y, dy, mean, invstd, relu, rows, C, dsums, scale, shift, nullptr, stream);
+    return pxl_bn_bwd_reduce_h16(x, y, dy, mean, invstd, relu, rows, C, dsums, scale, shift, nullptr, nullptr, stream);
 }
 
 // amax_slot (nullable DEVICE float[4], zeroed): slot[2] = max(slot[2], absmax(dz)) as a bit pattern
+// ReLU mask source, in this order: relu_mask (bytes written by pxl_bn_*apply_h16), y (the forward result), else
+// recomputed from x*scale+shift (no residual)
 extern "C" int pxl_bn_bwd_reduce_h16(const float* x, const float* y, const float* dy, const float* mean,
                                      const float* invstd, int relu, int64_t rows, int C, double* dsums,
-                                     const float* scale, const float* shift, float* amax_slot, void* stream) {
-    if (!x || !dy || !mean || !invstd || !dsums || rows <= 0 || C <= 0 || (C & 3) || (relu && !y && !(scale && shift))) return PXL_ERR_BAD_ARG;
+                                     const float* scale, const float* shift, float* amax_slot, const void* relu_mask,
+                                     void* stream) {
+    if (!x || !dy || !mean || !invstd || !dsums || rows <= 0 || C <= 0 || (C & 3) || (relu && !y && !relu_mask && !(scale && shift))) return PXL_ERR_BAD_ARG;
     RedLayout L = red_layout(rows, C);
     dim3 grid(L.rowBlocks, L.colBlocks);
     cudaStream_t st = (cudaStream_t)stream;
-    if (relu && y) bn_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot);
-    else if (relu) bn_bwd_reduce_kernel<2><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot);
-    else bn_bwd_reduce_kernel<0><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot);
+    const uint8_t* mk = (const uint8_t*)relu_mask;
+    if (relu && mk) bn_bwd_reduce_kernel<3><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot, mk);
+    else if (relu && y) bn_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot, mk);
+    else if (relu) bn_bwd_reduce_kernel<2><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot, mk);
+    else bn_bwd_reduce_kernel<0><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot, mk);
     PXL_CHECK_LAUNCH();
     return 0;
 }
@@ -431,7 +456,7 @@ bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, con
                  const float* __restrict__ scale, const float* __restrict__ shift,
                  float* dgamma_acc, float* dbeta_acc,
                  uint2* __restrict__ dhi, uint2* __restrict__ dlo, float* __restrict__ slot, int target_log2,
-                 int* __restrict__ sat) {
+                 int* __restrict__ sat, const uint8_t* __restrict__ mask) {
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
     float hs = 1.f;
@@ -489,6 +514,8 @@ bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, con
         } else if (RELU == 2) {
             d.x = fmaf(v.x, sc.x, sh.x) > 0.f ? d.x : 0.f; d.y = fmaf(v.y, sc.y, sh.y) > 0.f ? d.y : 0.f;
             d.z = fmaf(v.z, sc.z, sh.z) > 0.f ? d.z : 0.f; d.w = fmaf(v.w, sc.w, sh.w) > 0.f ? d.w : 0.f;
+        } else if (RELU == 3) {
+            apply_mask4(d, __ldg(mask + i));
         }
         if (DRES) dres[i] = d;
         float4 o4;
@@ -506,7 +533,7 @@ extern "C" int pxl_bn_bwd_dx_h16(const float* x, const float* y, const float* dy
                                  const float* invstd, const float* gamma, const double* dsums, double count,
                                  int relu, float* dx, float* dres, int64_t rows, int C,
                                  const float* scale, const float* shift, float* dgamma_acc, float* dbeta_acc,
-                                 void* dhi, void* dlo, float* slot, int target_log2, void* stream);
+                                 void* dhi, void* dlo, float* slot, int target_log2, const void* relu_mask, void* stream);
 
 extern "C" int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, const float* mean,
                              const float* invstd, const float* gamma, const double* dsums, double count,
@@ -514,7 +541,7 @@ extern "C" int pxl_bn_bwd_dx(const float* x, const float* y, const float* dy, co
                              const float* scale, const float* shift, float* dgamma_acc, float* dbeta_acc, void* stream) {
     if (!dx) return PXL_ERR_BAD_ARG;
     return pxl_bn_bwd_dx_h16(x, y, dy, mean, invstd, gamma, dsums, count, relu, dx, dres, rows, C, scale, shift,
-                             dgamma_acc, dbeta_acc, nullptr, nullptr, nullptr, 0, stream);
+                             dgamma_acc, dbeta_acc, nullptr, nullptr, nullptr, 0, nullptr, stream);
 }
 
 // dx also (or only: dx nullable) as the fp16 pair (dhi, dlo nullable) the dgrad / wgrad convolutions read; slot = the
@@ -523,11 +550,11 @@ extern "C" int pxl_bn_bwd_dx_h16(const float* x, const float* y, const float* dy
                                  const float* invstd, const float* gamma, const double* dsums, double count,
                                  int relu, float* dx, float* dres, int64_t rows, int C,
                                  const float* scale, const float* shift, float* dgamma_acc, float* dbeta_acc,
-                                 void* dhi, void* dlo, float* slot, int target_log2, void* stream) {
+                                 void* dhi, void* dlo, float* slot, int target_log2, const void* relu_mask, void* stream) {
     if ((!dx && !dhi) || (dhi && !slot)) return PXL_ERR_BAD_ARG;
     int* sat = dhi ? pxl_h16_sat_counter() : nullptr;
     if (sat) sat += 3;
-    if (!x || !dy || !mean || !invstd || !gamma || !dsums || rows <= 0 || C <= 0 || (C & 3) || (relu && !y && !(scale && shift))) return PXL_ERR_BAD_ARG;
+    if (!x || !dy || !mean || !invstd || !gamma || !dsums || rows <= 0 || C <= 0 || (C & 3) || (relu && !y && !relu_mask && !(scale && shift))) return PXL_ERR_BAD_ARG;
     const RedLayout L = stream_layout(rows, C);     // the reductions' decomposition without their atomics
     dim3 grid(L.rowBlocks, L.colBlocks);
     cudaStream_t st = (cudaStream_t)stream;
@@ -535,9 +562,11 @@ extern "C" int pxl_bn_bwd_dx_h16(const float* x, const float* y, const float* dy
     float4 *o4 = (float4*)dx, *r4 = (float4*)dres;
     const double ic = 1.0 / count;
 #define PXL_DX_ARGS x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock, scale, shift, \
-                    (dgamma_acc && dbeta_acc) ? dgamma_acc : nullptr, dbeta_acc, (uint2*)dhi, (uint2*)dlo, slot, target_log2, sat
-    const int mode = relu ? (y ? 1 : 2) : 0;
-    if (mode == 1 && dres) bn_bwd_dx_kernel<1, true><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
+                    (dgamma_acc && dbeta_acc) ? dgamma_acc : nullptr, dbeta_acc, (uint2*)dhi, (uint2*)dlo, slot, target_log2, sat, (const uint8_t*)relu_mask
+    const int mode = relu ? (relu_mask ? 3 : (y ? 1 : 2)) : 0;
+    if (mode == 3 && dres) bn_bwd_dx_kernel<3, true><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
+    else if (mode == 3) bn_bwd_dx_kernel<3, false><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
+    else if (mode == 1 && dres) bn_bwd_dx_kernel<1, true><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
     else if (mode == 1) bn_bwd_dx_kernel<1, false><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
     else if (mode == 2 && dres) bn_bwd_dx_kernel<2, true><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
     else if (mode == 2) bn_bwd_dx_kernel<2, false><<<grid, 256, 0, st>>>(PXL_DX_ARGS);

@@ -37,11 +37,21 @@ def get_conv_precision():
 
 
 def _p(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    """Device address for a C-ABI pointer argument (every entry point declares argtypes, so ctypes converts the
+    plain int / None itself: no c_void_p object per argument, ~9000 of them per step)."""
+    return t.data_ptr() if t is not None else None
+
+
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+_cur_device = getattr(torch._C, '_cuda_getDevice', None)
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Raw handle of torch's current stream.  torch.cuda.current_stream() builds a Stream object through three layers
+    of Python (~15 us; ~900 launches per step made that a fifth of the step's host time) - the C accessor is ~0.3 us."""
+    if _raw_stream is not None:
+        return _raw_stream(_cur_device())
+    return torch.cuda.current_stream().cuda_stream
 
 
 def _chk(t, name, cl=False):
@@ -1174,6 +1184,8 @@ def bn_act(x, gamma, beta, running_mean, running_var, training=True, momentum=0.
 # backward launches.  NEGATIVE RESULT (measured, B200, MT step): 53.8 ms -> 76.4 ms.  The wgrad CTAs (200 KB of
 # shared memory each) take SMs away from the persistent one-CTA-per-SM convolutions of the critical path, which then
 # wait for them - a priority inversion the default stream cannot be prioritised out of.  Opt-in: PXL_WGRAD_SIDE_STREAM=1.
+# block outputs: ReLU mask for the backward as 1 byte per 4 values (A/B switch; 0 re-reads the fp32 result)
+BN_RELU_MASK = _os.environ.get('PXL_BN_RELU_MASK', '1') != '0'
 WGRAD_SIDE_STREAM = _os.environ.get('PXL_WGRAD_SIDE_STREAM', '0') != '0'
 _side_streams = {}
 
@@ -1266,6 +1278,10 @@ class _ConvBnAct(torch.autograd.Function):
         y = torch.empty_like(c) if out_mode != 'pair' else None
         hi = pair[0] if pair is not None else None
         lo = pair[1] if (pair is not None and want_lo) else None
+        # block output (residual + ReLU): the backward takes the ReLU mask from one byte per 4 values instead of
+        # re-reading the fp32 result in both of its launches
+        mask = (torch.empty(n // 4, dtype=torch.uint8, device=dev)
+                if (BN_RELU_MASK and relu and residual is not None and any(ctx.needs_input_grad)) else None)
         if residual is not None:
             _chk(residual, 'residual', cl=True)
         applied = fused = False
@@ -1283,15 +1299,16 @@ class _ConvBnAct(torch.autograd.Function):
         if group is None and FUSE_BN_FINALIZE:
             call('pxl_bn_finalize_apply_h16', _p(c), _p(sums), count, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
                  float(momentum), float(eps), clamp, _p(coeff[0]), _p(coeff[1]), _p(coeff[2]), _p(coeff[3]),
-                 _p(residual), int(relu), _p(y), rows, Cout, _p(hi), _p(lo), float(H16_ACT_SCALE), _stream())
+                 _p(residual), int(relu), _p(y), rows, Cout, _p(hi), _p(lo), float(H16_ACT_SCALE), _p(mask), _stream())
             applied = True
         elif not fused:
             call('pxl_bn_finalize', _p(sums), count, Cout, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
                  float(momentum), float(eps), clamp, _p(coeff[0]), _p(coeff[1]), _p(coeff[2]), _p(coeff[3]), _stream())
         if not applied:
             call('pxl_bn_apply_h16', _p(c), _p(coeff[2]), _p(coeff[3]), _p(residual), int(relu), _p(y), rows, Cout,
-                 _p(hi), _p(lo), float(H16_ACT_SCALE), _stream())
-        ctx.save_for_backward(xh.buf, weight, c, y if (relu and residual is not None) else None, gamma, coeff, beta)
+                 _p(hi), _p(lo), float(H16_ACT_SCALE), _p(mask), _stream())
+        ctx.save_for_backward(xh.buf, weight, c, mask if BN_RELU_MASK else (y if (relu and residual is not None) else None),
+                              gamma, coeff, beta)
         ctx.meta = (taps, N, H, W, Cin, OH, OW, Cout, stride, kh * kw, count, bool(relu), residual is not None, group,
                     xh.scale, want_lo, prec)
         _unit_out_pair = H16(pair, n, H16_ACT_SCALE, None, want_lo) if pair is not None else None
@@ -1301,7 +1318,7 @@ class _ConvBnAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        xbuf, weight, c, y, gamma, coeff, beta = ctx.saved_tensors
+        xbuf, weight, c, mask, gamma, coeff, beta = ctx.saved_tensors
         taps, N, H, W, Cin, OH, OW, Cout, stride, T, count, relu, has_res, group, xscale, want_lo, prec = ctx.meta
         if is_carrier(dy):
             raise RuntimeError('gradient tensors are never fp16-pair carriers')
@@ -1312,9 +1329,13 @@ class _ConvBnAct(torch.autograd.Function):
         C = Cout
         dsums = _stat_zeros(2 * C, dev)
         slot = _scale_slot(dev)
-        ymask = y if (relu and has_res) else None
+        if relu and has_res and mask is None:
+            raise RuntimeError('the ReLU mask of a residual unit was not recorded in the forward')
+        ymask = None
+        if mask is not None and mask.dtype != torch.uint8:      # PXL_BN_RELU_MASK=0: the fp32 result is the mask
+            ymask, mask = mask, None
         call('pxl_bn_bwd_reduce_h16', _p(c), _p(ymask), _p(dy), _p(coeff[0]), _p(coeff[1]), int(relu), rows, C, _p(dsums),
-             _p(coeff[2]), _p(coeff[3]), _p(slot), _stream())
+             _p(coeff[2]), _p(coeff[3]), _p(slot), _p(mask), _stream())
         grads_in_arena = (ACCUM_WGRAD_INPLACE and gamma.grad is not None and beta.grad is not None
                           and gamma.grad.is_contiguous() and beta.grad.is_contiguous())
         px = _peer_exchanges.get(id(group)) if group is not None else None
@@ -1338,7 +1359,7 @@ class _ConvBnAct(torch.autograd.Function):
         call('pxl_bn_bwd_dx_h16', _p(c), _p(ymask), _p(dy), _p(coeff[0]), _p(coeff[1]), _p(gamma), _p(dsums), count, int(relu),
              _p(None), _p(dres), rows, C, _p(coeff[2]), _p(coeff[3]),
              _p(gamma.grad if acc_inplace else None), _p(beta.grad if acc_inplace else None),
-             _p(dpair[0]), _p(dpair[1] if want_lo else None), _p(slot), H16_DX_TARGET_LOG2, _stream())
+             _p(dpair[0]), _p(dpair[1] if want_lo else None), _p(slot), H16_DX_TARGET_LOG2, _p(mask), _stream())
         dh = H16(dpair, n, None, slot, want_lo)
         dx = dw = None
         stash_key, stash_role = ctx.stash

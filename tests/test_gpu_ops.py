@@ -236,6 +236,55 @@ def test_bn_act_train(ops, N, C, H, W, relu, res):
     if res:
         assert rel(rg.grad, rc.grad) <= 1e-6
 
+@pytest.mark.parametrize('rows,C', [(1000, 64), (33 * 33 * 2, 256), (77, 2048)])
+def test_bn_backward_relu_byte_mask_equals_the_fp32_result_mask(ops, rows, C):
+    """Block outputs record sign bits (1 byte per 4 values) in the forward apply; the backward launches that read
+    them must produce bit-identical sums, dX pair and residual gradient to the launches that re-read the fp32 result."""
+    from pixelssl_b200._lib import call
+    P = ops._p
+    g = gen(rows + C)
+    dev = 'cuda'
+    x = (torch.randn(rows, C, generator=g) * 2).to(dev)
+    res = torch.randn(rows, C, generator=g).to(dev)
+    dy = (torch.randn(rows, C, generator=g) * 1e-3).to(dev)
+    gamma = (1 + 0.3 * torch.randn(C, generator=g)).to(dev)
+    beta = (0.2 * torch.randn(C, generator=g)).to(dev)
+    sums = torch.cat((x.double().sum(0), (x.double() ** 2).sum(0)))
+    coeff = torch.empty(4, C, device=dev)
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    y = torch.empty_like(x)
+    pair = torch.empty(2, rows * C, dtype=torch.float16, device=dev)
+    mask = torch.zeros(rows * C // 4, dtype=torch.uint8, device=dev)
+    st = ops._stream()
+    call('pxl_bn_finalize_apply_h16', P(x), P(sums), float(rows), P(gamma), P(beta), P(rm), P(rv), 0.1, 1e-5, 0,
+         P(coeff[0]), P(coeff[1]), P(coeff[2]), P(coeff[3]), P(res), 1, P(y), rows, C, P(pair[0]), P(pair[1]), 16.0, P(mask), st)
+    bits = (y.view(-1, 4) > 0).to(torch.uint8)
+    want = bits[:, 0] | (bits[:, 1] << 1) | (bits[:, 2] << 2) | (bits[:, 3] << 3)
+    assert torch.equal(mask, want)
+    outs = []
+    ds_ref = None
+    for use_mask in (False, True):
+        dsums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+        slot = torch.zeros(4, device=dev)
+        call('pxl_bn_bwd_reduce_h16', P(x), P(None if use_mask else y), P(dy), P(coeff[0]), P(coeff[1]), 1, rows, C, P(dsums),
+             P(coeff[2]), P(coeff[3]), P(slot), P(mask if use_mask else None), st)
+        if ds_ref is None:
+            ds_ref = dsums.clone()
+        # the fp64 atomics of the reduction commute only up to rounding: same sums to 1e-12, and the dx launches of
+        # both variants then get the SAME sums so that their outputs can be compared bit for bit
+        assert rel(dsums, ds_ref) <= 1e-12
+        dpair = torch.empty(2, rows * C, dtype=torch.float16, device=dev)
+        dres = torch.empty_like(x)
+        dx = torch.empty_like(x)
+        call('pxl_bn_bwd_dx_h16', P(x), P(None if use_mask else y), P(dy), P(coeff[0]), P(coeff[1]), P(gamma), P(ds_ref), float(rows), 1,
+             P(dx), P(dres), rows, C, P(coeff[2]), P(coeff[3]), P(None), P(None), P(dpair[0]), P(dpair[1]), P(slot), 12,
+             P(mask if use_mask else None), st)
+        torch.cuda.synchronize()
+        outs.append((dx, dres, dpair, slot))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert ops.h16_status() == 0
+
 
 def test_bn_eval(ops):
     gs = gen(4)
