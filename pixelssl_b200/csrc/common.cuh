@@ -17,6 +17,31 @@ extern "C" void pxl_count_launch_(int n);
 
 static inline int64_t pxl_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (PDL): a kernel launched through pxl_launch_pdl may become resident while its
+// predecessor in the stream is still running (as SM resources free up); it must execute PXL_PDL_SYNC() before it
+// touches global memory - the predecessor's results are complete and visible after it.  What overlaps is the launch
+// latency, CTA scheduling and the part of the kernel before PXL_PDL_SYNC (barrier init, TMEM allocation, shared
+// memory clearing of the tcgen05 kernels).  PXL_PDL=0 launches everything with plain stream order.
+#define PXL_PDL_SYNC()                                                   \
+    do {                                                                 \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  \
+        asm volatile("griddepcontrol.wait;" ::: "memory");               \
+    } while (0)
+
+extern "C" int pxl_pdl_enabled_(void);
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pxl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pxl_pdl_enabled_() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

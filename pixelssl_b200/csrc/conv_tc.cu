@@ -351,6 +351,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_slot;
+    PXL_PDL_SYNC();          // everything above overlapped the previous kernel's tail; global memory from here on
 
     if (warp == 0) {
         // ================= TMA producer (whole warp converged, TMA under elect.sync) =================
@@ -594,6 +595,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_slot;
+    PXL_PDL_SYNC();          // everything above overlapped the previous kernel's tail; global memory from here on
 
     if (warp == 0) {
         // ================= TMA producer (whole warp converged, TMA under elect.sync) =================
@@ -1002,6 +1004,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     cluster_sync_all();                                   // peer barriers initialised, TMEM allocated in both CTAs
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_slot;
+    PXL_PDL_SYNC();          // everything above overlapped the previous kernel's tail; global memory from here on
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs; whole warp converged, TMA under elect.sync) =================
@@ -1526,10 +1529,12 @@ static int conv_tc_launch_core(const pxl_conv_geom* g, const int* taps, const px
         cfg.blockDim = dim3(320, 1, 1);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pxl_pdl_enabled_() ? 2 : 1;
         double* st_ptr = ext ? (double*)ext->bn_stats : nullptr;
         cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, mA, mAlo, mB, mBlo, mO, p, bias, out, st_ptr, g_err_flag, oscale_ptr);
         if (e != cudaSuccess) return (int)e;
@@ -1544,12 +1549,16 @@ static int conv_tc_launch_core(const pxl_conv_geom* g, const int* taps, const px
             attr2 = true;
         }
         const unsigned nblk = (unsigned)(p.total_tiles < PXL_NUM_SMS ? p.total_tiles : PXL_NUM_SMS);
-        conv_tc_persist_kernel<<<nblk, 320, smem, st>>>(mA, mAlo, mB, mBlo, mO, p, bias, out, ext ? ext->bn_stats : nullptr, g_err_flag, oscale_ptr);
+        cudaError_t le = pxl_launch_pdl(conv_tc_persist_kernel, dim3(nblk), dim3(320), smem, st, mA, mAlo, mB, mBlo, mO, p, bias, out,
+                                        ext ? (double*)ext->bn_stats : (double*)nullptr, g_err_flag, oscale_ptr);
+        if (le != cudaSuccess) return (int)le;
         PXL_CHECK_LAUNCH();
         return 0;
     }
     dim3 grid((unsigned)((int64_t)p.N * p.tilesH * p.tilesW), (unsigned)((g->Cout + p.BN - 1) / p.BN));
-    conv_tc_kernel<<<grid, 192, smem, st>>>(mA, mAlo, mB, mBlo, mO, p, bias, out, ext ? ext->bn_stats : nullptr, g_err_flag, oscale_ptr);
+    cudaError_t le = pxl_launch_pdl(conv_tc_kernel, grid, dim3(192), smem, st, mA, mAlo, mB, mBlo, mO, p, bias, out,
+                                    ext ? (double*)ext->bn_stats : (double*)nullptr, g_err_flag, oscale_ptr);
+    if (le != cudaSuccess) return (int)le;
     PXL_CHECK_LAUNCH();
     return 0;
 }
@@ -1669,6 +1678,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_slot;
+    PXL_PDL_SYNC();          // everything above overlapped the previous kernel's tail; global memory from here on
 
     if (iters > 0) {
         if (warp == 0) {
@@ -2009,7 +2019,9 @@ static int conv_wgrad_tc_core(const pxl_conv_geom* g, const int* taps, const voi
             p.tma_red = 1;
     }
     dim3 grid((unsigned)(tiles_co * p.tiles_ci), (unsigned)g->ntaps, (unsigned)split);
-    conv_wgrad_tc_kernel<<<grid, inkernel ? 320 : 192, smem, (cudaStream_t)stream>>>(mDy, mDyLo, mX, mXLo, mDw, p, dw, g_err_flag, oscale_ptr);
+    cudaError_t le = pxl_launch_pdl(conv_wgrad_tc_kernel, grid, dim3(inkernel ? 320 : 192), smem, (cudaStream_t)stream, mDy, mDyLo, mX, mXLo,
+                                    mDw, p, dw, g_err_flag, oscale_ptr);
+    if (le != cudaSuccess) return (int)le;
     PXL_CHECK_LAUNCH();
     return 0;
 }

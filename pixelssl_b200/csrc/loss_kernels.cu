@@ -1,6 +1,7 @@
 // Pixel-wise loss kernels on planar [n, C, H*W] maps: MSE consistency (the metric kernel),
 // cross-entropy with ignore_index, channel softmax, fused softmax+MSE, CutMix mix/confidence.
 #include "common.cuh"
+#include <stdlib.h>
 #include <math_constants.h>
 
 // ------------------------------------------------------------------------------------------
@@ -8,6 +9,12 @@
 // ------------------------------------------------------------------------------------------
 static int64_t g_launches = 0;
 extern "C" void pxl_count_launch_(int n) { g_launches += n; }
+// programmatic dependent launch switch (common.cuh): environment PXL_PDL, read once; default on
+extern "C" int pxl_pdl_enabled_(void) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PXL_PDL"); v = e ? (atoi(e) != 0) : 1; }
+    return v;
+}
 extern "C" int pxl_abi_version(void) { return 1; }
 extern "C" int64_t pxl_launch_count(void) { return g_launches; }
 extern "C" void pxl_reset_launch_count(void) { g_launches = 0; }

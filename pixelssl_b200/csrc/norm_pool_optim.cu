@@ -185,6 +185,7 @@ bn_apply_kernel(const float4* __restrict__ x, const float4* __restrict__ scale, 
                 const float4* __restrict__ res, float4* __restrict__ y, int64_t n4, int c4max,
                 uint2* __restrict__ hi, uint2* __restrict__ lo, float hscale, int* __restrict__ sat,
                 uint8_t* __restrict__ mask) {
+    PXL_PDL_SYNC();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     bool clipped = false;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -228,10 +229,10 @@ extern "C" int pxl_bn_apply_h16(const float* x, const float* scale, const float*
     int* sat = hi ? pxl_h16_sat_counter() : nullptr;
     if (sat) sat += 2;
 #define PXL_AP_ARGS x4, s4, h4, r4, y4, n4, C / 4, (uint2*)hi, (uint2*)lo, hscale, sat, (uint8_t*)relu_mask
-    if (residual && relu) bn_apply_kernel<true, true><<<blocks, 256, 0, st>>>(PXL_AP_ARGS);
-    else if (residual) bn_apply_kernel<true, false><<<blocks, 256, 0, st>>>(PXL_AP_ARGS);
-    else if (relu) bn_apply_kernel<false, true><<<blocks, 256, 0, st>>>(PXL_AP_ARGS);
-    else bn_apply_kernel<false, false><<<blocks, 256, 0, st>>>(PXL_AP_ARGS);
+    if (residual && relu) pxl_launch_pdl(bn_apply_kernel<true, true>, dim3(blocks), dim3(256), 0, st, PXL_AP_ARGS);
+    else if (residual) pxl_launch_pdl(bn_apply_kernel<true, false>, dim3(blocks), dim3(256), 0, st, PXL_AP_ARGS);
+    else if (relu) pxl_launch_pdl(bn_apply_kernel<false, true>, dim3(blocks), dim3(256), 0, st, PXL_AP_ARGS);
+    else pxl_launch_pdl(bn_apply_kernel<false, false>, dim3(blocks), dim3(256), 0, st, PXL_AP_ARGS);
 #undef PXL_AP_ARGS
     PXL_CHECK_LAUNCH();
     return 0;
@@ -252,6 +253,7 @@ bn_finalize_apply_kernel(const float4* __restrict__ x, const double* __restrict_
                          int64_t rows, int C, int TX, int TY, int64_t rowsPerBlock,
                          uint2* __restrict__ hi, uint2* __restrict__ lo, float hscale, int* __restrict__ sat,
                          uint8_t* __restrict__ mask) {
+    PXL_PDL_SYNC();
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
     if (c4 >= c4max) return;
@@ -346,10 +348,10 @@ extern "C" int pxl_bn_finalize_apply_h16(const float* x, const double* sums, dou
 #define PXL_FA_ARGS (const float4*)x, sums, count, 1.0 / count, gamma, beta, running_mean, running_var, momentum, eps, clamp_mode, mean, invstd, \
                     scale, shift, (const float4*)residual, (float4*)y, rows, C, L.TX, L.TY, L.rowsPerBlock, \
                     (uint2*)hi, (uint2*)lo, hscale, sat, (uint8_t*)relu_mask
-    if (residual && relu) bn_finalize_apply_kernel<true, true><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
-    else if (residual) bn_finalize_apply_kernel<true, false><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
-    else if (relu) bn_finalize_apply_kernel<false, true><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
-    else bn_finalize_apply_kernel<false, false><<<grid, 256, 0, st>>>(PXL_FA_ARGS);
+    if (residual && relu) pxl_launch_pdl(bn_finalize_apply_kernel<true, true>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS);
+    else if (residual) pxl_launch_pdl(bn_finalize_apply_kernel<true, false>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS);
+    else if (relu) pxl_launch_pdl(bn_finalize_apply_kernel<false, true>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS);
+    else pxl_launch_pdl(bn_finalize_apply_kernel<false, false>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS);
 #undef PXL_FA_ARGS
     PXL_CHECK_LAUNCH();
     return 0;
@@ -368,6 +370,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, c
                      int TX, int TY, int64_t rowsPerBlock, double* __restrict__ dsums,
                      const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ amax_slot,
                      const uint8_t* __restrict__ mask) {
+    PXL_PDL_SYNC();
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
     const int64_t r0 = (int64_t)blockIdx.x * rowsPerBlock;
@@ -436,10 +439,10 @@ extern "C" int pxl_bn_bwd_reduce_h16(const float* x, const float* y, const float
     dim3 grid(L.rowBlocks, L.colBlocks);
     cudaStream_t st = (cudaStream_t)stream;
     const uint8_t* mk = (const uint8_t*)relu_mask;
-    if (relu && mk) bn_bwd_reduce_kernel<3><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot, mk);
-    else if (relu && y) bn_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot, mk);
-    else if (relu) bn_bwd_reduce_kernel<2><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot, mk);
-    else bn_bwd_reduce_kernel<0><<<grid, 256, 0, st>>>(x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot, mk);
+    if (relu && mk) pxl_launch_pdl(bn_bwd_reduce_kernel<3>, dim3(grid), dim3(256), 0, st, x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot, mk);
+    else if (relu && y) pxl_launch_pdl(bn_bwd_reduce_kernel<1>, dim3(grid), dim3(256), 0, st, x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot, mk);
+    else if (relu) pxl_launch_pdl(bn_bwd_reduce_kernel<2>, dim3(grid), dim3(256), 0, st, x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot, mk);
+    else pxl_launch_pdl(bn_bwd_reduce_kernel<0>, dim3(grid), dim3(256), 0, st, x, y, dy, mean, invstd, rows, C, L.TX, L.TY, L.rowsPerBlock, dsums, scale, shift, amax_slot, mk);
     PXL_CHECK_LAUNCH();
     return 0;
 }
@@ -457,6 +460,7 @@ bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, con
                  float* dgamma_acc, float* dbeta_acc,
                  uint2* __restrict__ dhi, uint2* __restrict__ dlo, float* __restrict__ slot, int target_log2,
                  int* __restrict__ sat, const uint8_t* __restrict__ mask) {
+    PXL_PDL_SYNC();
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
     float hs = 1.f;
@@ -564,14 +568,14 @@ extern "C" int pxl_bn_bwd_dx_h16(const float* x, const float* y, const float* dy
 #define PXL_DX_ARGS x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock, scale, shift, \
                     (dgamma_acc && dbeta_acc) ? dgamma_acc : nullptr, dbeta_acc, (uint2*)dhi, (uint2*)dlo, slot, target_log2, sat, (const uint8_t*)relu_mask
     const int mode = relu ? (relu_mask ? 3 : (y ? 1 : 2)) : 0;
-    if (mode == 3 && dres) bn_bwd_dx_kernel<3, true><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
-    else if (mode == 3) bn_bwd_dx_kernel<3, false><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
-    else if (mode == 1 && dres) bn_bwd_dx_kernel<1, true><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
-    else if (mode == 1) bn_bwd_dx_kernel<1, false><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
-    else if (mode == 2 && dres) bn_bwd_dx_kernel<2, true><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
-    else if (mode == 2) bn_bwd_dx_kernel<2, false><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
-    else if (dres) bn_bwd_dx_kernel<0, true><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
-    else bn_bwd_dx_kernel<0, false><<<grid, 256, 0, st>>>(PXL_DX_ARGS);
+    if (mode == 3 && dres) pxl_launch_pdl(bn_bwd_dx_kernel<3, true>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
+    else if (mode == 3) pxl_launch_pdl(bn_bwd_dx_kernel<3, false>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
+    else if (mode == 1 && dres) pxl_launch_pdl(bn_bwd_dx_kernel<1, true>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
+    else if (mode == 1) pxl_launch_pdl(bn_bwd_dx_kernel<1, false>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
+    else if (mode == 2 && dres) pxl_launch_pdl(bn_bwd_dx_kernel<2, true>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
+    else if (mode == 2) pxl_launch_pdl(bn_bwd_dx_kernel<2, false>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
+    else if (dres) pxl_launch_pdl(bn_bwd_dx_kernel<0, true>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
+    else pxl_launch_pdl(bn_bwd_dx_kernel<0, false>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
 #undef PXL_DX_ARGS
     PXL_CHECK_LAUNCH();
     return 0;
