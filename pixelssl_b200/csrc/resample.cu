@@ -102,10 +102,11 @@ bilinear_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int
     int4* meta = reinterpret_cast<int4*>(smem + wpad);   // [wpad] {xlo, count, padded start, xlo % R}
     float* wtab = smem + wpad + 4 * wpad;                // [w][SUP]
     float* rb = wtab + (((size_t)w * SUP + 3) & ~(size_t)3);   // [G][rowbuf]
-    const int i = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
+    const int i = blockIdx.x, b = blockIdx.z;
 
+    // column tables: the same for every channel, built once per CTA; the CTA then walks over its channels
+    // (blockIdx.y, blockIdx.y + gridDim.y, ...) - one CTA per channel spent half its time on these tables
     for (int j = threadIdx.x; j < w; j += blockDim.x) {
-        acc[j] = 0.f;
         int xlo, xhi;
         if (sw <= 0.f) { xlo = 0; xhi = W - 1; }
         else {
@@ -142,6 +143,9 @@ bilinear_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int
     }
     int ylo, yhi;
     y_support(i, h, H, sh, ac, ylo, yhi);
+    for (int c = blockIdx.y; c < C; c += gridDim.y) {
+    __syncthreads();                                      // tables ready / previous channel written out
+    for (int j = threadIdx.x; j < w; j += blockDim.x) acc[j] = 0.f;
     const float* gp = gout + ((int64_t)b * C + c) * (int64_t)H * W;
     for (int y0g = ylo; y0g <= yhi; y0g += G) {
         const int rows = min(G, yhi - y0g + 1);
@@ -188,6 +192,7 @@ bilinear_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int
         if (NHWC) gin[((int64_t)(b * h + i) * w + j) * ldc + c] = acc[j];
         else gin[(((int64_t)b * C + c) * h + i) * w + j] = acc[j];
     }
+    }
 }
 
 extern "C" int pxl_bilinear_bwd(const float* grad_out, float* grad_in, int n, int C, int h, int w, int H, int W,
@@ -195,7 +200,11 @@ extern "C" int pxl_bilinear_bwd(const float* grad_out, float* grad_in, int n, in
     if (!grad_out || !grad_in || n <= 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return PXL_ERR_BAD_ARG;
     if (C > 65535 || n > 65535) return PXL_ERR_UNSUPPORTED;
     const float sh = resize_scale(h, H, align_corners), sw = resize_scale(w, W, align_corners);
-    dim3 grid((unsigned)h, (unsigned)C, (unsigned)n);
+    // channel groups: enough CTAs for ~8 per SM, each walking over C / groups channels with one set of column tables
+    int64_t cgroups = pxl_cdiv((int64_t)PXL_NUM_SMS * 8, (int64_t)h * n);
+    if (cgroups > C) cgroups = C;
+    if (cgroups < 1) cgroups = 1;
+    dim3 grid((unsigned)h, (unsigned)cgroups, (unsigned)n);
     cudaStream_t st = (cudaStream_t)stream;
     int R = sw > 0.f ? (int)(1.f / sw + 0.5f) : W;
     if (R < 1) R = 1;

@@ -53,10 +53,11 @@ class PeerExchange:
         if n > MAX_VALUES or sums.dtype != torch.float64 or not sums.is_cuda or not sums.is_contiguous():
             raise ValueError('peer exchange takes a contiguous CUDA fp64 vector of at most %d values' % MAX_VALUES)
         self.seq += 1
-        P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        from .. import ops
+        P = ops._p                              # plain ints / None: ~310 exchanges per step, keep the host side cheap
+        stream = ops._stream()
         if finalize is None:
-            z = ctypes.c_void_p(0)
+            z = None
             dg, db = (P(param_grads[0]), P(param_grads[1])) if param_grads is not None else (z, z)
             call('pxl_peer_allreduce_bn', P(sums), n, self._ptrs, self.rank, self.world, self.seq, 0.0, 0,
                  z, z, z, z, 0.0, 0.0, 0, z, z, z, z, dg, db, stream)
@@ -64,7 +65,7 @@ class PeerExchange:
             count, C, gamma, beta, rm, rv, momentum, eps, clamp, mean, invstd, scale, shift = finalize
             call('pxl_peer_allreduce_bn', P(sums), n, self._ptrs, self.rank, self.world, self.seq, float(count), int(C),
                  P(gamma), P(beta), P(rm), P(rv), float(momentum), float(eps), int(clamp), P(mean), P(invstd), P(scale),
-                 P(shift), ctypes.c_void_p(0), ctypes.c_void_p(0), stream)
+                 P(shift), None, None, stream)
         return sums
 
     def status(self):

@@ -1368,6 +1368,7 @@ class _ConvBnAct(torch.autograd.Function):
             # unit, whose dgrad epilogue adds into it (TMA reduce-add) - no elementwise add of the two branch gradients
             _residual_stash[stash_key] = dres
             dres = None
+        give_dx = stash_role == 'give_dx' and _residual_stash.get(stash_key) is None
         if ctx.needs_input_grad[0]:
             arena, off = _arena_of(weight) if BATCH_WEIGHT_PREP else (None, None)
             if arena is not None and arena._conv_at.get(off) == (Cout, T, Cin):
@@ -1376,6 +1377,8 @@ class _ConvBnAct(torch.autograd.Function):
             else:
                 wt = h16_split(transpose_weights(weight, Cout, T, Cin), H16_W_SCALE, want_lo)
             held = _residual_stash.pop(stash_key, None) if stash_role == 'take' else None
+            if stash_role == 'take' and held is None:
+                _residual_stash[stash_key] = 'taken'          # a 'give_dx' unit that runs later returns its dX itself
             if held is not None:
                 try:
                     dx = conv_raw(dh, wt, None, [-v for v in taps], N, OH, OW, Cout, H, W, Cin, Cin, 1, stride, out=held,
@@ -1389,6 +1392,11 @@ class _ConvBnAct(torch.autograd.Function):
                 dx = conv_raw(dh, wt, None, [-v for v in taps], N, OH, OW, Cout, H, W, Cin, Cin, 1, stride, precision=prec)
         elif stash_role == 'take':
             _residual_stash.pop(stash_key, None)
+        if give_dx and dx is not None:
+            # downsample unit of a bottleneck: the block input also feeds conv1, whose backward runs later (autograd
+            # executes later-created nodes first; conv1 waits for conv2's backward) and adds its dX into this buffer
+            _residual_stash[stash_key] = dx
+            dx = None
         if ctx.needs_input_grad[1]:
             inplace = ACCUM_WGRAD_INPLACE and weight.grad is not None and weight.grad.is_contiguous(memory_format=CL)
             dwbuf = weight.grad if inplace else torch.zeros_like(weight, memory_format=torch.preserve_format)

@@ -34,14 +34,18 @@ class Bottleneck(nn.Module):
             # fp16-pair tensor-core path: four fused conv+BN(+ReLU/residual) nodes; the inner activations only exist
             # as the fp16 pairs the next convolution reads
             # identity blocks: the residual gradient is added into the block-input gradient by conv1's dgrad epilogue
-            key = object() if (self.downsample is None and torch.is_grad_enabled() and x.requires_grad) else None
+            # blocks with a downsample branch: the downsample unit's dX is the buffer conv1's dgrad adds into
+            key = object() if (torch.is_grad_enabled() and x.requires_grad) else None
+            ident = self.downsample is None
             out = ops.conv_bn_act(x, self.conv1, self.bn1, relu=True, out_mode='pair', stash_key=key,
                                   stash_role='take' if key is not None else None)
             out = ops.conv_bn_act(out, self.conv2, self.bn2, relu=True, out_mode='pair')
-            residual = x if self.downsample is None else \
-                ops.conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False, out_mode='fp32')
-            return ops.conv_bn_act(out, self.conv3, self.bn3, relu=True, residual=residual, out_mode='both', stash_key=key,
-                                   stash_role='give' if key is not None else None)
+            residual = x if ident else \
+                ops.conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False, out_mode='fp32', stash_key=key,
+                                stash_role='give_dx' if key is not None else None)
+            return ops.conv_bn_act(out, self.conv3, self.bn3, relu=True, residual=residual, out_mode='both',
+                                   stash_key=key if ident else None,
+                                   stash_role='give' if (key is not None and ident) else None)
         out = self.bn1(self.conv1(x), relu=True)
         out = self.bn2(self.conv2(out), relu=True)
         out = self.conv3(out)
