@@ -378,7 +378,8 @@ def run_engine(args):
     tpath = os.path.join(ROOT, 'profiles', 'kernel_traffic.json')
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
-    kname = {'f16x3': 'conv_tc_persist_kernel, kind::f16 x3 (fp16 pairs)', 'f16': 'conv_tc_persist_kernel, kind::f16',
+    kname = {'f16x3': 'conv_tc_pair_kernel (cta_group::2, layers 3/4) + conv_tc_persist_kernel, kind::f16 x3 (fp16 pairs)',
+             'f16': 'conv_tc_pair_kernel + conv_tc_persist_kernel, kind::f16',
              'tf32x3': 'conv_tc_persist_kernel, kind::tf32 x3', 'tf32': 'conv_tc_kernel / conv_tc_persist_kernel, kind::tf32'}
     roof = _roofline_from(conv_rec, tf_peak, peak_src, 'forward/dgrad convolution: ' + kname.get(args.precision, ''),
                           traffic=traffic.get('conv_fwd_dram_bytes_per_launch'))

@@ -97,6 +97,9 @@ class _SSLBase:
         raise NotImplementedError
 
 
+_prefetch_state = {}
+
+
 def device_prefetch(data_loader):
     """Iterate ``data_loader`` one batch ahead: the host->HBM copy of batch k+1 (``Variable(i).cuda()`` of the
     reference's ``_batch_prehandle``, e.g. ssl_mt.py:337-357) is enqueued on a side stream before step k's kernels
@@ -111,9 +114,16 @@ def device_prefetch(data_loader):
         for batch in data_loader:
             yield batch
         return
-    copy_stream = torch.cuda.Stream()
-    slots = [{}, {}]                 # slot -> {(position, shape, dtype): device tensor}
-    done = [None, None]              # event on the main stream: the step that read this slot is enqueued
+    # the copy stream, the staging slots and their "consumed" events live as long as the process: a new side stream per
+    # epoch gets no cached blocks from torch's (per-stream) allocator pools, and the cudaMalloc of the 67 MB slots
+    # cost ~130 ms at the start of three epochs out of four (tools/e2e_probe2.py)
+    state = _prefetch_state.get(torch.cuda.current_device())
+    if state is None:
+        state = _prefetch_state[torch.cuda.current_device()] = {
+            'stream': torch.cuda.Stream(), 'slots': [{}, {}], 'done': [None, None]}
+    copy_stream = state['stream']
+    slots = state['slots']           # slot -> {(position, shape, dtype): device tensor}
+    done = state['done']             # event on the main stream: the step that read this slot is enqueued
 
     def stage(batch, k):
         inp, gt = batch
