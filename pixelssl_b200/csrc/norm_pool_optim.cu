@@ -2,6 +2,7 @@
 // All HBM-bound: every kernel moves 128-bit vectors along the channel dimension, one pass per
 // tensor, with per-channel reductions finished in fp64 atomics (tiny: 2*C doubles per layer).
 #include "common.cuh"
+#include <stdlib.h>
 #include <math_constants.h>
 #include <cuda_fp16.h>
 
@@ -243,8 +244,9 @@ extern "C" int pxl_bn_apply_h16(const float* x, const float* scale, const float*
 // from the fp64 sums) + apply.  The CTAs of row block 0 also store mean / inv_std / scale / shift for the backward
 // and update the running statistics.  Same 2-D decomposition as bn_bwd_dx_kernel.
 // ------------------------------------------------------------------------------------------
-template <bool RES, bool RELU>
-__global__ void __launch_bounds__(256)
+// BN_PRE: rows whose loads are issued before the per-channel prologue (0 or 2; registers: 4 CTAs of 256 threads per SM)
+template <bool RES, bool RELU, int BN_PRE>
+__global__ void __launch_bounds__(256, 4)
 bn_finalize_apply_kernel(const float4* __restrict__ x, const double* __restrict__ sums, double count, double inv_count,
                          const float* __restrict__ gamma, const float* __restrict__ beta,
                          float* running_mean, float* running_var, float momentum, float eps, int clamp_mode,
@@ -258,6 +260,21 @@ bn_finalize_apply_kernel(const float4* __restrict__ x, const double* __restrict_
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
     if (c4 >= c4max) return;
     bool clipped = false;
+    const int64_t r0 = (int64_t)blockIdx.x * rowsPerBlock;
+    const int64_t r1 = min(rows, r0 + rowsPerBlock);
+    // the first trip's loads go out BEFORE the per-channel prologue (fp64 finalize, 16 parameter loads): a 17 MB
+    // layer-3 tensor is one wave of CTAs, and the prologue's latency chain in front of the first load was a
+    // sizeable part of such a launch
+    float4 px[BN_PRE > 0 ? BN_PRE : 1], pq[BN_PRE > 0 ? BN_PRE : 1];
+#pragma unroll
+    for (int u = 0; u < BN_PRE; ++u) {
+        const int64_t r = r0 + ty + (int64_t)u * TY;
+        px[u] = make_float4(0.f, 0.f, 0.f, 0.f); pq[u] = px[u];
+        if (r < r1) {
+            px[u] = __ldcs(x + r * c4max + c4);
+            if (RES) pq[u] = __ldcs(res + r * c4max + c4);
+        }
+    }
     float sc[4], sh[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -282,21 +299,36 @@ bn_finalize_apply_kernel(const float4* __restrict__ x, const double* __restrict_
             mean[c] = mf; invstd[c] = is; scale[c] = sc[k]; shift[c] = sh[k];
         }
     }
-    const int64_t r0 = (int64_t)blockIdx.x * rowsPerBlock;
-    const int64_t r1 = min(rows, r0 + rowsPerBlock);
-#pragma unroll 4
-    for (int64_t r = r0 + ty; r < r1; r += TY) {
-        const int64_t i = r * c4max + c4;
-        float4 v = __ldcs(x + i);
+    auto emit = [&](int64_t i, float4 v, const float4& q) {
         v.x = fmaf(v.x, sc[0], sh[0]); v.y = fmaf(v.y, sc[1], sh[1]);
         v.z = fmaf(v.z, sc[2], sh[2]); v.w = fmaf(v.w, sc[3], sh[3]);
-        if (RES) { const float4 q = __ldcs(res + i); v = f4add(v, q); }
+        if (RES) v = f4add(v, q);
         if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         if (y) y[i] = v;
         if (hi) clipped |= h16_store4(v, hscale, hi, lo, i);
         if (mask) mask[i] = relu_mask4(v);
+    };
+#pragma unroll
+    for (int u = 0; u < BN_PRE; ++u) {
+        const int64_t r = r0 + ty + (int64_t)u * TY;
+        if (r < r1) emit(r * c4max + c4, px[u], pq[u]);
+    }
+#pragma unroll 4
+    for (int64_t r = r0 + ty + BN_PRE * (int64_t)TY; r < r1; r += TY) {
+        const int64_t i = r * c4max + c4;
+        const float4 v = __ldcs(x + i);
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (RES) q = __ldcs(res + i);
+        emit(i, v, q);
     }
     if (clipped && sat) atomicAdd(sat, 1);
+}
+
+// PXL_BN_PREFETCH (default 2; 0 = loads after the prologue): A/B switch of the first-trip prefetch
+static int bn_prefetch_rows() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PXL_BN_PREFETCH"); v = e ? atoi(e) : 2; }
+    return v;
 }
 
 static RedLayout stream_layout(int64_t rows, int C) {
@@ -348,10 +380,10 @@ extern "C" int pxl_bn_finalize_apply_h16(const float* x, const double* sums, dou
 #define PXL_FA_ARGS (const float4*)x, sums, count, 1.0 / count, gamma, beta, running_mean, running_var, momentum, eps, clamp_mode, mean, invstd, \
                     scale, shift, (const float4*)residual, (float4*)y, rows, C, L.TX, L.TY, L.rowsPerBlock, \
                     (uint2*)hi, (uint2*)lo, hscale, sat, (uint8_t*)relu_mask
-    if (residual && relu) pxl_launch_pdl(bn_finalize_apply_kernel<true, true>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS);
-    else if (residual) pxl_launch_pdl(bn_finalize_apply_kernel<true, false>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS);
-    else if (relu) pxl_launch_pdl(bn_finalize_apply_kernel<false, true>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS);
-    else pxl_launch_pdl(bn_finalize_apply_kernel<false, false>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS);
+    if (residual && relu) { if (bn_prefetch_rows()) pxl_launch_pdl(bn_finalize_apply_kernel<true, true, 2>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS); else pxl_launch_pdl(bn_finalize_apply_kernel<true, true, 0>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS); }
+    else if (residual) { if (bn_prefetch_rows()) pxl_launch_pdl(bn_finalize_apply_kernel<true, false, 2>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS); else pxl_launch_pdl(bn_finalize_apply_kernel<true, false, 0>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS); }
+    else if (relu) { if (bn_prefetch_rows()) pxl_launch_pdl(bn_finalize_apply_kernel<false, true, 2>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS); else pxl_launch_pdl(bn_finalize_apply_kernel<false, true, 0>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS); }
+    else { if (bn_prefetch_rows()) pxl_launch_pdl(bn_finalize_apply_kernel<false, false, 2>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS); else pxl_launch_pdl(bn_finalize_apply_kernel<false, false, 0>, dim3(grid), dim3(256), 0, st, PXL_FA_ARGS); }
 #undef PXL_FA_ARGS
     PXL_CHECK_LAUNCH();
     return 0;
@@ -450,8 +482,8 @@ extern "C" int pxl_bn_bwd_reduce_h16(const float* x, const float* y, const float
 // dx = A*dz + B*x + K per channel with A = gamma*invstd, B = -A*invstd*mean(dz*xhat), K = -A*mean(dz) - B*mean:
 // a thread owns 4 fixed channels (coefficients in registers, computed once from the fp64 sums) and walks down
 // the rows, 4 rows per trip.
-template <int RELU, bool DRES>
-__global__ void __launch_bounds__(256)
+template <int RELU, bool DRES, int BN_PRE>
+__global__ void __launch_bounds__(256, 4)
 bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, const float4* __restrict__ dy,
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                  const double* __restrict__ dsums, double inv_count, float4* __restrict__ dx, float4* __restrict__ dres,
@@ -463,6 +495,24 @@ bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, con
     PXL_PDL_SYNC();
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c4 = blockIdx.y * TX + tx, c4max = C >> 2;
+    const int64_t r0 = (int64_t)blockIdx.x * rowsPerBlock;
+    const int64_t r1 = min(rows, r0 + rowsPerBlock);
+    // first trip's loads before the prologue (scale reduction with a barrier, fp64 coefficient math), see
+    // bn_finalize_apply_kernel
+    float4 pd[BN_PRE > 0 ? BN_PRE : 1], pv[BN_PRE > 0 ? BN_PRE : 1], po[BN_PRE > 0 ? BN_PRE : 1];
+    unsigned pm[BN_PRE > 0 ? BN_PRE : 1];
+#pragma unroll
+    for (int u = 0; u < BN_PRE; ++u) {
+        const int64_t r = r0 + ty + (int64_t)u * TY;
+        pd[u] = make_float4(0.f, 0.f, 0.f, 0.f); pv[u] = pd[u]; po[u] = pd[u]; pm[u] = 0u;
+        if (c4 < c4max && r < r1) {
+            const int64_t i = r * c4max + c4;
+            pd[u] = __ldcs(dy + i);
+            pv[u] = __ldcs(x + i);
+            if (RELU == 1) po[u] = __ldcs(y + i);
+            if (RELU == 3) pm[u] = __ldg(mask + i);
+        }
+    }
     float hs = 1.f;
     if (dhi) {
         // fp16-pair scale of dx: |dx| <= max_c |gamma*invstd| * (absmax(dz) + |mean dz| + |xhat| |mean dz*xhat|); the
@@ -504,22 +554,15 @@ bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, con
     }
     float4 sc = make_float4(0, 0, 0, 0), sh = sc;
     if (RELU == 2) { sc = __ldg(reinterpret_cast<const float4*>(scale) + c4); sh = __ldg(reinterpret_cast<const float4*>(shift) + c4); }
-    const int64_t r0 = (int64_t)blockIdx.x * rowsPerBlock;
-    const int64_t r1 = min(rows, r0 + rowsPerBlock);
-#pragma unroll 4
-    for (int64_t r = r0 + ty; r < r1; r += TY) {
-        const int64_t i = r * c4max + c4;
-        float4 d = __ldcs(dy + i);
-        const float4 v = __ldcs(x + i);
+    auto emit = [&](int64_t i, float4 d, const float4& v, const float4& o, unsigned m) {
         if (RELU == 1) {
-            const float4 o = __ldcs(y + i);
             d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
             d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
         } else if (RELU == 2) {
             d.x = fmaf(v.x, sc.x, sh.x) > 0.f ? d.x : 0.f; d.y = fmaf(v.y, sc.y, sh.y) > 0.f ? d.y : 0.f;
             d.z = fmaf(v.z, sc.z, sh.z) > 0.f ? d.z : 0.f; d.w = fmaf(v.w, sc.w, sh.w) > 0.f ? d.w : 0.f;
         } else if (RELU == 3) {
-            apply_mask4(d, __ldg(mask + i));
+            apply_mask4(d, m);
         }
         if (DRES) dres[i] = d;
         float4 o4;
@@ -529,6 +572,22 @@ bn_bwd_dx_kernel(const float4* __restrict__ x, const float4* __restrict__ y, con
         o4.w = fmaf(A[3], d.w, fmaf(B[3], v.w, K[3]));
         if (dx) dx[i] = o4;
         if (dhi) clipped |= h16_store4(o4, hs, dhi, dlo, i);
+    };
+#pragma unroll
+    for (int u = 0; u < BN_PRE; ++u) {
+        const int64_t r = r0 + ty + (int64_t)u * TY;
+        if (r < r1) emit(r * c4max + c4, pd[u], pv[u], po[u], pm[u]);
+    }
+#pragma unroll 4
+    for (int64_t r = r0 + ty + BN_PRE * (int64_t)TY; r < r1; r += TY) {
+        const int64_t i = r * c4max + c4;
+        const float4 d = __ldcs(dy + i);
+        const float4 v = __ldcs(x + i);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned m = 0u;
+        if (RELU == 1) o = __ldcs(y + i);
+        if (RELU == 3) m = __ldg(mask + i);
+        emit(i, d, v, o, m);
     }
     if (clipped && sat) atomicAdd(sat, 1);
 }
@@ -568,14 +627,14 @@ extern "C" int pxl_bn_bwd_dx_h16(const float* x, const float* y, const float* dy
 #define PXL_DX_ARGS x4, y4, d4, mean, invstd, gamma, dsums, ic, o4, r4, rows, C, L.TX, L.TY, L.rowsPerBlock, scale, shift, \
                     (dgamma_acc && dbeta_acc) ? dgamma_acc : nullptr, dbeta_acc, (uint2*)dhi, (uint2*)dlo, slot, target_log2, sat, (const uint8_t*)relu_mask
     const int mode = relu ? (relu_mask ? 3 : (y ? 1 : 2)) : 0;
-    if (mode == 3 && dres) pxl_launch_pdl(bn_bwd_dx_kernel<3, true>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
-    else if (mode == 3) pxl_launch_pdl(bn_bwd_dx_kernel<3, false>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
-    else if (mode == 1 && dres) pxl_launch_pdl(bn_bwd_dx_kernel<1, true>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
-    else if (mode == 1) pxl_launch_pdl(bn_bwd_dx_kernel<1, false>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
-    else if (mode == 2 && dres) pxl_launch_pdl(bn_bwd_dx_kernel<2, true>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
-    else if (mode == 2) pxl_launch_pdl(bn_bwd_dx_kernel<2, false>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
-    else if (dres) pxl_launch_pdl(bn_bwd_dx_kernel<0, true>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
-    else pxl_launch_pdl(bn_bwd_dx_kernel<0, false>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS);
+    if (mode == 3 && dres) { if (bn_prefetch_rows()) pxl_launch_pdl(bn_bwd_dx_kernel<3, true, 2>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); else pxl_launch_pdl(bn_bwd_dx_kernel<3, true, 0>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); }
+    else if (mode == 3) { if (bn_prefetch_rows()) pxl_launch_pdl(bn_bwd_dx_kernel<3, false, 2>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); else pxl_launch_pdl(bn_bwd_dx_kernel<3, false, 0>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); }
+    else if (mode == 1 && dres) { if (bn_prefetch_rows()) pxl_launch_pdl(bn_bwd_dx_kernel<1, true, 2>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); else pxl_launch_pdl(bn_bwd_dx_kernel<1, true, 0>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); }
+    else if (mode == 1) { if (bn_prefetch_rows()) pxl_launch_pdl(bn_bwd_dx_kernel<1, false, 2>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); else pxl_launch_pdl(bn_bwd_dx_kernel<1, false, 0>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); }
+    else if (mode == 2 && dres) { if (bn_prefetch_rows()) pxl_launch_pdl(bn_bwd_dx_kernel<2, true, 2>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); else pxl_launch_pdl(bn_bwd_dx_kernel<2, true, 0>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); }
+    else if (mode == 2) { if (bn_prefetch_rows()) pxl_launch_pdl(bn_bwd_dx_kernel<2, false, 2>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); else pxl_launch_pdl(bn_bwd_dx_kernel<2, false, 0>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); }
+    else if (dres) { if (bn_prefetch_rows()) pxl_launch_pdl(bn_bwd_dx_kernel<0, true, 2>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); else pxl_launch_pdl(bn_bwd_dx_kernel<0, true, 0>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); }
+    else { if (bn_prefetch_rows()) pxl_launch_pdl(bn_bwd_dx_kernel<0, false, 2>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); else pxl_launch_pdl(bn_bwd_dx_kernel<0, false, 0>, dim3(grid), dim3(256), 0, st, PXL_DX_ARGS); }
 #undef PXL_DX_ARGS
     PXL_CHECK_LAUNCH();
     return 0;
