@@ -1440,7 +1440,15 @@ static int conv_tc_launch_core(const pxl_conv_geom* g, const int* taps, const px
     static int cfg_pair = -1;
     if (cfg_pair < 0) { const char* e = getenv("PXL_TC_PAIR"); cfg_pair = e ? atoi(e) : 2; }
     int use_pair = 0;
-    const bool pair_wanted = cfg_pair == 1 || (cfg_pair == 2 && f16 && g->Cout >= 256 && (int64_t)g->Cin * g->ntaps >= 256);
+    // auto rule, re-measured after the issue-loop rewrite (tools/bench_conv.py, PXL_TC_PAIR=0/1): pairs win when the
+    // reduction is long enough to amortise the cluster start-up (K >= 256) - except the 1x1 layers with K = 256 and a
+    // 4x wider output (layer3 conv3 / conv1-dgrad: epilogue-bound, 33.3 vs 36.9 us) - and also on 3x3 layers with only
+    // 128 output channels (layer2 conv2: 48 vs 57 us).  3 = the rule of the first half of round 2 (Cout >= 256).
+    const int64_t kred = (int64_t)g->Cin * g->ntaps;
+    const bool wide_1x1 = g->ntaps == 1 && kred < 512 && g->Cout >= 4 * g->Cin;
+    const bool pair_auto = f16 && kred >= 256 && !wide_1x1 && (g->Cout >= 256 || g->ntaps > 1);
+    const bool pair_wanted = cfg_pair == 1 || (cfg_pair == 2 && pair_auto) ||
+                             (cfg_pair == 3 && f16 && g->Cout >= 256 && kred >= 256);
     if (pair_wanted && cfg_persist && p.BN >= 128) {
         int bw, bh;
         pick_tile(p.OH, p.OW, flat, bw, bh);
