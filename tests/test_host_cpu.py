@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), 'missing export: ' + name
     # the ctypes table covers exactly the header
     assert set(_lib.SIGNATURES) == declared
-    assert _lib.load().pxl_abi_version() == 1
+    assert _lib.load().pxl_abi_version() == 2
 
 
 def test_ops_fail_loudly_without_cuda():
