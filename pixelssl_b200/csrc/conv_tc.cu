@@ -1,27 +1,32 @@
-// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a: forward / dgrad.
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a: forward / dgrad (wgrad at the end of the file).
 //
-//   D[128 output pixels, BN out channels] (fp32, in TMEM) += A[128, 32] * B[BN, 32]^T  per (tap, 32-channel chunk)
+//   D[128 output pixels, BN out channels] (fp32, in TMEM) += A[128, K] * B[BN, K]^T  per (tap, 128-byte channel chunk)
+//   K per chunk: 64 fp16 values (kind::f16, the benchmarked modes) or 32 tf32 values (kind::tf32)
 //
-// * A (activations, NHWC) is staged by TMA as a 4-D box {32 ch, BW, BH, 1}: one 128-byte row per
+// * A (activations, NHWC) is staged by TMA as a 4-D box {chunk, BW, BH, 1}: one 128-byte row per
 //   output pixel of a BH x BW spatial tile, shifted by the tap offset; out-of-image coordinates
 //   are zero-filled by the TMA unit, which IS the convolution's zero padding (im2col-free).
 //   1x1 convolutions use the same path with the pixel axis flattened (BW = 128, BH = 1).
-// * B (weights [Cout][tap][Cin], K-major) is a 2-D box {32, BN}.
-// * Both land in shared memory in the canonical K-major SWIZZLE_128B layout and feed
-//   tcgen05.mma.kind::tf32 (UMMA_K = 8 -> four MMAs per stage); accumulators live in TMEM and are
-//   read back with tcgen05.ld by four epilogue warps which add the bias and store NHWC rows.
-// * precision 1: single TF32 pass on the raw fp32 data.  precision 2 ("3xTF32"): operands are
-//   pre-split into hi = tf32(x), lo = x - hi; D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo recovers
-//   fp32-grade products with fp32 accumulation (error ~2^-21 per product).
-//   Weights are split once per step; activations arrive raw and are split in shared memory by the
-//   transform warps ("a_inkernel").
-// * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-//   warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4), warps 6..9 (persistent kernels) =
-//   operand transform.  mbarrier full/empty ring.
-// * three kernels share this scheme: conv_tc_kernel (one tile per CTA, up to two CTAs per SM),
-//   conv_tc_persist_kernel (default: one CTA per SM walks over tiles, accumulator double-buffered in
-//   TMEM, epilogue through a swizzled staging slab + TMA store, overlapped with the next tile) and
-//   conv_tc_pair_kernel (opt-in cta_group::2 variant).  The wgrad kernel is at the end of the file.
+// * B (weights [Cout][tap][Cin], K-major) is a 2-D box {chunk, BN}.
+// * Both land in shared memory in the canonical K-major SWIZZLE_128B layout and feed tcgen05.mma (four MMAs of
+//   32 bytes of K per operand pair and stage); accumulators live in TMEM (double-buffered in the persistent
+//   kernels) and are read back with tcgen05.ld by the epilogue warps.
+// * precision 3 ("f16x3", default of bench.py): both operands arrive as fp16 PAIRS x*s = hi + lo written by the
+//   producing kernels (csrc/h16_prep.cu), D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo recovers fp32-grade products with
+//   fp32 accumulation; the epilogue multiplies by the operands' inverse power-of-two scales.  precision 4 ("f16"):
+//   hi*hi only.  precision 1 / 2: kind::tf32 single pass / 3xTF32 (activations split in shared memory by the
+//   transform warps, "a_inkernel").
+// * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer - both run their loops with all 32 lanes
+//   converged and predicate the TMA / tcgen05 instructions with elect.sync (see elect_one) -, warps 2..9 = epilogue
+//   in two groups of four on alternate 32-column slabs (TMEM lane quarter = warp_idx % 4); in the 3xTF32 mode
+//   warps 6..9 are the operand transform instead.  mbarrier full/empty ring.
+// * epilogue: TMEM -> registers -> scale / bias -> 128B-swizzled staging slab -> TMA store (or TMA reduce-add when the
+//   launch accumulates into its output); BatchNorm statistics by a column walk over the staged slab, accumulated per
+//   CTA across tiles, combined across the four warps of a group, one fp64 atomic pair per channel and CTA.
+// * three kernels share this scheme: conv_tc_persist_kernel (one CTA per SM walks over tiles), conv_tc_pair_kernel
+//   (cta_group::2: a CTA pair computes 256 pixels x BN per step, each CTA stages half of the weight tile; selected per
+//   shape, see conv_tc_launch_core) and conv_tc_kernel (one tile per CTA, single-pass TF32 multi-tap layers only).
+// * launched with programmatic stream serialization: everything before PXL_PDL_SYNC() overlaps the previous kernel.
 //
 // Every mbarrier wait has a watchdog: on expiry the kernel raises a device-side flag and bails
 // out, so a protocol bug can never hang the GPU.
