@@ -28,6 +28,15 @@ def test_library_exports_every_declared_symbol():
     # the ctypes table covers exactly the header
     assert set(_lib.SIGNATURES) == declared
     assert _lib.load().pxl_abi_version() == 2
+    # ... with the same number of parameters per entry point (a pointer passed in the wrong slot is silent in ctypes)
+    text = re.sub(r'/\*.*?\*/', ' ', header, flags=re.S)
+    for name in sorted(declared):
+        m = re.search(r'\b' + name + r'\s*\(([^;{]*?)\)\s*;', text, flags=re.S)
+        assert m, 'declaration of %s not found' % name
+        params = m.group(1).strip()
+        n = 0 if params in ('', 'void') else params.count(',') + 1
+        assert n == len(_lib.SIGNATURES[name][1]), '%s: header declares %d parameters, _lib.SIGNATURES %d' % (
+            name, n, len(_lib.SIGNATURES[name][1]))
 
 
 def test_ops_fail_loudly_without_cuda():
